@@ -1,0 +1,146 @@
+/* libb2s — C ABI of the B200 (sm_100a) UNet segmentation hot path.
+ *
+ * The reference (WuJiaqiii/Thyroid-nodule-image-segmentation-UNet-DDTI) has no FFI of its own: its hot path is
+ * the set of torch.nn call sites in models/model.py, models/vnet.py, models/loss.py and utils/trainer.py. Each
+ * entry point below names the reference call site (file:line) whose arithmetic it replaces. The Python side
+ * (package models/model.py, models/loss.py) binds these with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise; caller owns all
+ *     buffers (outputs, saved tensors, workspaces); the library never allocates and never synchronises.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns immediately.
+ *   - activations are NHWC bf16; `*_cstride` is the pixel stride in ELEMENTS of the buffer the pointer lives
+ *     in (>= the channel count when the pointer addresses a channel slice of a wider concat buffer).
+ *   - return value: 0 = ok, negative = error (B2S_ERR_*); b2s_last_error() returns a thread-local message.
+ */
+#ifndef B2S_H_
+#define B2S_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_OK 0
+#define B2S_ERR_ARG (-1)
+#define B2S_ERR_CUDA (-2)
+
+#define B2S_FLAG_RELU 1   /* apply max(x,0) in the conv epilogue            (models/model.py:37,40) */
+#define B2S_FLAG_STATS 2  /* emit per-channel sum / sum-of-squares partials (BatchNorm2d, model.py:38,41) */
+
+const char* b2s_last_error(void);
+long long b2s_launch_count(void); /* kernels launched by this library in this process (bench.py gpu_launches) */
+int b2s_version(void);
+
+/* ---- tensor-core convolutions (tcgen05 + TMA + TMEM) ------------------------------------------------------ */
+
+/* nn.Conv2d(Cin,Cout,3,padding=1) / nn.Conv2d(Cin,Cout,1) forward (models/model.py:36,39; models/vnet.py:43,59)
+ * and, with rotated weights from b2s_pack_conv_weight, the 3x3 input gradient (autograd of the same call sites).
+ *   x [N,H,W,Cin] bf16, w_packed [ksize*ksize][Cout][Cin] bf16, bias [Cout] fp32 or NULL,
+ *   y [N,H,W,Cout] bf16, stats_partial [b2s_conv_fwd_tiles_m(N,H,W)][2][Cout] fp32 when B2S_FLAG_STATS.
+ *   tile_n: 0 = auto, else 64/128/256 (must divide Cout). Cin, Cout multiples of 64. */
+int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y, int y_cstride,
+                 float* stats_partial, int N, int H, int W, int Cin, int Cout, int ksize, int flags, int tile_n,
+                 void* stream);
+int b2s_conv_fwd_tiles_m(int N, int H, int W);
+
+/* nn.ConvTranspose2d(Cin,Cout,2,stride=2) forward (models/model.py:19,49): x [N,Hi,Wi,Cin] -> y [N,2Hi,2Wi,Cout];
+ * w_packed [(a*2+b)*Cout+co][Cin] bf16 (b2s_pack_convt_weight). */
+int b2s_convt2x2_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y, int y_cstride,
+                     int N, int Hi, int Wi, int Cin, int Cout, int tile_n, void* stream);
+/* its input gradient: dy [N,2Hi,2Wi,Cout] -> dx [N,Hi,Wi,Cin]; w_packed [(a*2+b)*Cin+ci][Cout] bf16. */
+int b2s_convt2x2_dgrad(const void* dy, int dy_cstride, const void* w_packed, void* dx, int dx_cstride, int N, int Hi,
+                       int Wi, int Cin, int Cout, int tile_n, void* stream);
+
+/* Weight gradients (autograd of the conv call sites): split-K fp32 partials ws[split][tap*Cin+ci][co], reduced and
+ * re-laid-out by b2s_wgrad_reduce. taps: 9 for the 3x3 conv (pass ksize_or_taps = 3), 4 for the transposed conv. */
+long long b2s_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ksize_or_taps, int tile_n, int splits,
+                                   int* splits_out);
+int b2s_conv3x3_wgrad(const void* x, int x_cstride, const void* dz, int dz_cstride, float* ws, int N, int H, int W,
+                      int Cin, int Cout, int tile_n, int splits, void* stream);
+int b2s_convt2x2_wgrad(const void* x, int x_cstride, const void* dy, int dy_cstride, float* ws, int N, int Hi, int Wi,
+                       int Cin, int Cout, int tile_n, int splits, void* stream);
+/* layout 0: dw[co][ci][tap] (Conv2d OIHW); layout 1: dw[ci][co][tap] (ConvTranspose2d IOHW). */
+int b2s_wgrad_reduce(const float* ws, int splits, int taps, int Cin, int Cout, float* dw, int layout, void* stream);
+
+/* ---- weight packing (fp32 parameters -> bf16 GEMM operands) ---------------------------------------------------- */
+/* w [Cout][Cin][k][k] fp32 -> w_fwd [k*k][Cout][Cin] bf16 and (optional) w_dgrad [k*k][Cin][Cout] bf16 with the
+ * taps reversed, so that the input gradient is a forward conv of dz with w_dgrad. */
+int b2s_pack_conv_weight(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int ksize, void* stream);
+/* w [Cin][Cout][2][2] fp32 -> w_fwd [(a*2+b)*Cout+co][Cin], w_dgrad [(a*2+b)*Cin+ci][Cout] (either may be NULL). */
+int b2s_pack_convt_weight(const float* w, void* w_fwd, void* w_dgrad, int Cin, int Cout, void* stream);
+
+/* ---- bandwidth kernels ------------------------------------------------------------------------------------------ */
+/* first layer nn.Conv2d(1,Cout,3,padding=1)+ReLU (models/model.py:10): x [N,H,W] fp32 -> r [N,H,W,Cout] bf16.
+ * stats_partial [b2s_c1_rows(N,H,W)][2][Cout]. Cout multiple of 8, <= 128. */
+int b2s_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, void* r, float* stats_partial, int N, int H,
+                       int W, int Cout, int flags, void* stream);
+int b2s_c1_rows(int N, int H, int W);
+/* its weight gradient: partial [b2s_c1_rows][Cout*9] fp32 (reduce with b2s_reduce_rows). */
+int b2s_conv3x3_c1_wgrad(const float* x, const void* dz, float* partial, int N, int H, int W, int Cout, void* stream);
+
+/* out[k] = sum_r in[r][k]; scratch >= 64*K floats (used when rows > 64). Deterministic. */
+int b2s_reduce_rows(const float* in, int rows, int K, float* scratch, float* out, void* stream);
+
+/* nn.BatchNorm2d training statistics (models/model.py:38,41): reduces conv-epilogue partials [rows][2][C] over
+ * count = N*H*W elements; writes mean, invstd, scale = gamma*invstd, shift = beta - mean*scale; updates
+ * running_mean/var with `momentum` (unbiased variance) and ++num_batches_tracked when the pointers are non-NULL. */
+int b2s_bn_finalize(const float* partial, int rows, int C, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                    float eps, float* scale, float* shift, float* mean, float* invstd, float* scratch, void* stream);
+/* eval mode: scale/shift from the running statistics. */
+int b2s_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, float* scale, float* shift, int C, void* stream);
+/* y = r*scale + shift (bf16 out, may be a concat slice); if pooled != NULL also F.max_pool2d(y, 2)
+ * (models/model.py:17,56-58) into the dense tensor pooled [N,H/2,W/2,C]. */
+int b2s_bn_apply(const void* r, int r_cstride, const float* scale, const float* shift, void* y, int y_cstride,
+                 void* pooled, int N, int H, int W, int C, void* stream);
+int b2s_ew_rows(void); /* partial rows written by the element-wise reduction kernels below */
+/* BatchNorm+ReLU backward, pass 1: partial [b2s_ew_rows][2][C] = sum dy, sum dy*xhat, where
+ * dy = dy_in (+ max-pool routed dpool when dpool != NULL; first maximum in row-major window order). */
+int b2s_bn_bwd_reduce(const void* dy, int dy_cstride, const void* dpool, const void* r, int r_cstride,
+                      const float* scale, const float* shift, const float* mean, const float* invstd, float* partial,
+                      int N, int H, int W, int C, void* stream);
+/* pass 1 finalize: dgamma, dbeta and coef [3][C] = {gamma*invstd, mean(dy), mean(dy*xhat)}. */
+int b2s_bn_bwd_finalize(const float* partial, int rows, int C, double count, const float* gamma, const float* invstd,
+                        float* dgamma, float* dbeta, float* coef, float* scratch, void* stream);
+/* pass 2: dz = (r>0) * coef0 * (dy - coef1 - xhat*coef2) (bf16) and conv-bias gradient partials [b2s_ew_rows][C]. */
+int b2s_bn_bwd_apply(const void* dy, int dy_cstride, const void* dpool, const void* r, int r_cstride,
+                     const float* scale, const float* shift, const float* mean, const float* invstd, const float* coef,
+                     void* dz, int dz_cstride, float* dbias_partial, int N, int H, int W, int C, void* stream);
+
+/* head: BatchNorm apply folded into nn.Conv2d(C,O,1) (models/model.py:30): logits [N,O,H,W] fp32 from r [N,H,W,C];
+ * mask (optional, uint8 [N,O,H,W]) = sigmoid(logit) > 0.5 evaluated in fp32 (utils/trainer.py:101,152,217). */
+int b2s_head_fwd(const void* r, int r_cstride, const float* scale, const float* shift, const float* w, const float* b,
+                 float* logits, unsigned char* mask, int N, long long HW, int C, int O, void* stream);
+/* head backward: dy [N,H,W,C] bf16 (gradient w.r.t. the BN output), partial [b2s_ew_rows][O*C+O] = dW, db. */
+int b2s_head_bwd(const float* dlogits, const void* r, int r_cstride, const float* scale, const float* shift,
+                 const float* w, void* dy, int dy_cstride, float* partial, int N, long long HW, int C, int O,
+                 void* stream);
+
+/* Dice + BCE (+ FocalTversky) loss (models/loss.py:13-24,34-46; nn.BCEWithLogitsLoss utils/trainer.py:37):
+ * sums [B][4] = {sum p*t, sum p, sum t, sum bce}; out [8] = {total, bce, dice, focal_tversky, TP, sum p, sum t, -};
+ * total = w_bce*bce + w_dice*dice + w_ft*ft; out+4 is the batch-global triple b2s_seg_loss_bwd takes as ft_tot. partial: [B][b2s_loss_chunks(per_sample)][4] scratch. */
+int b2s_loss_chunks(long long per_sample);
+int b2s_seg_loss_fwd(const float* logits, const float* targets, int B, long long per_sample, float* partial,
+                     float* sums, float* out, float dice_smooth, float w_bce, float w_dice, float w_ft, float ft_alpha,
+                     float ft_beta, float ft_gamma, float ft_smooth, void* stream);
+/* dlogits = grad_out * d total / d logits; grad_out: device scalar or NULL (= 1). ft_tot [3] = batch-global
+ * {TP, sum p, sum t} (all-reduced by the caller under data parallelism) or NULL to derive from sums. */
+int b2s_seg_loss_bwd(const float* logits, const float* targets, const float* sums, const float* ft_tot, int B,
+                     long long per_sample, long long bce_count, int dice_batch, const float* grad_out, float* dlogits,
+                     float dice_smooth, float w_bce, float w_dice, float w_ft, float ft_alpha, float ft_beta,
+                     float ft_gamma, float ft_smooth, void* stream);
+
+/* torch.optim.AdamW step (utils/trainer.py:41,92) over a flat fp32 parameter/gradient bucket;
+ * grad_scale multiplies g first (1/world_size after a sum all-reduce). step is 1-based. */
+int b2s_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+/* torch.cat along channels for API-visible concat (models/model.py:64-70): strided channel-slice copy. */
+int b2s_copy_channels(const void* src, int src_cstride, void* dst, int dst_cstride, long long npix, int C,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H_ */

@@ -1,0 +1,739 @@
+// Implicit-GEMM convolution kernels on tcgen05 tensor cores (sm_100a), TMA-fed, accumulators in TMEM.
+//
+//   conv_tc_kernel   : out[pix, n] = sum_tap sum_c A_tap[pix, c] * B[tap][n][c]   (K-major operands)
+//                      covers 3x3 conv forward, 3x3 conv dgrad (rotated weights), 1x1 conv,
+//                      ConvTranspose2d(k2,s2) forward (pixel-shuffle TMA store) and its dgrad.
+//                      Replaces torch.nn.Conv2d / ConvTranspose2d calls of reference models/model.py:36,39,49.
+//   wgrad_tc_kernel  : dW[(tap,ci), co] = sum_pix x[pix+tap, ci] * dz[pix, co]        (MN-major operands)
+//                      split-K over pixels, fp32 partials to a workspace, deterministic second-stage reduce.
+//
+// Warp roles (192 threads): warp0 = TMA producer (+TMEM alloc), warp1 = MMA issuer, warps2-5 = epilogue.
+#include "ptx.cuh"
+#include "b2s_internal.h"
+
+namespace b2s {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kNumThreads = 192;
+
+enum AMode : int { A_CONV3 = 0, A_1X1 = 1, A_CONVT_DGRAD = 2 };
+enum OutMode : int { OUT_4D = 0, OUT_CONVT_5D = 1 };
+
+struct ConvTcParams {
+  int bw, bh, bn;                  // pixel box of one M tile, bw*bh*bn == 128
+  int tiles_w, tiles_h, tiles_n;   // tiles over (W, H, N)
+  int W, H, N;                     // pixel space of the GEMM rows
+  int num_taps, k_chunks;          // K loop = taps x (Cin/64)
+  int a_mode, out_mode;
+  int n_total;                     // GEMM N (= Cout; 4*Cout for convT forward)
+  int cout_sub;                    // convT forward: Cout per (a,b) sub-position; else n_total
+  int tiles_nn;                    // n_total / BLOCK_N
+  int flags;                       // B2S_FLAG_*
+  const float* bias;               // [cout_sub] or nullptr
+  float* stats;                    // [tiles_m][2][n_total] partial column sums, or nullptr
+};
+
+template <int BLOCK_N, int STAGES>
+struct ConvSmem {
+  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kPipeBytes = STAGES * kStageBytes;
+  static constexpr int kBarOffset = kPipeBytes;                       // full[STAGES], empty[STAGES], tmem_full
+  static constexpr int kTmemPtrOffset = kBarOffset + (2 * STAGES + 1) * 8;
+  static constexpr int kStatsOffset = (kTmemPtrOffset + 4 + 15) / 16 * 16;  // [2 buf][4 warps][2][64] float
+  static constexpr int kTotal = kStatsOffset + 2 * 4 * 2 * 64 * 4;
+  static constexpr int kDynBytes = kTotal + 1024;  // slack for manual 1024-B alignment
+  static_assert((BLOCK_N / 64) * kATileBytes <= kPipeBytes, "epilogue staging must fit in the pipeline smem");
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmOut, const ConvTcParams p) {
+  using L = ConvSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * kATileBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOffset);
+  float* stats_smem = reinterpret_cast<float*>(smem + L::kStatsOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates -------------------------------------------------------------------
+  const int n_tile = blockIdx.x % p.tiles_nn;
+  const int m_tile = blockIdx.x / p.tiles_nn;
+  const int tw = m_tile % p.tiles_w;
+  const int th = (m_tile / p.tiles_w) % p.tiles_h;
+  const int tn = m_tile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+  const int ncol0 = n_tile * BLOCK_N;  // first GEMM column of this CTA
+
+  // ---- one-time setup -----------------------------------------------------------------------
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      tma_prefetch_desc(&tmOut);
+    }
+    tmem_alloc(tmem_ptr_smem, BLOCK_N);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_ptr_smem;
+
+  const int k_iters = p.num_taps * p.k_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        const int tap = it / p.k_chunks;
+        const int kc = it - tap * p.k_chunks;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+        uint8_t* a_dst = smem_a + stage * kATileBytes;
+        uint8_t* b_dst = smem_b + stage * L::kBTileBytes;
+        if (p.a_mode == A_CONV3) {
+          const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;
+          tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0 + dw, h0 + dh, n0);
+        } else if (p.a_mode == A_1X1) {
+          tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0, h0, n0);
+        } else {  // A_CONVT_DGRAD: dY viewed as (C, b, j, a, i*N)
+          const int a = tap >> 1, b = tap & 1;
+          tma_load_5d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, b, w0, a, n0 * p.H + h0);
+        }
+        // B rows: [tap][n_total] x Cin; the host encodes the box as (64, BLOCK_N)
+        tma_load_2d(&tmB, &full_bar[stage], b_dst, kc * kBlockK, tap * p.n_total + ncol0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (single thread) =====
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + stage * kATileBytes);
+        const uint32_t b_addr = smem_u32(smem_b + stage * L::kBTileBytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_acc, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> regs -> (+bias, ReLU) -> bf16 -> swizzled smem -> TMA store; BN partial sums =====
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;   // tile row == TMEM lane
+    const int ethread = row;         // 0..127 linear epilogue thread id (for stats write-out)
+    const int wl = row % p.bw;
+    const int hl = (row / p.bw) % p.bh;
+    const int nl = row / (p.bw * p.bh);
+    const bool valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
+    const bool do_relu = p.flags & B2S_FLAG_RELU;
+    const bool do_stats = (p.flags & B2S_FLAG_STATS) && p.stats != nullptr;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+
+#pragma unroll 1
+    for (int s = 0; s < BLOCK_N / 64; ++s) {
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + s * 64;
+      tmem_ld_32x32(taddr, v0);
+      tmem_ld_32x32(taddr + 32, v1);
+      tmem_ld_wait();
+
+      uint8_t* stage_buf = smem + s * kATileBytes;  // pipeline smem is idle now
+      const int col_base = ncol0 + s * 64;           // GEMM column of v0[0]
+      const int bias_base = col_base % p.cout_sub;
+      uint32_t packed[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float a = __uint_as_float(j < 16 ? v0[2 * j] : v1[2 * j - 32]);
+        float b = __uint_as_float(j < 16 ? v0[2 * j + 1] : v1[2 * j - 31]);
+        if (p.bias != nullptr) {
+          a += __ldg(p.bias + bias_base + 2 * j);
+          b += __ldg(p.bias + bias_base + 2 * j + 1);
+        }
+        if (do_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        if (!valid) { a = 0.f; b = 0.f; }
+        packed[j] = pack_bf16x2(a, b);
+      }
+      // 128-B row, 16-B chunk c stored at chunk (c ^ (row & 7)): the SWIZZLE_128B pattern of tmOut
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+        *reinterpret_cast<uint4*>(stage_buf + row * 128 + ((c ^ (row & 7)) << 4)) = val;
+      }
+      if (do_stats) {
+        // column sums over this warp's own 32 rows, taken from the bf16-rounded values actually stored
+        __syncwarp();
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        const int chunk = lane >> 2, within = (lane & 3) * 4;  // lane <-> column pair (2*lane, 2*lane+1)
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int rr = q * 32 + r;
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
+          const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+          s0 += x0; s1 += x1;
+          q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+        }
+        float* sb = stats_smem + (s & 1) * (4 * 2 * 64) + q * (2 * 64);
+        sb[2 * lane] = s0; sb[2 * lane + 1] = s1;
+        sb[64 + 2 * lane] = q0; sb[64 + 2 * lane + 1] = q1;
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ethread == 0) {
+        if (p.out_mode == OUT_4D) {
+          tma_store_4d(&tmOut, stage_buf, col_base, w0, h0, n0);
+        } else {  // convT forward: column block belongs to one (a,b) sub-position
+          const int ab = col_base / p.cout_sub;
+          tma_store_5d(&tmOut, stage_buf, col_base - ab * p.cout_sub, ab & 1, w0, ab >> 1, n0 * p.H + h0);
+        }
+        tma_store_commit();
+      }
+      if (do_stats) {
+        const float* sb = stats_smem + (s & 1) * (4 * 2 * 64);
+        // 128 threads: thread e -> (which = e/64, column = e%64)
+        const int which = ethread >> 6, col = ethread & 63;
+        float acc = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) acc += sb[wq * 128 + which * 64 + col];
+        p.stats[(static_cast<size_t>(m_tile) * 2 + which) * p.n_total + col_base + col] = acc;
+      }
+    }
+    if (ethread == 0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BLOCK_N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: D[(tap,ci), co] = sum_pix A[pix, (tap,ci)] * B[pix, co], both operands MN-major in smem
+// ------------------------------------------------------------------------------------------------
+enum WgMode : int { WG_CONV3 = 0, WG_CONVT = 1 };
+
+struct WgradParams {
+  int pw, ph, pn;                 // pixel box of one K chunk, pw*ph*pn == 64
+  int chunks_w, chunks_h, chunks_n;
+  int H;                          // rows per image (5D merged coordinate)
+  int num_taps, ci_blocks;        // row space = num_taps x (Cin/64) blocks of 64 rows
+  int total_rb;                   // num_taps * ci_blocks
+  int cin, cout;
+  int tiles_nn;                   // cout / BLOCK_N
+  int m_tiles;                    // ceil(total_rb / 2)
+  int splits, chunks_total, chunks_per_split;
+  int mode;
+  float* ws;                      // [splits][num_taps*cin][cout] fp32
+};
+
+template <int BLOCK_N, int STAGES>
+struct WgSmem {
+  static constexpr int kABytes = 2 * 64 * 128;            // two (64 px x 64 ch) boxes
+  static constexpr int kBBytes = (BLOCK_N / 64) * 64 * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kPipeBytes = STAGES * kStageBytes;
+  static constexpr int kBarOffset = kPipeBytes;
+  static constexpr int kTmemPtrOffset = kBarOffset + (2 * STAGES + 1) * 8;
+  static constexpr int kTotal = kTmemPtrOffset + 16;
+  static constexpr int kDynBytes = kTotal + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const WgradParams p) {
+  using L = WgSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * L::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_tile = blockIdx.x % p.tiles_nn;
+  const int m_tile = (blockIdx.x / p.tiles_nn) % p.m_tiles;
+  const int split = blockIdx.x / (p.tiles_nn * p.m_tiles);
+  const int chunk_begin = split * p.chunks_per_split;
+  const int chunk_end = min(chunk_begin + p.chunks_per_split, p.chunks_total);
+  const int k_iters = max(chunk_end - chunk_begin, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+    tmem_alloc(tmem_ptr_smem, BLOCK_N);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // row blocks (tap, ci block of 64) of this tile; a padding block re-loads the last valid one
+      int tap_j[2], cib_j[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        int rb = min(m_tile * 2 + j, p.total_rb - 1);
+        tap_j[j] = rb / p.ci_blocks;
+        cib_j[j] = rb - tap_j[j] * p.ci_blocks;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        const int chunk = chunk_begin + it;
+        const int cw = chunk % p.chunks_w;
+        const int chh = (chunk / p.chunks_w) % p.chunks_h;
+        const int cn = chunk / (p.chunks_w * p.chunks_h);
+        const int w0 = cw * p.pw, h0 = chh * p.ph, n0 = cn * p.pn;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+        uint8_t* a_dst = smem_a + stage * L::kABytes;
+        uint8_t* b_dst = smem_b + stage * L::kBBytes;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          int dh = 0, dw = 0;
+          if (p.mode == WG_CONV3) { dh = tap_j[j] / 3 - 1; dw = tap_j[j] % 3 - 1; }
+          tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 8192, cib_j[j] * 64, w0 + dw, h0 + dh, n0);
+        }
+        if (p.mode == WG_CONV3) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_4d(&tmB, &full_bar[stage], b_dst + j * 8192, n_tile * BLOCK_N + j * 64, w0, h0, n0);
+        } else {
+          // convT: both row blocks of a tile share one tap only if ci_blocks is even (host guarantees it)
+          const int a = tap_j[0] >> 1, b = tap_j[0] & 1;
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_5d(&tmB, &full_bar[stage], b_dst + j * 8192, n_tile * BLOCK_N + j * 64, b, w0, a,
+                        n0 * p.H + h0);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && k_iters > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + stage * L::kABytes);
+        const uint32_t b_addr = smem_u32(smem_b + stage * L::kBBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 16 pixels (K rows of 128 B) per MMA
+          const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, 8192, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
+          umma_bf16(tmem_acc, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rb = m_tile * 2 + (row >> 6);
+    const bool valid = rb < p.total_rb;
+    const size_t grow = static_cast<size_t>(rb) * 64 + (row & 63);  // row in (tap, ci) space
+    float* dst = p.ws + (static_cast<size_t>(split) * p.num_taps * p.cin + grow) * p.cout + n_tile * BLOCK_N;
+    if (k_iters > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int s = 0; s < BLOCK_N / 32; ++s) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + s * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(dst + s * 32 + c * 4) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+      }
+    } else if (valid) {
+      for (int c = 0; c < BLOCK_N / 4; ++c) *reinterpret_cast<uint4*>(dst + c * 4) = make_uint4(0, 0, 0, 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BLOCK_N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// bf16 tensor map, SWIZZLE_128B, inner box = 64 elements. dims/strides innermost first; strides in BYTES for
+// dims 1..rank-1.
+static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                     const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(B2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_b[i];
+  if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(B2S_ERR_ARG, "tensor base not 16-B aligned");
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gstr[i] & 15) return set_error(B2S_ERR_ARG, "tensor stride not a multiple of 16 B");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[256];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu %llu box %u %u %u %u)",
+             (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1],
+             (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0), bdim[0],
+             bdim[1], rank > 2 ? bdim[2] : 0, rank > 3 ? bdim[3] : 0);
+    return set_error(B2S_ERR_CUDA, msg);
+  }
+  return B2S_OK;
+}
+
+static int pow2_ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
+
+// Split `total` (power of two) pixels of one tile over (w, h, n).
+static void pick_box(int W, int H, int N, int total, int* bw, int* bh, int* bn) {
+  int w = pow2_ceil(W); if (w > total) w = total;
+  int h = pow2_ceil(H); if (h > total / w) h = total / w;
+  int n = total / (w * h);
+  (void)N;
+  *bw = w; *bh = h; *bn = n;
+}
+
+// NHWC activation map (C, W, H, N) over a channel slice of a buffer whose pixel stride is cstride elements.
+static int make_act_map4(CUtensorMap* m, const void* base, int C, int W, int H, int N, int cstride, int bw, int bh,
+                         int bn) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)cstride * 2, (uint64_t)W * cstride * 2, (uint64_t)H * W * cstride * 2};
+  uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  return make_tmap(m, base, 4, dims, str, box);
+}
+// 2x-upsampled NHWC tensor [N, 2Hi, 2Wi, C] viewed as (C, b, j, a, i*N) so that one (a,b) sub-lattice is a box.
+static int make_up_map5(CUtensorMap* m, const void* base, int C, int Wi, int Hi, int N, int cstride, int bw,
+                        int bhn) {
+  const uint64_t Wo = 2ull * Wi;
+  uint64_t dims[5] = {(uint64_t)C, 2, (uint64_t)Wi, 2, (uint64_t)Hi * N};
+  uint64_t str[4] = {(uint64_t)cstride * 2, 2ull * cstride * 2, Wo * cstride * 2, 2ull * Wo * cstride * 2};
+  uint32_t box[5] = {64, 1, (uint32_t)bw, 1, (uint32_t)bhn};
+  return make_tmap(m, base, 5, dims, str, box);
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                       const ConvTcParams& p, int grid, cudaStream_t stream) {
+  using L = ConvSmem<BLOCK_N, STAGES>;
+  auto kfn = conv_tc_kernel<BLOCK_N, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
+    attr_set = true;
+  }
+  kfn<<<grid, kNumThreads, L::kDynBytes, stream>>>(tmA, tmB, tmOut, p);
+  return check_launch("conv_tc_kernel");
+}
+
+static int dispatch_conv(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                         const ConvTcParams& p, int grid, cudaStream_t stream) {
+  count_launch();
+  switch (block_n) {
+    case 64:  return launch_conv<64, 4>(tmA, tmB, tmOut, p, grid, stream);    // 4 x 24 KB
+    case 128: return launch_conv<128, 3>(tmA, tmB, tmOut, p, grid, stream);   // 3 x 32 KB -> 2 CTAs / SM
+    case 256: return launch_conv<256, 4>(tmA, tmB, tmOut, p, grid, stream);   // 4 x 48 KB -> 1 CTA / SM
+    default:  return set_error(B2S_ERR_ARG, "unsupported tile_n");
+  }
+}
+
+static int auto_block_n(int n_total, int cout_sub, int tile_n) {
+  if (tile_n == 0) tile_n = (cout_sub >= 128) ? 128 : 64;
+  if (tile_n > cout_sub) tile_n = cout_sub;
+  return tile_n;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+// Generic tap-GEMM conv. ksize 3 (pad 1) or 1. See include/b2s.h.
+extern "C" int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y,
+                            int y_cstride, float* stats_partial, int N, int H, int W, int Cin, int Cout, int ksize,
+                            int flags, int tile_n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !w_packed || !y) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: null pointer");
+  if (ksize != 3 && ksize != 1) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: ksize must be 1 or 3");
+  if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: Cin and Cout must be multiples of 64");
+  if (N <= 0 || H <= 0 || W <= 0) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: empty tensor");
+  if ((flags & B2S_FLAG_STATS) && !stats_partial) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: stats buffer missing");
+  const int block_n = auto_block_n(Cout, Cout, tile_n);
+  if (Cout % block_n) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: tile_n must divide Cout");
+
+  ConvTcParams p{};
+  pick_box(W, H, N, kBlockM, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.W = W; p.H = H; p.N = N;
+  p.num_taps = ksize * ksize; p.k_chunks = Cin / 64;
+  p.a_mode = ksize == 3 ? A_CONV3 : A_1X1; p.out_mode = OUT_4D;
+  p.n_total = Cout; p.cout_sub = Cout; p.tiles_nn = Cout / block_n;
+  p.flags = flags; p.bias = bias; p.stats = stats_partial;
+
+  CUtensorMap tmA, tmB, tmOut;
+  int rc;
+  if ((rc = make_act_map4(&tmA, x, Cin, W, H, N, x_cstride, p.bw, p.bh, p.bn))) return rc;
+  {
+    uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)p.num_taps * Cout};
+    uint64_t str[1] = {(uint64_t)Cin * 2};
+    uint32_t box[2] = {64, (uint32_t)block_n};
+    if ((rc = make_tmap(&tmB, w_packed, 2, dims, str, box))) return rc;
+  }
+  if ((rc = make_act_map4(&tmOut, y, Cout, W, H, N, y_cstride, p.bw, p.bh, p.bn))) return rc;
+  const int grid = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nn;
+  return dispatch_conv(block_n, tmA, tmB, tmOut, p, grid, stream);
+}
+
+extern "C" int b2s_conv_fwd_tiles_m(int N, int H, int W) {
+  int bw, bh, bn;
+  pick_box(W, H, N, kBlockM, &bw, &bh, &bn);
+  return ((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((N + bn - 1) / bn);
+}
+
+// ConvTranspose2d(k=2,s=2) forward: x [N,Hi,Wi,Cin] -> y [N,2Hi,2Wi,Cout]; w_packed [(a*2+b)*Cout+co][Cin].
+extern "C" int b2s_convt2x2_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y,
+                                int y_cstride, int N, int Hi, int Wi, int Cin, int Cout, int tile_n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !w_packed || !y) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: null pointer");
+  if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: channels must be multiples of 64");
+  const int block_n = auto_block_n(4 * Cout, Cout, tile_n);
+  if (Cout % block_n) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: tile_n must divide Cout");
+  ConvTcParams p{};
+  pick_box(Wi, Hi, N, kBlockM, &p.bw, &p.bh, &p.bn);
+  if (p.bn > 1 && p.bh != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: unsupported tiny non-pow2 image");
+  p.tiles_w = (Wi + p.bw - 1) / p.bw; p.tiles_h = (Hi + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.W = Wi; p.H = Hi; p.N = N;
+  p.num_taps = 1; p.k_chunks = Cin / 64;
+  p.a_mode = A_1X1; p.out_mode = OUT_CONVT_5D;
+  p.n_total = 4 * Cout; p.cout_sub = Cout; p.tiles_nn = 4 * Cout / block_n;
+  p.flags = 0; p.bias = bias; p.stats = nullptr;
+  CUtensorMap tmA, tmB, tmOut;
+  int rc;
+  if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hi, N, x_cstride, p.bw, p.bh, p.bn))) return rc;
+  {
+    uint64_t dims[2] = {(uint64_t)Cin, 4ull * Cout};
+    uint64_t str[1] = {(uint64_t)Cin * 2};
+    uint32_t box[2] = {64, (uint32_t)block_n};
+    if ((rc = make_tmap(&tmB, w_packed, 2, dims, str, box))) return rc;
+  }
+  if ((rc = make_up_map5(&tmOut, y, Cout, Wi, Hi, N, y_cstride, p.bw, p.bh * p.bn))) return rc;
+  const int grid = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nn;
+  return dispatch_conv(block_n, tmA, tmB, tmOut, p, grid, stream);
+}
+
+// ConvTranspose2d(k=2,s=2) input gradient: dy [N,2Hi,2Wi,Cout] -> dx [N,Hi,Wi,Cin]; w_packed [(a*2+b)*Cin+ci][Cout].
+extern "C" int b2s_convt2x2_dgrad(const void* dy, int dy_cstride, const void* w_packed, void* dx, int dx_cstride,
+                                  int N, int Hi, int Wi, int Cin, int Cout, int tile_n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!dy || !w_packed || !dx) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: null pointer");
+  if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: channels must be multiples of 64");
+  const int block_n = auto_block_n(Cin, Cin, tile_n);
+  if (Cin % block_n) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: tile_n must divide Cin");
+  ConvTcParams p{};
+  pick_box(Wi, Hi, N, kBlockM, &p.bw, &p.bh, &p.bn);
+  if (p.bn > 1 && p.bh != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: unsupported tiny non-pow2 image");
+  p.tiles_w = (Wi + p.bw - 1) / p.bw; p.tiles_h = (Hi + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.W = Wi; p.H = Hi; p.N = N;
+  p.num_taps = 4; p.k_chunks = Cout / 64;
+  p.a_mode = A_CONVT_DGRAD; p.out_mode = OUT_4D;
+  p.n_total = Cin; p.cout_sub = Cin; p.tiles_nn = Cin / block_n;
+  p.flags = 0; p.bias = nullptr; p.stats = nullptr;
+  CUtensorMap tmA, tmB, tmOut;
+  int rc;
+  if ((rc = make_up_map5(&tmA, dy, Cout, Wi, Hi, N, dy_cstride, p.bw, p.bh * p.bn))) return rc;
+  {
+    uint64_t dims[2] = {(uint64_t)Cout, 4ull * Cin};
+    uint64_t str[1] = {(uint64_t)Cout * 2};
+    uint32_t box[2] = {64, (uint32_t)block_n};
+    if ((rc = make_tmap(&tmB, w_packed, 2, dims, str, box))) return rc;
+  }
+  if ((rc = make_act_map4(&tmOut, dx, Cin, Wi, Hi, N, dx_cstride, p.bw, p.bh, p.bn))) return rc;
+  const int grid = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nn;
+  return dispatch_conv(block_n, tmA, tmB, tmOut, p, grid, stream);
+}
+
+// ---- wgrad -----------------------------------------------------------------------------------
+namespace b2s {
+template <int BLOCK_N, int STAGES>
+static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, int grid,
+                        cudaStream_t stream) {
+  using L = WgSmem<BLOCK_N, STAGES>;
+  auto kfn = wgrad_tc_kernel<BLOCK_N, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(wgrad_tc_kernel)");
+    attr_set = true;
+  }
+  kfn<<<grid, kNumThreads, L::kDynBytes, stream>>>(tmA, tmB, p);
+  return check_launch("wgrad_tc_kernel");
+}
+
+static int wgrad_plan(int N, int H, int W, int Cin, int Cout, int num_taps, int tile_n, int splits_req,
+                      WgradParams* p, int* block_n_out) {
+  int block_n = tile_n ? tile_n : (Cout >= 256 ? 256 : Cout);
+  if (block_n > Cout) block_n = Cout;
+  if (Cout % block_n || (block_n != 64 && block_n != 128 && block_n != 256)) return -1;
+  pick_box(W, H, N, 64, &p->pw, &p->ph, &p->pn);
+  p->chunks_w = (W + p->pw - 1) / p->pw; p->chunks_h = (H + p->ph - 1) / p->ph; p->chunks_n = (N + p->pn - 1) / p->pn;
+  p->H = H;
+  p->num_taps = num_taps; p->ci_blocks = Cin / 64; p->total_rb = num_taps * p->ci_blocks;
+  p->cin = Cin; p->cout = Cout; p->tiles_nn = Cout / block_n; p->m_tiles = (p->total_rb + 1) / 2;
+  p->chunks_total = p->chunks_w * p->chunks_h * p->chunks_n;
+  int splits = splits_req;
+  if (splits <= 0) {
+    // fill ~2 CTAs per SM for 2 waves, keep >= 16 K-chunks per CTA
+    const int base = p->m_tiles * p->tiles_nn;
+    splits = (4 * 148 + base - 1) / base;
+    const int max_by_work = p->chunks_total / 16 > 0 ? p->chunks_total / 16 : 1;
+    if (splits > max_by_work) splits = max_by_work;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p->chunks_total) splits = p->chunks_total;
+  p->chunks_per_split = (p->chunks_total + splits - 1) / splits;
+  p->splits = (p->chunks_total + p->chunks_per_split - 1) / p->chunks_per_split;
+  *block_n_out = block_n;
+  return 0;
+}
+}  // namespace b2s
+
+// Workspace query: bytes needed and the number of K splits that b2s_conv_wgrad will use.
+extern "C" long long b2s_conv_wgrad_workspace(int N, int H, int W, int Cin, int Cout, int ksize_or_taps, int tile_n,
+                                              int splits, int* splits_out) {
+  WgradParams p{};
+  int block_n;
+  const int taps = ksize_or_taps == 3 ? 9 : ksize_or_taps;
+  if (Cin % 64 || Cout % 64 || wgrad_plan(N, H, W, Cin, Cout, taps, tile_n, splits, &p, &block_n)) {
+    set_error(B2S_ERR_ARG, "b2s_conv_wgrad_workspace: unsupported shape");
+    return -1;
+  }
+  if (splits_out) *splits_out = p.splits;
+  return static_cast<long long>(p.splits) * taps * Cin * Cout * 4;
+}
+
+// 3x3 conv weight gradient partials: ws[split][tap*Cin+ci][co] = sum over the split's pixels.
+extern "C" int b2s_conv3x3_wgrad(const void* x, int x_cstride, const void* dz, int dz_cstride, float* ws, int N, int H,
+                                 int W, int Cin, int Cout, int tile_n, int splits, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !dz || !ws) return set_error(B2S_ERR_ARG, "b2s_conv3x3_wgrad: null pointer");
+  if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_conv3x3_wgrad: channels must be multiples of 64");
+  WgradParams p{};
+  int block_n;
+  if (wgrad_plan(N, H, W, Cin, Cout, 9, tile_n, splits, &p, &block_n))
+    return set_error(B2S_ERR_ARG, "b2s_conv3x3_wgrad: bad tile_n");
+  p.mode = WG_CONV3; p.ws = ws;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_act_map4(&tmA, x, Cin, W, H, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
+  if ((rc = make_act_map4(&tmB, dz, Cout, W, H, N, dz_cstride, p.pw, p.ph, p.pn))) return rc;
+  const int grid = p.m_tiles * p.tiles_nn * p.splits;
+  count_launch();
+  switch (block_n) {
+    case 64:  return launch_wgrad<64, 6>(tmA, tmB, p, grid, stream);    // 6 x 24 KB
+    case 128: return launch_wgrad<128, 3>(tmA, tmB, p, grid, stream);   // 3 x 32 KB
+    case 256: return launch_wgrad<256, 4>(tmA, tmB, p, grid, stream);   // 4 x 48 KB
+  }
+  return set_error(B2S_ERR_ARG, "b2s_conv3x3_wgrad: unsupported tile_n");
+}
+
+// ConvTranspose2d(k2,s2) weight gradient partials: ws[split][(a*2+b)*Cin+ci][co]; x [N,Hi,Wi,Cin], dy [N,2Hi,2Wi,Cout].
+extern "C" int b2s_convt2x2_wgrad(const void* x, int x_cstride, const void* dy, int dy_cstride, float* ws, int N,
+                                  int Hi, int Wi, int Cin, int Cout, int tile_n, int splits, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !dy || !ws) return set_error(B2S_ERR_ARG, "b2s_convt2x2_wgrad: null pointer");
+  if (Cin % 128 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_convt2x2_wgrad: need Cin % 128 == 0, Cout % 64 == 0");
+  WgradParams p{};
+  int block_n;
+  if (wgrad_plan(N, Hi, Wi, Cin, Cout, 4, tile_n, splits, &p, &block_n))
+    return set_error(B2S_ERR_ARG, "b2s_convt2x2_wgrad: bad tile_n");
+  if (p.pn > 1 && p.ph != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_wgrad: unsupported tiny non-pow2 image");
+  p.mode = WG_CONVT; p.ws = ws;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hi, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
+  if ((rc = make_up_map5(&tmB, dy, Cout, Wi, Hi, N, dy_cstride, p.pw, p.ph * p.pn))) return rc;
+  const int grid = p.m_tiles * p.tiles_nn * p.splits;
+  count_launch();
+  switch (block_n) {
+    case 64:  return launch_wgrad<64, 6>(tmA, tmB, p, grid, stream);
+    case 128: return launch_wgrad<128, 3>(tmA, tmB, p, grid, stream);
+    case 256: return launch_wgrad<256, 4>(tmA, tmB, p, grid, stream);
+  }
+  return set_error(B2S_ERR_ARG, "b2s_convt2x2_wgrad: unsupported tile_n");
+}

@@ -1,0 +1,1053 @@
+// Bandwidth-bound kernels of the UNet hot path (sm_100a): first conv (Cin=1), BatchNorm finalize / apply /
+// backward, 2x2 max-pool (fused into BN apply and BN backward), 1x1 head + threshold, Dice+BCE(+FocalTversky)
+// loss and gradient, weight packing, wgrad second-stage reduce, AdamW. All activations NHWC bf16, 16-byte
+// vectorised (8 channels per thread), grids sized in multiples of the SM count.
+#include "ptx.cuh"
+#include "b2s_internal.h"
+
+namespace b2s {
+
+constexpr int kThreads = 256;
+constexpr int kSMs = 148;
+constexpr int kEwBlocks = kSMs * 4;  // rows of every element-wise partial buffer
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// ------------------------------------------------------------------------------------------------
+// generic deterministic row reduction: out[k] = sum_r in[r][k]
+// ------------------------------------------------------------------------------------------------
+__global__ void reduce_rows_kernel(const float* __restrict__ in, int rows, int K, int rows_per_slice,
+                                   float* __restrict__ out) {
+  // grid (ceil(K/32), slices); block (32, 8)
+  __shared__ double red[8][33];
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_slice;
+  const int r1 = min(r0 + rows_per_slice, rows);
+  double acc = 0.0;
+  if (k < K)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += static_cast<double>(in[static_cast<size_t>(r) * K + k]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < K) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+    out[static_cast<size_t>(blockIdx.y) * K + k] = static_cast<float>(s);
+  }
+}
+
+// Reduce [rows][K] down to at most 64 rows (in scratch) when rows > 64; returns pointer/rows to finalize from.
+static int reduce_to_small(const float* in, int rows, int K, float* scratch, const float** out_ptr, int* out_rows,
+                           cudaStream_t stream) {
+  if (rows <= 64) { *out_ptr = in; *out_rows = rows; return B2S_OK; }
+  if (!scratch) return set_error(B2S_ERR_ARG, "scratch buffer required for rows > 64");
+  const int slices = 64;
+  const int rps = (rows + slices - 1) / slices;
+  const int used = (rows + rps - 1) / rps;
+  dim3 grid((K + 31) / 32, used), block(32, 8);
+  count_launch();
+  reduce_rows_kernel<<<grid, block, 0, stream>>>(in, rows, K, rps, scratch);
+  int rc = check_launch("reduce_rows_kernel");
+  *out_ptr = scratch; *out_rows = used;
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// first conv: Cin = 1
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      __nv_bfloat16* __restrict__ r, float* __restrict__ stats_partial, int N, int H, int W, int Cout,
+                      int flags) {
+  __shared__ float red[kThreads * 16];
+  const int groups = Cout / 8;              // threads per pixel
+  const int ppi = kThreads / groups;        // pixels per block iteration
+  const int cg = threadIdx.x % groups;
+  const int pl = threadIdx.x / groups;
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int co = cg * 8 + k;
+    br[k] = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][k] = w[co * 9 + t];
+  }
+  float st[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) st[k] = 0.f;
+  const long long npix = static_cast<long long>(N) * H * W;
+  const bool relu = flags & B2S_FLAG_RELU;
+  for (long long p0 = static_cast<long long>(blockIdx.x) * ppi; p0 < npix; p0 += static_cast<long long>(gridDim.x) * ppi) {
+    const long long p = p0 + pl;
+    if (p < npix) {
+      const int wq = static_cast<int>(p % W);
+      const int hq = static_cast<int>((p / W) % H);
+      const float* xi = x + (p - wq - static_cast<long long>(hq) * W);  // image base
+      float xv[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
+        xv[t] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + static_cast<long long>(hh) * W + ww) : 0.f;
+      }
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float a = br[k];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a = fmaf(xv[t], wr[t][k], a);
+        if (relu) a = fmaxf(a, 0.f);
+        a = bf16_round(a);
+        acc[k] = a;
+        st[k] += a;
+        st[8 + k] = fmaf(a, a, st[8 + k]);
+      }
+      stg16(r + p * Cout + cg * 8, pack8(acc));
+    }
+  }
+  if (stats_partial) {
+    // out row layout [2][Cout]: thread-group g holds channels g*8..g*8+7 -> sum at [g*8+k], sumsq at [Cout+g*8+k]
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) red[threadIdx.x * 16 + k] = st[k];
+    __syncthreads();
+    float* row = stats_partial + static_cast<size_t>(blockIdx.x) * 2 * Cout;
+    for (int o = threadIdx.x; o < 2 * Cout; o += kThreads) {
+      const int which = o / Cout, ch = o - which * Cout;
+      const int g = ch / 8, k = ch % 8;
+      float acc = 0.f;
+      for (int t = 0; t < ppi; ++t) acc += red[(t * groups + g) * 16 + which * 8 + k];
+      row[o] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+conv3x3_c1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                        float* __restrict__ partial, int N, int H, int W, int Cout) {
+  __shared__ float red[kThreads * 8];
+  const int groups = Cout / 8;
+  const int ppi = kThreads / groups;
+  const int cg = threadIdx.x % groups;
+  const int pl = threadIdx.x / groups;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  const long long npix = static_cast<long long>(N) * H * W;
+  for (long long p0 = static_cast<long long>(blockIdx.x) * ppi; p0 < npix; p0 += static_cast<long long>(gridDim.x) * ppi) {
+    const long long p = p0 + pl;
+    if (p < npix) {
+      const int wq = static_cast<int>(p % W);
+      const int hq = static_cast<int>((p / W) % H);
+      const float* xi = x + (p - wq - static_cast<long long>(hq) * W);
+      float g[8];
+      unpack8(ldg16(dz + p * Cout + cg * 8), g);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
+        const float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + static_cast<long long>(hh) * W + ww) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(xv, g[k], acc[t][k]);
+      }
+    }
+  }
+  float* row = partial + static_cast<size_t>(blockIdx.x) * Cout * 9;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[t][k];
+    __syncthreads();
+    for (int o = threadIdx.x; o < Cout; o += kThreads) {
+      const int g = o / 8, k = o % 8;
+      float s = 0.f;
+      for (int tt = 0; tt < ppi; ++tt) s += red[(tt * groups + g) * 8 + k];
+      row[o * 9 + t] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
+                                   float* scale, float* shift, float* mean_out, float* invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    s += static_cast<double>(partial[(static_cast<size_t>(r) * 2) * C + c]);
+    q += static_cast<double>(partial[(static_cast<size_t>(r) * 2 + 1) * C + c]);
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - static_cast<float>(mean) * sc;
+  mean_out[c] = static_cast<float>(mean);
+  invstd_out[c] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+__global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                      float eps, float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.f / sqrtf(rv[c] + eps);
+  const float sc = (gamma ? gamma[c] : 1.f) * invstd;
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN apply (+ fused 2x2 max-pool)
+// ------------------------------------------------------------------------------------------------
+template <bool POOL>
+__global__ void __launch_bounds__(kThreads)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __restrict__ scale,
+                const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int y_cs,
+                __nv_bfloat16* __restrict__ pooled, int N, int H, int W, int C) {
+  const int groups = C / 8;
+  const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;  // multiple of groups
+  const int cg = static_cast<int>(tid % groups);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
+  if (!POOL) {
+    const long long total = static_cast<long long>(N) * H * W * groups;
+    for (long long i = tid; i < total; i += stride) {
+      const long long pix = i / groups;
+      float v[8];
+      unpack8(ldg16(r + pix * r_cs + cg * 8), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+      stg16(y + pix * y_cs + cg * 8, pack8(v));
+    }
+  } else {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = static_cast<long long>(N) * Ho * Wo * groups;
+    for (long long i = tid; i < total; i += stride) {
+      const long long pp = i / groups;
+      const int wo = static_cast<int>(pp % Wo);
+      const int ho = static_cast<int>((pp / Wo) % Ho);
+      const long long n = pp / (static_cast<long long>(Wo) * Ho);
+      const long long p00 = (n * H + 2 * ho) * W + 2 * wo;
+      float m[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long pix = p00 + (q >> 1) * W + (q & 1);
+        float v[8];
+        unpack8(ldg16(r + pix * r_cs + cg * 8), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = bf16_round(fmaf(v[k], sc[k], sh[k]));
+        stg16(y + pix * y_cs + cg * 8, pack8(v));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = q == 0 ? v[k] : fmaxf(m[k], v[k]);
+      }
+      stg16(pooled + pp * C + cg * 8, pack8(m));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN (+ReLU, + max-pool routing) backward
+// ------------------------------------------------------------------------------------------------
+// Loads dy for the 2x2 window (or single pixel) handled by this thread. With POOL, adds dpool to the FIRST
+// maximum of y = bf16(r*scale+shift) in row-major window order (torch max_pool2d backward semantics).
+template <bool POOL, bool APPLY>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat16* __restrict__ dpool,
+              const __nv_bfloat16* __restrict__ r, int r_cs, const float* __restrict__ scale,
+              const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+              const float* __restrict__ coef, __nv_bfloat16* __restrict__ dz, int dz_cs, float* __restrict__ partial,
+              int N, int H, int W, int C) {
+  __shared__ float red[kThreads * 16];
+  const int groups = C / 8;
+  const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  const int cg = static_cast<int>(tid % groups);
+  float sc[8], sh[8], mu[8], is[8], c0[8], c1[8], c2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = cg * 8 + k;
+    mu[k] = mean[c]; is[k] = invstd[c];
+    if (POOL) { sc[k] = scale[c]; sh[k] = shift[c]; }
+    if (APPLY) { c0[k] = coef[c]; c1[k] = coef[C + c]; c2[k] = coef[2 * C + c]; }
+  }
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+
+  constexpr int Q = POOL ? 4 : 1;
+  const int Ho = POOL ? H / 2 : H, Wo = POOL ? W / 2 : W;
+  const long long total = static_cast<long long>(N) * Ho * Wo * groups;
+  for (long long i = tid; i < total; i += stride) {
+    const long long pp = i / groups;
+    long long p00 = pp;
+    if (POOL) {
+      const int wo = static_cast<int>(pp % Wo);
+      const int ho = static_cast<int>((pp / Wo) % Ho);
+      const long long n = pp / (static_cast<long long>(Wo) * Ho);
+      p00 = (n * H + 2 * ho) * W + 2 * wo;
+    }
+    float rv[Q][8], g[Q][8];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const long long pix = POOL ? p00 + (q >> 1) * W + (q & 1) : p00;
+      unpack8(ldg16(r + pix * r_cs + cg * 8), rv[q]);
+      unpack8(ldg16(dy + pix * dy_cs + cg * 8), g[q]);
+    }
+    if (POOL) {
+      float dp[8];
+      unpack8(ldg16(dpool + pp * C + cg * 8), dp);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float best = bf16_round(fmaf(rv[0][k], sc[k], sh[k]));
+        int arg = 0;
+#pragma unroll
+        for (int q = 1; q < Q; ++q) {
+          const float yv = bf16_round(fmaf(rv[q][k], sc[k], sh[k]));
+          if (yv > best) { best = yv; arg = q; }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) g[q][k] += (arg == q) ? dp[k] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      float out[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (rv[q][k] - mu[k]) * is[k];
+        if (!APPLY) {
+          acc[k] += g[q][k];
+          acc[8 + k] = fmaf(g[q][k], xh, acc[8 + k]);
+        } else {
+          float d = c0[k] * (g[q][k] - c1[k] - xh * c2[k]);
+          d = rv[q][k] > 0.f ? d : 0.f;
+          d = bf16_round(d);
+          out[k] = d;
+          acc[k] += d;
+        }
+      }
+      if (APPLY) {
+        const long long pix = POOL ? p00 + (q >> 1) * W + (q & 1) : p00;
+        stg16(dz + pix * dz_cs + cg * 8, pack8(out));
+      }
+    }
+  }
+  // block partials: !APPLY -> row [2][C] (sum dy, sum dy*xhat); APPLY -> row [C] (sum dz = conv bias gradient)
+  constexpr int NV = APPLY ? 8 : 16;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) red[threadIdx.x * NV + k] = acc[k];
+  __syncthreads();
+  const int per_group = kThreads / groups;
+  const int nout = APPLY ? C : 2 * C;
+  float* row = partial + static_cast<size_t>(blockIdx.x) * nout;
+  // NOTE: all threads of a block share tid % groups == threadIdx.x % groups because kThreads % groups == 0
+  for (int o = threadIdx.x; o < nout; o += kThreads) {
+    const int which = o / C, ch = o - which * C;
+    const int gi = ch / 8, k = ch % 8;
+    float s = 0.f;
+    for (int t = 0; t < per_group; ++t) s += red[(t * groups + gi) * NV + which * 8 + k];
+    row[o] = s;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                       float* dgamma, float* dbeta, float* coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    s += static_cast<double>(partial[(static_cast<size_t>(r) * 2) * C + c]);
+    q += static_cast<double>(partial[(static_cast<size_t>(r) * 2 + 1) * C + c]);
+  }
+  if (dgamma) dgamma[c] = static_cast<float>(q);
+  if (dbeta) dbeta[c] = static_cast<float>(s);
+  coef[c] = (gamma ? gamma[c] : 1.f) * invstd[c];
+  coef[C + c] = static_cast<float>(s / count);
+  coef[2 * C + c] = static_cast<float>(q / count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: folded BN + 1x1 conv (+ threshold); backward
+// ------------------------------------------------------------------------------------------------
+// 8 lanes cooperate on one pixel (C == 64): lane j holds channels 8j..8j+7.
+__global__ void __launch_bounds__(kThreads)
+head_fwd_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __restrict__ scale,
+                const float* __restrict__ shift, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ logits, unsigned char* __restrict__ mask, int N, long long HW, int C, int O) {
+  extern __shared__ float wf[];  // [O][C] folded weights, then [O] folded bias
+  for (int i = threadIdx.x; i < O * C; i += kThreads) {
+    const int c = i % C;
+    wf[i] = w[i] * (scale ? scale[c] : 1.f);
+  }
+  for (int o = threadIdx.x; o < O; o += kThreads) {
+    float acc = b ? b[o] : 0.f;
+    if (shift)
+      for (int c = 0; c < C; ++c) acc = fmaf(w[o * C + c], shift[c], acc);
+    wf[O * C + o] = acc;
+  }
+  __syncthreads();
+  const int groups = C / 8;  // lanes per pixel (power of two <= 32)
+  const int cg = threadIdx.x % groups;
+  const long long npix = static_cast<long long>(N) * HW;
+  const long long ppi = kThreads / groups;
+  for (long long p0 = static_cast<long long>(blockIdx.x) * ppi; p0 < npix; p0 += static_cast<long long>(gridDim.x) * ppi) {
+    const long long p = p0 + threadIdx.x / groups;
+    float v[8];
+    if (p < npix) unpack8(ldg16(r + p * r_cs + cg * 8), v);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    }
+    for (int o = 0; o < O; ++o) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(v[k], wf[o * C + cg * 8 + k], acc);
+      for (int off = groups >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (cg == 0 && p < npix) {
+        const float logit = acc + wf[O * C + o];
+        const long long n = p / HW, hw = p - n * HW;
+        const long long oi = (n * O + o) * HW + hw;
+        logits[oi] = logit;
+        if (mask) mask[oi] = (1.f / (1.f + expf(-logit))) > 0.5f ? 1 : 0;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ r, int r_cs,
+                const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ w,
+                __nv_bfloat16* __restrict__ dy, int dy_cs, float* __restrict__ partial, int N, long long HW, int C,
+                int O) {
+  __shared__ float red[kThreads * 9];
+  const int groups = C / 8;
+  const int cg = threadIdx.x % groups;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = scale ? scale[cg * 8 + k] : 1.f;
+    sh[k] = shift ? shift[cg * 8 + k] : 0.f;
+  }
+  const long long npix = static_cast<long long>(N) * HW;
+  const long long ppi = kThreads / groups;
+  float* row = partial + static_cast<size_t>(blockIdx.x) * (O * C + O);
+  // pass over output channels one at a time for dW/db; dy accumulates over o in registers when O == 1,
+  // otherwise dy is recomputed (O is 1 for the reference's UNet(in_channels=1,out_channels=1)).
+  for (int o = 0; o < O; ++o) {
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    for (long long p0 = static_cast<long long>(blockIdx.x) * ppi; p0 < npix;
+         p0 += static_cast<long long>(gridDim.x) * ppi) {
+      const long long p = p0 + threadIdx.x / groups;
+      if (p < npix) {
+        const long long n = p / HW, hw = p - n * HW;
+        const float g = dlogits[(n * O + o) * HW + hw];
+        float v[8];
+        unpack8(ldg16(r + p * r_cs + cg * 8), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(g, bf16_round(fmaf(v[k], sc[k], sh[k])), acc[k]);
+        if (cg == 0) acc[8] += g;
+        if (o == O - 1) {
+          float d[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] = 0.f;
+          for (int oo = 0; oo < O; ++oo) {
+            const float go = dlogits[(n * O + oo) * HW + hw];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) d[k] = fmaf(go, w[oo * C + cg * 8 + k], d[k]);
+          }
+          stg16(dy + p * dy_cs + cg * 8, pack8(d));
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 9; ++k) red[threadIdx.x * 9 + k] = acc[k];
+    __syncthreads();
+    const int per_group = kThreads / groups;
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      const int gi = c / 8, k = c % 8;
+      float s = 0.f;
+      for (int t = 0; t < per_group; ++t) s += red[(t * groups + gi) * 9 + k];
+      row[o * C + c] = s;
+    }
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int t = 0; t < per_group; ++t) s += red[(t * groups) * 9 + 8];
+      row[O * C + o] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss
+// ------------------------------------------------------------------------------------------------
+constexpr long long kLossChunk = 16384;  // elements per block
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+seg_loss_partial_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long long per_sample,
+                        int chunks, float* __restrict__ partial) {
+  __shared__ float red[4][kThreads / 32];
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const long long base = static_cast<long long>(b) * per_sample;
+  const long long i0 = static_cast<long long>(ch) * kLossChunk;
+  const long long i1 = min(i0 + kLossChunk, per_sample);
+  float s_pt = 0.f, s_p = 0.f, s_t = 0.f, s_b = 0.f;
+  const bool vec = ((per_sample & 3) == 0);
+  if (vec) {
+    for (long long i = i0 + threadIdx.x * 4; i < i1; i += kThreads * 4) {
+      const float4 x4 = __ldg(reinterpret_cast<const float4*>(logits + base + i));
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(targets + base + i));
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ts[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x = xs[k], t = ts[k];
+        const float e = expf(-fabsf(x));
+        const float p = x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+        s_pt = fmaf(p, t, s_pt); s_p += p; s_t += t;
+        s_b += fmaxf(x, 0.f) - x * t + log1pf(e);
+      }
+    }
+  } else {
+    for (long long i = i0 + threadIdx.x; i < i1; i += kThreads) {
+      const float x = logits[base + i], t = targets[base + i];
+      const float e = expf(-fabsf(x));
+      const float p = x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+      s_pt = fmaf(p, t, s_pt); s_p += p; s_t += t;
+      s_b += fmaxf(x, 0.f) - x * t + log1pf(e);
+    }
+  }
+  s_pt = warp_sum(s_pt); s_p = warp_sum(s_p); s_t = warp_sum(s_t); s_b = warp_sum(s_b);
+  const int wi = threadIdx.x >> 5, li = threadIdx.x & 31;
+  if (li == 0) { red[0][wi] = s_pt; red[1][wi] = s_p; red[2][wi] = s_t; red[3][wi] = s_b; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kThreads / 32; ++j) s += red[threadIdx.x][j];
+    partial[(static_cast<size_t>(b) * chunks + ch) * 4 + threadIdx.x] = s;
+  }
+}
+
+__global__ void seg_loss_finalize_kernel(const float* __restrict__ partial, int B, int chunks, long long per_sample,
+                                         float* __restrict__ sums, float* __restrict__ out, float dice_smooth,
+                                         float w_bce, float w_dice, float w_ft, float ft_alpha, float ft_beta,
+                                         float ft_gamma, float ft_smooth) {
+  // single block; thread b < B reduces its sample
+  __shared__ double sh[4][kThreads];
+  double acc[4] = {0, 0, 0, 0};
+  double dice_sum = 0.0;
+  for (int b = threadIdx.x; b < B; b += kThreads) {
+    double s[4] = {0, 0, 0, 0};
+    for (int c = 0; c < chunks; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += static_cast<double>(partial[(static_cast<size_t>(b) * chunks + c) * 4 + k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sums[b * 4 + k] = static_cast<float>(s[k]); acc[k] += s[k]; }
+    dice_sum += (2.0 * s[0] + dice_smooth) / (s[1] + s[2] + dice_smooth);
+  }
+  // reuse sh: 0..2 = TP, sum p, sum t ; 3 = bce ; dice via second pass
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  __shared__ double dsum[kThreads];
+  dsum[threadIdx.x] = dice_sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[4] = {0, 0, 0, 0}, d = 0.0;
+    for (int j = 0; j < kThreads; ++j) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] += sh[k][j];
+      d += dsum[j];
+    }
+    const double bce = t[3] / (static_cast<double>(B) * static_cast<double>(per_sample));
+    const double dice = 1.0 - d / B;
+    const double TP = t[0], FP = t[1] - t[0], FN = t[2] - t[0];
+    const double ti = (TP + ft_smooth) / (TP + ft_alpha * FP + ft_beta * FN + ft_smooth);
+    const double ft = pow(fmax(1.0 - ti, 0.0), static_cast<double>(ft_gamma));
+    out[0] = static_cast<float>(w_bce * bce + w_dice * dice + w_ft * ft);
+    out[1] = static_cast<float>(bce);
+    out[2] = static_cast<float>(dice);
+    out[3] = static_cast<float>(ft);
+    out[4] = static_cast<float>(t[0]);
+    out[5] = static_cast<float>(t[1]);
+    out[6] = static_cast<float>(t[2]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+seg_loss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ targets,
+                    const float* __restrict__ sums, const float* __restrict__ ft_tot, int B, long long per_sample,
+                    long long bce_count, int dice_batch, const float* __restrict__ grad_out,
+                    float* __restrict__ dlogits, float dice_smooth, float w_bce, float w_dice, float w_ft,
+                    float ft_alpha, float ft_beta, float ft_gamma, float ft_smooth) {
+  const int b = blockIdx.y;
+  const float go = grad_out ? *grad_out : 1.f;
+  const float I = sums[b * 4 + 0], U = sums[b * 4 + 1] + sums[b * 4 + 2];
+  const float den = U + dice_smooth;
+  // d dice_b / d p_i = (2 t_i den - (2I+s)) / den^2 ; loss = 1 - mean_b dice_b
+  const float kd_a = -w_dice / dice_batch * 2.f / den;
+  const float kd_b = w_dice / dice_batch * (2.f * I + dice_smooth) / (den * den);
+  const float kb = w_bce / static_cast<float>(bce_count);
+  float kf_t = 0.f, kf_1 = 0.f;
+  if (w_ft != 0.f) {
+    float TP, SP, ST;
+    if (ft_tot) { TP = ft_tot[0]; SP = ft_tot[1]; ST = ft_tot[2]; }
+    else {
+      TP = SP = ST = 0.f;
+      for (int j = 0; j < B; ++j) { TP += sums[j * 4]; SP += sums[j * 4 + 1]; ST += sums[j * 4 + 2]; }
+    }
+    const float FP = SP - TP, FN = ST - TP;
+    const float D = TP + ft_alpha * FP + ft_beta * FN + ft_smooth;
+    const float ti = (TP + ft_smooth) / D;
+    const float base = fmaxf(1.f - ti, 0.f);
+    const float dL_dti = base > 0.f ? -ft_gamma * powf(base, ft_gamma - 1.f) : 0.f;
+    // d ti / d p_i = [t_i D - (TP+s)(t_i + alpha (1 - t_i))] / D^2   (FN' = -t_i cancels with beta term below)
+    // D' = t_i + alpha (1 - t_i) - beta t_i
+    // => d ti/d p_i = t_i * [D - (TP+s)(1 - alpha - beta)] / D^2 - (TP+s) alpha / D^2
+    kf_t = w_ft * dL_dti * (D - (TP + ft_smooth) * (1.f - ft_alpha - ft_beta)) / (D * D);
+    kf_1 = -w_ft * dL_dti * (TP + ft_smooth) * ft_alpha / (D * D);
+  }
+  const long long base_i = static_cast<long long>(b) * per_sample;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < per_sample;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const float x = logits[base_i + i], t = targets[base_i + i];
+    const float e = expf(-fabsf(x));
+    const float p = x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+    const float dp = p * (1.f - p);
+    float g = kb * (p - t);
+    g += (kd_a * t + kd_b + kf_t * t + kf_1) * dp;
+    dlogits[base_i + i] = go * g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing / wgrad reduce / AdamW / copy
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                        __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) {
+  // one block per (32 co x 32 ci) tile: coalesced fp32 reads, both transposed bf16 layouts written in 64-B runs
+  __shared__ float tile[32][32 * 9 + 1];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int col = ty; col < nco; col += 8) {
+    const float* src = w + (static_cast<size_t>(co0 + col) * Cin + ci0) * taps;
+    for (int i = tx; i < nci * taps; i += 32) tile[col][i] = src[i];
+  }
+  __syncthreads();
+  for (int t = 0; t < taps; ++t) {
+    if (wf)
+      for (int col = ty; col < nco; col += 8)
+        if (tx < nci)
+          wf[(static_cast<size_t>(t) * Cout + co0 + col) * Cin + ci0 + tx] = __float2bfloat16_rn(tile[col][tx * taps + t]);
+    if (wd)
+      for (int cil = ty; cil < nci; cil += 8)
+        if (tx < nco)
+          wd[(static_cast<size_t>(taps - 1 - t) * Cin + ci0 + cil) * Cout + co0 + tx] =
+              __float2bfloat16_rn(tile[tx][cil * taps + t]);
+  }
+}
+
+__global__ void pack_convt_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                         __nv_bfloat16* __restrict__ wd, int Cin, int Cout) {
+  // w [Cin][Cout][4]; wf [(ab)*Cout+co][Cin]; wd [(ab)*Cin+ci][Cout]
+  const long long total = static_cast<long long>(Cin) * Cout * 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ab = static_cast<int>(i & 3);
+    const long long cc = i >> 2;
+    const int co = static_cast<int>(cc % Cout);
+    const int ci = static_cast<int>(cc / Cout);
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    if (wf) wf[(static_cast<size_t>(ab) * Cout + co) * Cin + ci] = v;
+    if (wd) wd[(static_cast<size_t>(ab) * Cin + ci) * Cout + co] = v;
+  }
+}
+
+// ws [splits][taps][Cin][Cout] -> layout 0: dw[co][ci][t]; layout 1: dw[ci][co][t]
+__global__ void __launch_bounds__(kThreads)
+wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int Cin, int Cout, float* __restrict__ dw,
+                    int layout) {
+  __shared__ float tile[9][32][33];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const size_t split_stride = static_cast<size_t>(taps) * Cin * Cout;
+  for (int t = 0; t < taps; ++t)
+    for (int cil = ty; cil < 32; cil += 8) {
+      const int ci = ci0 + cil, co = co0 + tx;
+      float s = 0.f;
+      if (ci < Cin && co < Cout) {
+        const float* src = ws + (static_cast<size_t>(t) * Cin + ci) * Cout + co;
+        for (int sp = 0; sp < splits; ++sp) s += src[sp * split_stride];
+      }
+      tile[t][cil][tx] = s;
+    }
+  __syncthreads();
+  if (layout == 0) {
+    // for each co: contiguous run of 32 ci x taps
+    for (int col = ty; col < 32; col += 8) {
+      const int co = co0 + col;
+      if (co >= Cout) continue;
+      float* dst = dw + (static_cast<size_t>(co) * Cin + ci0) * taps;
+      const int n = min(32, Cin - ci0) * taps;
+      for (int i = tx; i < n; i += 32) dst[i] = tile[i % taps][i / taps][col];
+    }
+  } else {
+    for (int cil = ty; cil < 32; cil += 8) {
+      const int ci = ci0 + cil;
+      if (ci >= Cin) continue;
+      float* dst = dw + (static_cast<size_t>(ci) * Cout + co0) * taps;
+      const int n = min(32, Cout - co0) * taps;
+      for (int i = tx; i < n; i += 32) dst[i] = tile[i % taps][cil][i / taps];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+             float grad_scale) {
+  const float step_size = lr / bc1;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_bfloat16* __restrict__ dst, int dst_cs,
+                     long long npix, int C) {
+  const int groups = C / 8;
+  const long long total = npix * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const long long pix = i / groups;
+    const int cg = static_cast<int>(i - pix * groups);
+    stg16(dst + pix * dst_cs + cg * 8, ldg16(src + pix * src_cs + cg * 8));
+  }
+}
+
+static int grid_for(long long work_items, int per_block) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  if (blocks > kEwBlocks) blocks = kEwBlocks;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+// channel counts the vectorised element-wise kernels accept: C/8 must divide 256
+static bool ew_channels_ok(int C) { return C >= 8 && C % 8 == 0 && pow2(C / 8) && C / 8 <= kThreads; }
+
+}  // namespace b2s
+
+using namespace b2s;
+#define STREAM(s) static_cast<cudaStream_t>(s)
+
+extern "C" int b2s_ew_rows(void) { return kEwBlocks; }
+
+extern "C" int b2s_reduce_rows(const float* in, int rows, int K, float* scratch, float* out, void* stream) {
+  if (!in || !out || rows <= 0 || K <= 0) return set_error(B2S_ERR_ARG, "b2s_reduce_rows: bad argument");
+  const float* src; int r;
+  int rc = reduce_to_small(in, rows, K, scratch, &src, &r, STREAM(stream));
+  if (rc) return rc;
+  dim3 grid((K + 31) / 32, 1), block(32, 8);
+  count_launch();
+  reduce_rows_kernel<<<grid, block, 0, STREAM(stream)>>>(src, r, K, r, out);
+  return check_launch("reduce_rows_kernel");
+}
+
+extern "C" int b2s_c1_rows(int N, int H, int W) {
+  const long long npix = static_cast<long long>(N) * H * W;
+  return grid_for(npix, 32 * 16);
+}
+
+extern "C" int b2s_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, void* r, float* stats_partial,
+                                  int N, int H, int W, int Cout, int flags, void* stream) {
+  if (!x || !w || !r) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: null pointer");
+  if (!ew_channels_ok(Cout) || Cout > 128) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: unsupported Cout");
+  if ((flags & B2S_FLAG_STATS) && !stats_partial) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: stats missing");
+  const int grid = b2s_c1_rows(N, H, W);
+  count_launch();
+  conv3x3_c1_fwd_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(
+      x, w, bias, static_cast<__nv_bfloat16*>(r), (flags & B2S_FLAG_STATS) ? stats_partial : nullptr, N, H, W, Cout,
+      flags);
+  return check_launch("conv3x3_c1_fwd_kernel");
+}
+
+extern "C" int b2s_conv3x3_c1_wgrad(const float* x, const void* dz, float* partial, int N, int H, int W, int Cout,
+                                    void* stream) {
+  if (!x || !dz || !partial) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_wgrad: null pointer");
+  if (!ew_channels_ok(Cout) || Cout > 128) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_wgrad: unsupported Cout");
+  const int grid = b2s_c1_rows(N, H, W);
+  count_launch();
+  conv3x3_c1_wgrad_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(x, static_cast<const __nv_bfloat16*>(dz), partial, N,
+                                                                H, W, Cout);
+  return check_launch("conv3x3_c1_wgrad_kernel");
+}
+
+extern "C" int b2s_bn_finalize(const float* partial, int rows, int C, double count, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var,
+                               long long* num_batches_tracked, float momentum, float eps, float* scale, float* shift,
+                               float* mean, float* invstd, float* scratch, void* stream) {
+  if (!partial || !scale || !shift || !mean || !invstd) return set_error(B2S_ERR_ARG, "b2s_bn_finalize: null pointer");
+  if (rows <= 0 || C <= 0 || count <= 0) return set_error(B2S_ERR_ARG, "b2s_bn_finalize: empty");
+  if ((running_mean == nullptr) != (running_var == nullptr))
+    return set_error(B2S_ERR_ARG, "b2s_bn_finalize: running_mean/var must both be given");
+  const float* src; int r;
+  int rc = reduce_to_small(partial, rows, 2 * C, scratch, &src, &r, STREAM(stream));
+  if (rc) return rc;
+  count_launch();
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM(stream)>>>(src, r, C, count, gamma, beta, running_mean,
+                                                                  running_var, num_batches_tracked, momentum, eps,
+                                                                  scale, shift, mean, invstd);
+  return check_launch("bn_finalize_kernel");
+}
+
+extern "C" int b2s_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float eps, float* scale, float* shift, int C,
+                                  void* stream) {
+  if (!running_mean || !running_var || !scale || !shift) return set_error(B2S_ERR_ARG, "b2s_bn_eval_affine: null");
+  count_launch();
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, STREAM(stream)>>>(gamma, beta, running_mean, running_var, eps, scale,
+                                                                     shift, C);
+  return check_launch("bn_eval_affine_kernel");
+}
+
+extern "C" int b2s_bn_apply(const void* r, int r_cstride, const float* scale, const float* shift, void* y,
+                            int y_cstride, void* pooled, int N, int H, int W, int C, void* stream) {
+  if (!r || !scale || !shift || !y) return set_error(B2S_ERR_ARG, "b2s_bn_apply: null pointer");
+  if (!ew_channels_ok(C)) return set_error(B2S_ERR_ARG, "b2s_bn_apply: C/8 must be a power of two <= 256");
+  if (r_cstride % 8 || y_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_bn_apply: strides must be multiples of 8");
+  const auto* rp = static_cast<const __nv_bfloat16*>(r);
+  auto* yp = static_cast<__nv_bfloat16*>(y);
+  count_launch();
+  if (pooled) {
+    if (H % 2 || W % 2) return set_error(B2S_ERR_ARG, "b2s_bn_apply: pooling needs even H and W");
+    const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
+    bn_apply_kernel<true><<<grid_for(items, kThreads * 2), kThreads, 0, STREAM(stream)>>>(
+        rp, r_cstride, scale, shift, yp, y_cstride, static_cast<__nv_bfloat16*>(pooled), N, H, W, C);
+  } else {
+    const long long items = static_cast<long long>(N) * H * W * (C / 8);
+    bn_apply_kernel<false><<<grid_for(items, kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+        rp, r_cstride, scale, shift, yp, y_cstride, nullptr, N, H, W, C);
+  }
+  return check_launch("bn_apply_kernel");
+}
+
+extern "C" int b2s_bn_bwd_reduce(const void* dy, int dy_cstride, const void* dpool, const void* r, int r_cstride,
+                                 const float* scale, const float* shift, const float* mean, const float* invstd,
+                                 float* partial, int N, int H, int W, int C, void* stream) {
+  if (!dy || !r || !mean || !invstd || !partial) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: null pointer");
+  if (!ew_channels_ok(C)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: unsupported C");
+  if (dpool && (!scale || !shift || H % 2 || W % 2)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: pool args");
+  const auto* dyp = static_cast<const __nv_bfloat16*>(dy);
+  const auto* rp = static_cast<const __nv_bfloat16*>(r);
+  count_launch();
+  // every block must write its partial row: launch exactly kEwBlocks blocks
+  if (dpool)
+    bn_bwd_kernel<true, false><<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
+        dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, nullptr,
+        nullptr, 0, partial, N, H, W, C);
+  else
+    bn_bwd_kernel<false, false><<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
+        dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, nullptr, nullptr, 0, partial, N, H, W, C);
+  return check_launch("bn_bwd_kernel<reduce>");
+}
+
+extern "C" int b2s_bn_bwd_finalize(const float* partial, int rows, int C, double count, const float* gamma,
+                                   const float* invstd, float* dgamma, float* dbeta, float* coef, float* scratch,
+                                   void* stream) {
+  if (!partial || !invstd || !coef) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_finalize: null pointer");
+  const float* src; int r;
+  int rc = reduce_to_small(partial, rows, 2 * C, scratch, &src, &r, STREAM(stream));
+  if (rc) return rc;
+  count_launch();
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM(stream)>>>(src, r, C, count, gamma, invstd, dgamma, dbeta,
+                                                                      coef);
+  return check_launch("bn_bwd_finalize_kernel");
+}
+
+extern "C" int b2s_bn_bwd_apply(const void* dy, int dy_cstride, const void* dpool, const void* r, int r_cstride,
+                                const float* scale, const float* shift, const float* mean, const float* invstd,
+                                const float* coef, void* dz, int dz_cstride, float* dbias_partial, int N, int H, int W,
+                                int C, void* stream) {
+  if (!dy || !r || !mean || !invstd || !coef || !dz || !dbias_partial)
+    return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: null pointer");
+  if (!ew_channels_ok(C)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: unsupported C");
+  if (dpool && (!scale || !shift || H % 2 || W % 2)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: pool args");
+  const auto* dyp = static_cast<const __nv_bfloat16*>(dy);
+  const auto* rp = static_cast<const __nv_bfloat16*>(r);
+  auto* dzp = static_cast<__nv_bfloat16*>(dz);
+  count_launch();
+  if (dpool)
+    bn_bwd_kernel<true, true><<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
+        dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, coef, dzp,
+        dz_cstride, dbias_partial, N, H, W, C);
+  else
+    bn_bwd_kernel<false, true><<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
+        dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, coef, dzp, dz_cstride, dbias_partial, N, H,
+        W, C);
+  return check_launch("bn_bwd_kernel<apply>");
+}
+
+extern "C" int b2s_head_fwd(const void* r, int r_cstride, const float* scale, const float* shift, const float* w,
+                            const float* b, float* logits, unsigned char* mask, int N, long long HW, int C, int O,
+                            void* stream) {
+  if (!r || !w || !logits) return set_error(B2S_ERR_ARG, "b2s_head_fwd: null pointer");
+  if (C % 8 || !pow2(C / 8) || C / 8 > 32) return set_error(B2S_ERR_ARG, "b2s_head_fwd: C/8 must be a power of 2 <= 32");
+  if (O < 1 || O > 64) return set_error(B2S_ERR_ARG, "b2s_head_fwd: unsupported out_channels");
+  const long long npix = static_cast<long long>(N) * HW;
+  const int ppi = kThreads / (C / 8);
+  count_launch();
+  head_fwd_kernel<<<grid_for(npix, ppi * 8), kThreads, (O * C + O) * sizeof(float), STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(r), r_cstride, scale, shift, w, b, logits, mask, N, HW, C, O);
+  return check_launch("head_fwd_kernel");
+}
+
+extern "C" int b2s_head_bwd(const float* dlogits, const void* r, int r_cstride, const float* scale, const float* shift,
+                            const float* w, void* dy, int dy_cstride, float* partial, int N, long long HW, int C, int O,
+                            void* stream) {
+  if (!dlogits || !r || !w || !dy || !partial) return set_error(B2S_ERR_ARG, "b2s_head_bwd: null pointer");
+  if (C % 8 || !pow2(C / 8) || C / 8 > 32) return set_error(B2S_ERR_ARG, "b2s_head_bwd: C/8 must be a power of 2 <= 32");
+  if (O < 1 || O > 64) return set_error(B2S_ERR_ARG, "b2s_head_bwd: unsupported out_channels");
+  count_launch();
+  head_bwd_kernel<<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(dlogits, static_cast<const __nv_bfloat16*>(r), r_cstride,
+                                                             scale, shift, w, static_cast<__nv_bfloat16*>(dy),
+                                                             dy_cstride, partial, N, HW, C, O);
+  return check_launch("head_bwd_kernel");
+}
+
+extern "C" int b2s_loss_chunks(long long per_sample) {
+  return static_cast<int>((per_sample + kLossChunk - 1) / kLossChunk);
+}
+
+extern "C" int b2s_seg_loss_fwd(const float* logits, const float* targets, int B, long long per_sample, float* partial,
+                                float* sums, float* out, float dice_smooth, float w_bce, float w_dice, float w_ft,
+                                float ft_alpha, float ft_beta, float ft_gamma, float ft_smooth, void* stream) {
+  if (!logits || !targets || !partial || !sums || !out) return set_error(B2S_ERR_ARG, "b2s_seg_loss_fwd: null pointer");
+  if (B <= 0 || per_sample <= 0 || B > 65535) return set_error(B2S_ERR_ARG, "b2s_seg_loss_fwd: bad batch");
+  const int chunks = b2s_loss_chunks(per_sample);
+  count_launch();
+  seg_loss_partial_kernel<<<dim3(chunks, B), kThreads, 0, STREAM(stream)>>>(logits, targets, per_sample, chunks,
+                                                                           partial);
+  int rc = check_launch("seg_loss_partial_kernel");
+  if (rc) return rc;
+  count_launch();
+  seg_loss_finalize_kernel<<<1, kThreads, 0, STREAM(stream)>>>(partial, B, chunks, per_sample, sums, out, dice_smooth,
+                                                              w_bce, w_dice, w_ft, ft_alpha, ft_beta, ft_gamma,
+                                                              ft_smooth);
+  return check_launch("seg_loss_finalize_kernel");
+}
+
+extern "C" int b2s_seg_loss_bwd(const float* logits, const float* targets, const float* sums, const float* ft_tot,
+                                int B, long long per_sample, long long bce_count, int dice_batch,
+                                const float* grad_out, float* dlogits, float dice_smooth, float w_bce, float w_dice,
+                                float w_ft, float ft_alpha, float ft_beta, float ft_gamma, float ft_smooth,
+                                void* stream) {
+  if (!logits || !targets || !sums || !dlogits) return set_error(B2S_ERR_ARG, "b2s_seg_loss_bwd: null pointer");
+  if (B <= 0 || per_sample <= 0 || B > 65535) return set_error(B2S_ERR_ARG, "b2s_seg_loss_bwd: bad batch");
+  int gx = static_cast<int>((per_sample + kThreads * 4 - 1) / (kThreads * 4));
+  if (gx > 1024) gx = 1024;
+  count_launch();
+  seg_loss_bwd_kernel<<<dim3(gx, B), kThreads, 0, STREAM(stream)>>>(logits, targets, sums, ft_tot, B, per_sample,
+                                                                   bce_count, dice_batch, grad_out, dlogits,
+                                                                   dice_smooth, w_bce, w_dice, w_ft, ft_alpha, ft_beta,
+                                                                   ft_gamma, ft_smooth);
+  return check_launch("seg_loss_bwd_kernel");
+}
+
+extern "C" int b2s_pack_conv_weight(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int ksize,
+                                    void* stream) {
+  if (!w || (!w_fwd && !w_dgrad)) return set_error(B2S_ERR_ARG, "b2s_pack_conv_weight: null pointer");
+  if (ksize != 1 && ksize != 3) return set_error(B2S_ERR_ARG, "b2s_pack_conv_weight: ksize must be 1 or 3");
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
+  count_launch();
+  pack_conv_weight_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(w, static_cast<__nv_bfloat16*>(w_fwd),
+                                                           static_cast<__nv_bfloat16*>(w_dgrad), Cout, Cin,
+                                                           ksize * ksize);
+  return check_launch("pack_conv_weight_kernel");
+}
+
+extern "C" int b2s_pack_convt_weight(const float* w, void* w_fwd, void* w_dgrad, int Cin, int Cout, void* stream) {
+  if (!w || (!w_fwd && !w_dgrad)) return set_error(B2S_ERR_ARG, "b2s_pack_convt_weight: null pointer");
+  const long long total = static_cast<long long>(Cin) * Cout * 4;
+  count_launch();
+  pack_convt_weight_kernel<<<grid_for(total, kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad), Cin, Cout);
+  return check_launch("pack_convt_weight_kernel");
+}
+
+extern "C" int b2s_wgrad_reduce(const float* ws, int splits, int taps, int Cin, int Cout, float* dw, int layout,
+                                void* stream) {
+  if (!ws || !dw) return set_error(B2S_ERR_ARG, "b2s_wgrad_reduce: null pointer");
+  if (taps < 1 || taps > 9 || splits < 1) return set_error(B2S_ERR_ARG, "b2s_wgrad_reduce: bad taps/splits");
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
+  count_launch();
+  wgrad_reduce_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(ws, splits, taps, Cin, Cout, dw, layout);
+  return check_launch("wgrad_reduce_kernel");
+}
+
+extern "C" int b2s_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v) return set_error(B2S_ERR_ARG, "b2s_adamw_step: null pointer");
+  if (step < 1) return set_error(B2S_ERR_ARG, "b2s_adamw_step: step is 1-based");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  count_launch();
+  adamw_kernel<<<grid_for(n, kThreads * 8), kThreads, 0, STREAM(stream)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
+      grad_scale);
+  return check_launch("adamw_kernel");
+}
+
+extern "C" int b2s_copy_channels(const void* src, int src_cstride, void* dst, int dst_cstride, long long npix, int C,
+                                 void* stream) {
+  if (!src || !dst) return set_error(B2S_ERR_ARG, "b2s_copy_channels: null pointer");
+  if (C % 8 || src_cstride % 8 || dst_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_copy_channels: need multiples of 8");
+  count_launch();
+  copy_channels_kernel<<<grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), src_cstride, static_cast<__nv_bfloat16*>(dst), dst_cstride, npix, C);
+  return check_launch("copy_channels_kernel");
+}

@@ -1,0 +1,300 @@
+"""Host-side plan of the UNet hot path: owns the NHWC bf16 activation buffers, the packed bf16 weights and the
+launch order of the libb2s kernels for forward (train / eval), loss and backward.
+
+Graph mirrored: reference models/model.py:53-73 (forward), autograd of the same for backward. Data layout in HBM
+(DESIGN.md §3): per level l (H/2^l x W/2^l, C_l = 64*2^l)
+    cat[l]   [N,H_l,W_l,2*C_l]  = [ up-conv output | encoder skip ]   (torch.cat is never materialised)
+    r/y      post-ReLU conv outputs (saved) and BatchNorm outputs (operands of the next conv / wgrad)
+    pooled[l] max-pooled skip, input of level l+1
+"""
+import torch
+
+from . import ops
+from .ops import Act
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+ENC = ["encoder1", "encoder2", "encoder3", "encoder4"]
+DEC = {3: "decoder3.0", 2: "decoder2.0", 1: "decoder1.0"}          # block consuming cat[l]
+CONVT_INTO = {3: "middle.2", 2: "decoder3.1", 1: "decoder2.1", 0: "decoder1.1"}  # up-conv writing cat[l]
+
+
+def conv_stages():
+    """(prefix, idx, Cin, Cout, level) of the 18 conv3x3+ReLU+BN stages in forward order."""
+    st = []
+    cin = None
+    for l, name in enumerate(ENC):
+        c = 64 << l
+        st.append((name, 0, cin if l else None, c, l))
+        st.append((name, 3, c, c, l))
+        cin = c
+    st.append(("middle.1", 0, 512, 1024, 4))
+    st.append(("middle.1", 3, 1024, 1024, 4))
+    for l in (3, 2, 1):
+        c = 64 << l
+        st.append((DEC[l], 0, 2 * c, c, l))
+        st.append((DEC[l], 3, c, c, l))
+    st.append(("final.0", 0, 128, 64, 0))
+    st.append(("final.0", 3, 64, 64, 0))
+    return st
+
+
+class _Stage:
+    """Per conv stage: saved tensors and BN vectors."""
+    __slots__ = ("name", "idx", "cin", "cout", "level", "x", "r", "y", "scale", "shift", "mean", "invstd", "wf", "wd")
+
+
+class UNetPlan:
+    """Buffers for one (N,H,W) on one device."""
+
+    def __init__(self, N, H, W, device, in_channels=1, out_channels=1, train_buffers=True):
+        if H % 16 or W % 16:
+            raise RuntimeError(f"Sizes of tensors must match: H={H}, W={W} must be multiples of 16 "
+                               "(reference models/model.py:64 torch.cat)")
+        if in_channels != 1:
+            raise NotImplementedError("the B200 path implements the reference default in_channels=1")
+        self.N, self.H, self.W, self.device = N, H, W, device
+        self.O = out_channels
+        f32 = dict(dtype=torch.float32, device=device)
+        dims = [(H >> l, W >> l, 64 << l) for l in range(5)]
+        self.dims = dims
+        A = lambda l, C: Act.empty(N, dims[l][0], dims[l][1], C, device)
+        self.cat = [A(l, 2 * dims[l][2]) for l in range(4)]
+        self.pooled = [A(l + 1, dims[l][2]) for l in range(4)]
+        self.stages = {}
+        for (name, idx, cin, cout, l) in conv_stages():
+            s = _Stage()
+            s.name, s.idx, s.cin, s.cout, s.level = name, idx, cin, cout, l
+            s.r = A(l, cout)
+            s.y = None
+            for k in ("scale", "shift", "mean", "invstd"):
+                setattr(s, k, torch.empty(cout, **f32))
+            s.wf = s.wd = None
+            self.stages[(name, idx)] = s
+        # BN outputs: first stage of each block -> dense y; second stage -> concat slice (encoders) or dense
+        for (name, idx, cin, cout, l) in conv_stages():
+            s = self.stages[(name, idx)]
+            if idx == 0:
+                s.y = A(l, cout)
+            elif name in ENC:
+                s.y = self.cat[l].slice(cout, cout)
+            elif name != "final.0":
+                s.y = A(l, cout)
+        self.logits = torch.empty((N, out_channels, H, W), **f32)
+        self.mask = torch.empty((N, out_channels, H, W), dtype=torch.uint8, device=device)
+        # partial / scratch buffers
+        rows0 = ops.conv_tiles_m(N, H, W)
+        self.stats_partial = torch.empty(max(rows0 * 2 * 128, ops.c1_rows(N, H, W) * 2 * 64), **f32)
+        self.ew_partial = torch.empty(ops.ew_rows() * 2 * 1024, **f32)
+        self.c1_partial = torch.empty(ops.c1_rows(N, H, W) * 64 * 9, **f32)
+        self.scratch = torch.empty(64 * 2 * 1024, **f32)
+        self.coef = torch.empty(3 * 1024, **f32)
+        self.tmp_vec = torch.empty(2 * 1024, **f32)
+        # loss
+        per = out_channels * H * W
+        self.loss_partial = torch.empty(N * ops.loss_chunks(per) * 4, **f32)
+        self.loss_sums = torch.empty(N * 4, **f32)
+        self.loss_out = torch.empty(8, **f32)
+        self.generation = 0
+        self.train_ready = False
+        if train_buffers:
+            self._alloc_train()
+
+    def _alloc_train(self):
+        if self.train_ready:
+            return
+        N, dims, device = self.N, self.dims, self.device
+        A = lambda l, C: Act.empty(N, dims[l][0], dims[l][1], C, device)
+        self.dlogits = torch.empty_like(self.logits)
+        self.dcat = [A(l, 2 * dims[l][2]) for l in range(4)]
+        self.ga = [A(l, dims[l][2]) for l in range(5)]
+        self.gb = [A(l, dims[l][2]) for l in range(5)]
+        self.dpool = [A(l + 1, dims[l][2]) for l in range(4)]
+        ws_bytes = 0
+        for (name, idx, cin, cout, l) in conv_stages():
+            if cin is None:
+                continue
+            nb, _ = ops.wgrad_workspace(N, dims[l][0], dims[l][1], cin, cout, 9)
+            ws_bytes = max(ws_bytes, nb)
+        for l in range(4):
+            cin, cout = 2 * dims[l][2], dims[l][2]
+            nb, _ = ops.wgrad_workspace(N, dims[l + 1][0], dims[l + 1][1], cin, cout, 4)
+            ws_bytes = max(ws_bytes, nb)
+        self.wgrad_ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=device)
+        self.train_ready = True
+
+
+class UNetEngine:
+    """Runs the reference UNet graph on libb2s kernels for a dict of parameters/buffers (reference state_dict keys)."""
+
+    def __init__(self, out_channels=1):
+        self.O = out_channels
+        self.plans = {}
+        self._packed_versions = None
+        self._packed = {}
+
+    # ---- plumbing -----------------------------------------------------------------------------------------
+    def plan(self, N, H, W, device, train):
+        key = (N, H, W, str(device))
+        p = self.plans.get(key)
+        if p is None:
+            p = UNetPlan(N, H, W, device, out_channels=self.O, train_buffers=train)
+            self.plans[key] = p
+        if train:
+            p._alloc_train()
+        return p
+
+    def _pack_weights(self, P, need_dgrad):
+        """fp32 parameters -> bf16 GEMM operands; cached on the parameters' version counters."""
+        names = [k for k in P if k.endswith(".weight") and P[k].dim() == 4 and k != "encoder1.0.weight"
+                 and k != "final.1.weight"]
+        versions = tuple((k, P[k]._version, P[k].data_ptr(), need_dgrad) for k in names)
+        if versions == self._packed_versions:
+            return
+        for k in names:
+            w = P[k]
+            if k.split(".")[0] in ("middle", "decoder3", "decoder2", "decoder1") and w.shape[2] == 2:
+                self._packed[k] = ops.pack_convt_weight(w)
+            else:
+                self._packed[k] = ops.pack_conv_weight(w, want_dgrad=need_dgrad)
+        self._packed_versions = versions
+
+    # ---- forward ----------------------------------------------------------------------------------------------
+    def forward(self, P, x, train, want_mask=False, need_backward=None):
+        """x [N,1,H,W] fp32 CUDA. Returns (logits fp32 [N,O,H,W], plan). P: name -> tensor (params and BN buffers)."""
+        if not x.is_cuda:
+            raise ops._lib.B2SError("UNetEngine.forward needs a CUDA tensor: the B200 path has no CPU fallback")
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise RuntimeError(f"expected input [N,1,H,W], got {tuple(x.shape)}")
+        need_backward = train if need_backward is None else need_backward
+        N, _, H, W = x.shape
+        pl = self.plan(N, H, W, x.device, need_backward)
+        pl.generation += 1
+        x = x.contiguous().float()
+        pl.x = x
+        self._pack_weights(P, need_dgrad=need_backward)
+        count = lambda l: float(N * pl.dims[l][0] * pl.dims[l][1])
+
+        def stage(name, idx, xin, pooled=None):
+            s = pl.stages[(name, idx)]
+            s.x = xin
+            bn = f"{name}.{idx + 2}"
+            if xin is None:  # first conv on the fp32 image
+                ops.conv3x3_c1_fwd(x, P[f"{name}.{idx}.weight"], P[f"{name}.{idx}.bias"], s.r, relu=True,
+                                   stats=pl.stats_partial if train else None)
+                rows = ops.c1_rows(N, H, W)
+            else:
+                wf, _ = self._packed[f"{name}.{idx}.weight"]
+                ops.conv_fwd(xin, wf, P[f"{name}.{idx}.bias"], s.r, ksize=3, relu=True,
+                             stats=pl.stats_partial if train else None)
+                rows = ops.conv_tiles_m(N, s.r.H, s.r.W)
+            if train:
+                ops.bn_finalize(pl.stats_partial, rows, s.cout, count(s.level), P[f"{bn}.weight"], P[f"{bn}.bias"],
+                                P[f"{bn}.running_mean"], P[f"{bn}.running_var"], P[f"{bn}.num_batches_tracked"],
+                                BN_MOMENTUM, BN_EPS, s.scale, s.shift, s.mean, s.invstd, pl.scratch)
+            else:
+                ops.bn_eval_affine(P[f"{bn}.weight"], P[f"{bn}.bias"], P[f"{bn}.running_mean"],
+                                   P[f"{bn}.running_var"], BN_EPS, s.scale, s.shift)
+            if s.y is not None:
+                ops.bn_apply(s.r, s.scale, s.shift, s.y, pooled)
+            return s
+
+        def block(name, xin, pooled=None):
+            s0 = stage(name, 0, xin)
+            return stage(name, 3, s0.y, pooled)
+
+        cur = None
+        for l, name in enumerate(ENC):
+            block(name, cur, pl.pooled[l])
+            cur = pl.pooled[l]
+        s = block("middle.1", cur)
+        for l in (3, 2, 1, 0):
+            ct = CONVT_INTO[l]
+            wf, _ = self._packed[f"{ct}.weight"]
+            C = pl.dims[l][2]
+            ops.convt_fwd(s.y, wf, P[f"{ct}.bias"], pl.cat[l].slice(0, C))
+            s = block(DEC[l] if l else "final.0", pl.cat[l])
+        ops.head_fwd(s.r, s.scale, s.shift, P["final.1.weight"], P["final.1.bias"], pl.logits,
+                     pl.mask if want_mask else None)
+        return pl.logits, pl
+
+    # ---- loss -------------------------------------------------------------------------------------------------
+    def loss(self, pl, targets, w_bce=1.0, w_dice=1.0, w_ft=0.0, **kw):
+        """Fused Dice+BCE(+FocalTversky) on pl.logits; returns the 8-float result vector (total, bce, dice, ft, ...)."""
+        ops.seg_loss_fwd(pl.logits, targets, pl.loss_partial, pl.loss_sums, pl.loss_out, w_bce=w_bce, w_dice=w_dice,
+                         w_ft=w_ft, **kw)
+        return pl.loss_out
+
+    def loss_backward(self, pl, targets, grad_out=None, ft_tot=None, w_bce=1.0, w_dice=1.0, w_ft=0.0, **kw):
+        ops.seg_loss_bwd(pl.logits, targets, pl.loss_sums, ft_tot, grad_out, pl.dlogits, w_bce=w_bce, w_dice=w_dice,
+                         w_ft=w_ft, **kw)
+        return pl.dlogits
+
+    # ---- backward ---------------------------------------------------------------------------------------------
+    def backward(self, P, pl, dlogits, G, on_grad_ready=None):
+        """Writes the gradient of every parameter into G[name] (fp32 tensors, parameter shapes).
+        on_grad_ready(name) is called as soon as G[name] has been enqueued (DDP bucket hook)."""
+        N = pl.N
+        dlogits = dlogits.contiguous().float()
+        ready = on_grad_ready or (lambda name: None)
+        count = lambda l: float(N * pl.dims[l][0] * pl.dims[l][1])
+
+        def stage_bwd(name, idx, dy, dx_out, dpool=None, dx_stats=False):
+            """BN+ReLU backward -> dz; conv wgrad; conv dgrad into dx_out (None for the image conv)."""
+            s = pl.stages[(name, idx)]
+            bn = f"{name}.{idx + 2}"
+            l = s.level
+            dz = pl.gb[l]
+            ops.bn_bwd(dy, dpool, s.r, s.scale, s.shift, s.mean, s.invstd, P[f"{bn}.weight"], count(l), dz,
+                       pl.ew_partial, pl.scratch, pl.coef, G[f"{bn}.weight"], G[f"{bn}.bias"],
+                       G[f"{name}.{idx}.bias"])
+            ready(f"{bn}.weight"); ready(f"{bn}.bias"); ready(f"{name}.{idx}.bias")
+            wname = f"{name}.{idx}.weight"
+            if s.x is None:
+                ops.conv3x3_c1_wgrad(pl.x, dz, pl.c1_partial, pl.scratch, G[wname])
+                ready(wname)
+                return
+            ops.conv3x3_wgrad(s.x, dz, pl.wgrad_ws, G[wname])
+            ready(wname)
+            _, wd = self._packed[wname]
+            ops.conv_fwd(dz, wd, None, dx_out, ksize=3, relu=False, stats=pl.stats_partial if dx_stats else None)
+
+        def block_bwd(name, dy1, dx_out, dpool=None, dx_stats=False):
+            l = pl.stages[(name, 0)].level
+            stage_bwd(name, 3, dy1, pl.ga[l], dpool=dpool)
+            stage_bwd(name, 0, pl.ga[l], dx_out, dx_stats=dx_stats)
+
+        # head (final.1) -> dy of final.0's second BN
+        s = pl.stages[("final.0", 3)]
+        dwdb = pl.tmp_vec[: self.O * 64 + self.O]
+        ops.head_bwd(dlogits, s.r, s.scale, s.shift, P["final.1.weight"], pl.ga[0], pl.ew_partial, pl.scratch, dwdb)
+        G["final.1.weight"].view(-1).copy_(dwdb[: self.O * 64])
+        G["final.1.bias"].copy_(dwdb[self.O * 64:])
+        ready("final.1.weight"); ready("final.1.bias")
+
+        dy = pl.ga[0]
+        for l in (0, 1, 2, 3):
+            name = "final.0" if l == 0 else DEC[l]
+            C = pl.dims[l][2]
+            block_bwd(name, dy, pl.dcat[l], dx_stats=True)
+            # transposed conv writing cat[l][:, :C]: bias grad = column sums of dcat[l][..., :C] (dgrad epilogue)
+            ct = CONVT_INTO[l]
+            rows = ops.conv_tiles_m(N, pl.dims[l][0], pl.dims[l][1])
+            ops.reduce_rows(pl.stats_partial, rows, 2 * 2 * C, pl.scratch, pl.tmp_vec)
+            G[f"{ct}.bias"].copy_(pl.tmp_vec[:C])
+            ready(f"{ct}.bias")
+            up_in = pl.stages[(DEC[l + 1] if l < 3 else "middle.1", 3)].y      # input of the transposed conv
+            dY = pl.dcat[l].slice(0, C)
+            ops.convt_wgrad(up_in, dY, pl.wgrad_ws, G[f"{ct}.weight"])
+            ready(f"{ct}.weight")
+            _, wd = self._packed[f"{ct}.weight"]
+            ops.convt_dgrad(dY, wd, pl.ga[l + 1])
+            dy = pl.ga[l + 1]
+        block_bwd("middle.1", dy, pl.dpool[3])
+        for l in (3, 2, 1, 0):
+            C = pl.dims[l][2]
+            skip_grad = pl.dcat[l].slice(C, C)
+            dx_out = pl.dpool[l - 1] if l > 0 else None
+            block_bwd(ENC[l], skip_grad, dx_out, dpool=pl.dpool[l])
+        return G

@@ -1,0 +1,271 @@
+"""Tensor-level wrappers over the C ABI (include/b2s.h). PyTorch supplies device memory and streams only; every
+computation below is a libb2s kernel. Activations are NHWC bf16 `Act` views (a channel slice of a buffer)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import B2S_FLAG_RELU, B2S_FLAG_STATS, check
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.B2SError("libb2s kernels need CUDA tensors; there is no CPU fallback")
+
+
+class Act:
+    """Channel slice [c0, c0+C) of an NHWC bf16 buffer [N,H,W,Ctot]."""
+
+    __slots__ = ("buf", "c0", "C")
+
+    def __init__(self, buf, c0=0, C=None):
+        assert buf.dtype == BF16 and buf.dim() == 4 and buf.is_contiguous()
+        self.buf = buf
+        self.c0 = c0
+        self.C = buf.shape[3] - c0 if C is None else C
+        assert 0 <= c0 and c0 + self.C <= buf.shape[3] and c0 % 8 == 0
+
+    @staticmethod
+    def empty(N, H, W, C, device):
+        return Act(torch.empty((N, H, W, C), dtype=BF16, device=device))
+
+    @property
+    def N(self):
+        return self.buf.shape[0]
+
+    @property
+    def H(self):
+        return self.buf.shape[1]
+
+    @property
+    def W(self):
+        return self.buf.shape[2]
+
+    @property
+    def cstride(self):
+        return self.buf.shape[3]
+
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.buf.data_ptr() + 2 * self.c0)
+
+    def slice(self, c0, C):
+        return Act(self.buf, self.c0 + c0, C)
+
+    def view(self):
+        return self.buf[..., self.c0:self.c0 + self.C]
+
+    def to_nchw_float(self):
+        return self.view().permute(0, 3, 1, 2).float().contiguous()
+
+    @staticmethod
+    def from_nchw(x):
+        return Act(x.permute(0, 2, 3, 1).contiguous().to(BF16))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# weights
+# ---------------------------------------------------------------------------------------------------------
+def pack_conv_weight(w, want_dgrad=True):
+    """w [Cout,Cin,k,k] fp32 -> (w_fwd [k*k,Cout,Cin] bf16, w_dgrad [k*k,Cin,Cout] bf16 | None)."""
+    _need_cuda(w)
+    Cout, Cin, k, _ = w.shape
+    w = w.detach().contiguous().float()
+    wf = torch.empty((k * k, Cout, Cin), dtype=BF16, device=w.device)
+    wd = torch.empty((k * k, Cin, Cout), dtype=BF16, device=w.device) if want_dgrad else None
+    check(_lib.lib().b2s_pack_conv_weight(_p(w), _p(wf), _p(wd), Cout, Cin, k, _stream()), "pack_conv_weight")
+    return wf, wd
+
+
+def pack_convt_weight(w):
+    """w [Cin,Cout,2,2] fp32 -> (w_fwd [4*Cout,Cin], w_dgrad [4*Cin,Cout]) bf16."""
+    _need_cuda(w)
+    Cin, Cout = w.shape[0], w.shape[1]
+    w = w.detach().contiguous().float()
+    wf = torch.empty((4 * Cout, Cin), dtype=BF16, device=w.device)
+    wd = torch.empty((4 * Cin, Cout), dtype=BF16, device=w.device)
+    check(_lib.lib().b2s_pack_convt_weight(_p(w), _p(wf), _p(wd), Cin, Cout, _stream()), "pack_convt_weight")
+    return wf, wd
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tensor-core convs
+# ---------------------------------------------------------------------------------------------------------
+def conv_fwd(x, w_packed, bias, y, ksize=3, relu=False, stats=None, tile_n=0):
+    """y = conv(x, w) (+bias)(+ReLU); stats: fp32 [tiles_m, 2, Cout] partial buffer or None."""
+    flags = (B2S_FLAG_RELU if relu else 0) | (B2S_FLAG_STATS if stats is not None else 0)
+    Cout = y.C
+    check(_lib.lib().b2s_conv_fwd(x.ptr, x.cstride, _p(w_packed), _p(bias), y.ptr, y.cstride, _p(stats), x.N, x.H,
+                                  x.W, x.C, Cout, ksize, flags, tile_n, _stream()), "b2s_conv_fwd")
+
+
+def conv_tiles_m(N, H, W):
+    return _lib.lib().b2s_conv_fwd_tiles_m(N, H, W)
+
+
+def convt_fwd(x, w_packed, bias, y, tile_n=0):
+    check(_lib.lib().b2s_convt2x2_fwd(x.ptr, x.cstride, _p(w_packed), _p(bias), y.ptr, y.cstride, x.N, x.H, x.W, x.C,
+                                      y.C, tile_n, _stream()), "b2s_convt2x2_fwd")
+
+
+def convt_dgrad(dy, w_packed_d, dx, tile_n=0):
+    check(_lib.lib().b2s_convt2x2_dgrad(dy.ptr, dy.cstride, _p(w_packed_d), dx.ptr, dx.cstride, dx.N, dx.H, dx.W,
+                                        dx.C, dy.C, tile_n, _stream()), "b2s_convt2x2_dgrad")
+
+
+def wgrad_workspace(N, H, W, Cin, Cout, taps, tile_n=0, splits=0):
+    s = ctypes.c_int(0)
+    nbytes = _lib.lib().b2s_conv_wgrad_workspace(N, H, W, Cin, Cout, 3 if taps == 9 else taps, tile_n, splits,
+                                                 ctypes.byref(s))
+    if nbytes < 0:
+        check(-1, "b2s_conv_wgrad_workspace")
+    return nbytes, s.value
+
+
+def conv3x3_wgrad(x, dz, ws, dw, tile_n=0, splits=0):
+    """dw [Cout,Cin,3,3] fp32 = sum_pix dz (x) x ; ws: fp32 workspace tensor."""
+    nbytes, s = wgrad_workspace(x.N, x.H, x.W, x.C, dz.C, 9, tile_n, splits)
+    assert ws.numel() * 4 >= nbytes, "wgrad workspace too small"
+    L = _lib.lib()
+    check(L.b2s_conv3x3_wgrad(x.ptr, x.cstride, dz.ptr, dz.cstride, _p(ws), x.N, x.H, x.W, x.C, dz.C, tile_n, splits,
+                              _stream()), "b2s_conv3x3_wgrad")
+    check(L.b2s_wgrad_reduce(_p(ws), s, 9, x.C, dz.C, _p(dw), 0, _stream()), "b2s_wgrad_reduce")
+
+
+def convt_wgrad(x, dy, ws, dw, tile_n=0, splits=0):
+    """dw [Cin,Cout,2,2] fp32; x [N,Hi,Wi,Cin], dy [N,2Hi,2Wi,Cout]."""
+    nbytes, s = wgrad_workspace(x.N, x.H, x.W, x.C, dy.C, 4, tile_n, splits)
+    assert ws.numel() * 4 >= nbytes, "wgrad workspace too small"
+    L = _lib.lib()
+    check(L.b2s_convt2x2_wgrad(x.ptr, x.cstride, dy.ptr, dy.cstride, _p(ws), x.N, x.H, x.W, x.C, dy.C, tile_n, splits,
+                               _stream()), "b2s_convt2x2_wgrad")
+    check(L.b2s_wgrad_reduce(_p(ws), s, 4, x.C, dy.C, _p(dw), 1, _stream()), "b2s_wgrad_reduce")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bandwidth kernels
+# ---------------------------------------------------------------------------------------------------------
+def c1_rows(N, H, W):
+    return _lib.lib().b2s_c1_rows(N, H, W)
+
+
+def conv3x3_c1_fwd(x, w, bias, r, relu=True, stats=None):
+    """x [N,1,H,W] or [N,H,W] fp32 -> r Act [N,H,W,Cout]."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    flags = (B2S_FLAG_RELU if relu else 0) | (B2S_FLAG_STATS if stats is not None else 0)
+    assert r.c0 == 0 and r.C == r.cstride
+    check(_lib.lib().b2s_conv3x3_c1_fwd(_p(x), _p(w), _p(bias), r.ptr, _p(stats), r.N, r.H, r.W, r.C, flags,
+                                        _stream()), "b2s_conv3x3_c1_fwd")
+
+
+def conv3x3_c1_wgrad(x, dz, partial, scratch, dw):
+    assert dz.c0 == 0 and dz.C == dz.cstride
+    L = _lib.lib()
+    rows = L.b2s_c1_rows(dz.N, dz.H, dz.W)
+    check(L.b2s_conv3x3_c1_wgrad(_p(x), dz.ptr, _p(partial), dz.N, dz.H, dz.W, dz.C, _stream()), "c1_wgrad")
+    check(L.b2s_reduce_rows(_p(partial), rows, dz.C * 9, _p(scratch), _p(dw), _stream()), "reduce_rows")
+
+
+def reduce_rows(partial, rows, K, scratch, out):
+    check(_lib.lib().b2s_reduce_rows(_p(partial), rows, K, _p(scratch), _p(out), _stream()), "b2s_reduce_rows")
+
+
+def ew_rows():
+    return _lib.lib().b2s_ew_rows()
+
+
+def bn_finalize(partial, rows, C, count, gamma, beta, running_mean, running_var, nbt, momentum, eps, scale, shift,
+                mean, invstd, scratch):
+    check(_lib.lib().b2s_bn_finalize(_p(partial), rows, C, float(count), _p(gamma), _p(beta), _p(running_mean),
+                                     _p(running_var), _p(nbt), momentum, eps, _p(scale), _p(shift), _p(mean),
+                                     _p(invstd), _p(scratch), _stream()), "b2s_bn_finalize")
+
+
+def bn_eval_affine(gamma, beta, rm, rv, eps, scale, shift):
+    check(_lib.lib().b2s_bn_eval_affine(_p(gamma), _p(beta), _p(rm), _p(rv), eps, _p(scale), _p(shift),
+                                        scale.numel(), _stream()), "b2s_bn_eval_affine")
+
+
+def bn_apply(r, scale, shift, y, pooled=None):
+    check(_lib.lib().b2s_bn_apply(r.ptr, r.cstride, _p(scale), _p(shift), y.ptr, y.cstride,
+                                  pooled.ptr if pooled is not None else None, r.N, r.H, r.W, r.C, _stream()),
+          "b2s_bn_apply")
+
+
+def bn_bwd(dy, dpool, r, scale, shift, mean, invstd, gamma, count, dz, partial, scratch, coef, dgamma, dbeta, dbias):
+    """Full BatchNorm(+ReLU, + optional max-pool routing) backward: writes dz, dgamma, dbeta, dbias."""
+    L = _lib.lib()
+    rows = L.b2s_ew_rows()
+    C = r.C
+    dp = dpool.ptr if dpool is not None else None
+    check(L.b2s_bn_bwd_reduce(dy.ptr, dy.cstride, dp, r.ptr, r.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
+                              _p(partial), r.N, r.H, r.W, C, _stream()), "b2s_bn_bwd_reduce")
+    check(L.b2s_bn_bwd_finalize(_p(partial), rows, C, float(count), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta),
+                                _p(coef), _p(scratch), _stream()), "b2s_bn_bwd_finalize")
+    check(L.b2s_bn_bwd_apply(dy.ptr, dy.cstride, dp, r.ptr, r.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
+                             _p(coef), dz.ptr, dz.cstride, _p(partial), r.N, r.H, r.W, C, _stream()),
+          "b2s_bn_bwd_apply")
+    check(L.b2s_reduce_rows(_p(partial), rows, C, _p(scratch), _p(dbias), _stream()), "b2s_reduce_rows")
+
+
+def head_fwd(r, scale, shift, w, b, logits, mask=None):
+    """logits [N,O,H,W] fp32 = conv1x1(BN(r)); mask uint8 optional."""
+    O = logits.shape[1]
+    check(_lib.lib().b2s_head_fwd(r.ptr, r.cstride, _p(scale), _p(shift), _p(w), _p(b), _p(logits), _p(mask), r.N,
+                                  r.H * r.W, r.C, O, _stream()), "b2s_head_fwd")
+
+
+def head_bwd(dlogits, r, scale, shift, w, dy, partial, scratch, dw_db):
+    """dy (Act) and dw_db fp32 [O*C+O] (weight grad then bias grad)."""
+    L = _lib.lib()
+    O = dlogits.shape[1]
+    check(L.b2s_head_bwd(_p(dlogits), r.ptr, r.cstride, _p(scale), _p(shift), _p(w), dy.ptr, dy.cstride, _p(partial),
+                         r.N, r.H * r.W, r.C, O, _stream()), "b2s_head_bwd")
+    check(L.b2s_reduce_rows(_p(partial), L.b2s_ew_rows(), O * r.C + O, _p(scratch), _p(dw_db), _stream()),
+          "b2s_reduce_rows")
+
+
+def loss_chunks(per_sample):
+    return _lib.lib().b2s_loss_chunks(per_sample)
+
+
+def seg_loss_fwd(logits, targets, partial, sums, out, dice_smooth=1.0, w_bce=1.0, w_dice=1.0, w_ft=0.0, ft_alpha=0.4,
+                 ft_beta=0.6, ft_gamma=2.0, ft_smooth=1e-6):
+    B = logits.shape[0]
+    per = logits.numel() // B
+    check(_lib.lib().b2s_seg_loss_fwd(_p(logits), _p(targets), B, per, _p(partial), _p(sums), _p(out), dice_smooth,
+                                      w_bce, w_dice, w_ft, ft_alpha, ft_beta, ft_gamma, ft_smooth, _stream()),
+          "b2s_seg_loss_fwd")
+
+
+def seg_loss_bwd(logits, targets, sums, ft_tot, grad_out, dlogits, dice_smooth=1.0, w_bce=1.0, w_dice=1.0, w_ft=0.0,
+                 ft_alpha=0.4, ft_beta=0.6, ft_gamma=2.0, ft_smooth=1e-6):
+    B = logits.shape[0]
+    per = logits.numel() // B
+    check(_lib.lib().b2s_seg_loss_bwd(_p(logits), _p(targets), _p(sums), _p(ft_tot), B, per, B * per, B,
+                                      _p(grad_out), _p(dlogits), dice_smooth, w_bce, w_dice, w_ft, ft_alpha, ft_beta,
+                                      ft_gamma, ft_smooth, _stream()), "b2s_seg_loss_bwd")
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(_lib.lib().b2s_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                    grad_scale, _stream()), "b2s_adamw_step")
+
+
+def copy_channels(src, dst):
+    npix = src.N * src.H * src.W
+    check(_lib.lib().b2s_copy_channels(src.ptr, src.cstride, dst.ptr, dst.cstride, npix, src.C, _stream()),
+          "b2s_copy_channels")
