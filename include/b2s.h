@@ -78,7 +78,8 @@ int b2s_c1_rows(int N, int H, int W);
 /* its weight gradient: partial [b2s_c1_rows][Cout*9] fp32 (reduce with b2s_reduce_rows). */
 int b2s_conv3x3_c1_wgrad(const float* x, const void* dz, float* partial, int N, int H, int W, int Cout, void* stream);
 
-/* out[k] = sum_r in[r][k]; scratch >= 64*K floats (used when rows > 64). Deterministic. */
+/* out[k] = sum_r in[r][k]; scratch >= 128*K floats (used when rows > 1024; the same rule applies to every
+ * `scratch` argument below with K = the row width of the partial buffer). Deterministic. */
 int b2s_reduce_rows(const float* in, int rows, int K, float* scratch, float* out, void* stream);
 
 /* nn.BatchNorm2d training statistics (models/model.py:38,41): reduces conv-epilogue partials [rows][2][C] over

@@ -1,0 +1,146 @@
+"""Host-side logic of the data-parallel step on CPU: flat bucket layout, gradient-ready order, bucketed all-reduce
+hook (gloo, world_size 2), LR schedule, C-ABI symbol export. No kernels are launched (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import b200seg  # noqa: F401
+from b200seg import _lib
+from b200seg.models.model import UNet
+from b200seg.train import TrainStep, cosine_warm_restarts_lr, grad_ready_order
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b2s.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decls = re.findall(r"\b(b2s_\w+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(decls) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name, args in decls:
+        assert hasattr(lib, name), f"libb2s.so does not export {name}"
+        nargs = 0 if args.strip() in ("", "void") else len(args.split(","))
+        assert name in _lib.SIGNATURES, f"no ctypes binding for {name}"
+        assert len(_lib.SIGNATURES[name][1]) == nargs, f"ctypes arity mismatch for {name}"
+    assert set(_lib.SIGNATURES) == {n for n, _ in decls}
+    # host-only entry points are callable without a GPU
+    L = _lib.lib()
+    assert L.b2s_version() >= 100 and L.b2s_ew_rows() % 148 == 0
+    assert L.b2s_conv_fwd_tiles_m(64, 256, 256) == 64 * 256 * 256 // 128
+    s = ctypes.c_int(0)
+    assert L.b2s_conv_wgrad_workspace(64, 256, 256, 64, 64, 3, 0, 0, ctypes.byref(s)) > 0 and s.value >= 1
+    assert L.b2s_conv_wgrad_workspace(1, 16, 16, 48, 64, 3, 0, 0, ctypes.byref(s)) < 0     # Cin % 64 != 0
+    assert b"unsupported" in L.b2s_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libb2s.so")
+    with pytest.raises(_lib.B2SError):
+        _lib.lib()
+
+
+def test_cpu_tensors_are_rejected():
+    m = UNet()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 32, 32))
+    from b200seg.models.loss import DiceLoss
+    with pytest.raises(RuntimeError):
+        DiceLoss()(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+
+
+def test_grad_ready_order_covers_all_parameters():
+    m = UNet()
+    names = [n for n, _ in m.named_parameters()]
+    order = grad_ready_order()
+    assert sorted(order) == sorted(names) and len(order) == 82
+    assert order[0] == "final.1.weight" and order[-1] == "encoder1.0.weight"
+
+
+def test_bucket_layout():
+    m = UNet()
+    ts = TrainStep(m.state_dict(), "cpu", use_dist=False, bucket_mb=16.0)
+    # buckets tile the flat buffer exactly once, in order
+    assert ts.buckets[0][0] == 0 and ts.buckets[-1][1] == ts.flat_g.numel()
+    for (s0, e0), (s1, e1) in zip(ts.buckets, ts.buckets[1:]):
+        assert e0 == s1 and e0 > s0
+    # parameter views alias the flat buffers and carry the initial values
+    sd = m.state_dict()
+    for k in ts.order:
+        assert torch.equal(ts.P[k], sd[k])
+        assert ts.P[k].data_ptr() >= ts.flat_p.data_ptr() and ts.G[k].data_ptr() % 16 == 0
+    assert sum(ts.P[k].numel() for k in ts.order) == 31042369
+    # each bucket's trigger is the last-ready parameter inside it
+    for b, (s0, e0) in enumerate(ts.buckets):
+        last = ts.bucket_last[b]
+        off = (ts.G[last].data_ptr() - ts.flat_g.data_ptr()) // 4
+        assert s0 <= off < e0
+
+
+def test_cosine_warm_restarts_matches_torch():
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1e-3)
+    sch = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=20, T_mult=2, eta_min=0)
+    for epoch in range(70):
+        assert abs(opt.param_groups[0]["lr"] - cosine_warm_restarts_lr(1e-3, epoch)) < 1e-12
+        opt.step()
+        sch.step()
+
+
+class _FakeEngine:
+    """Stands in for UNetEngine on CPU: 'computes' rank-dependent gradients in gradient-ready order."""
+
+    def __init__(self, rank):
+        self.rank = rank
+        self.calls = []
+
+    def invalidate_packed(self):
+        pass
+
+    def forward(self, P, x, train):
+        return None, None
+
+    def loss(self, pl, t, **kw):
+        return torch.zeros(8)
+
+    def loss_backward(self, pl, t, **kw):
+        return None
+
+    def backward(self, P, pl, dl, G, on_grad_ready=None):
+        for i, k in enumerate(grad_ready_order()):
+            G[k].fill_(float(self.rank + 1) * (1 + i % 7))
+            self.calls.append(k)
+            on_grad_ready(k)
+
+
+def _ddp_worker(rank, world, port, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        sd = UNet().state_dict()
+        ts = TrainStep(sd, "cpu", bucket_mb=8.0, engine=_FakeEngine(rank))
+        assert ts.world == world and len(ts.buckets) > 3
+        ts.forward_backward(torch.zeros(1), torch.zeros(1))
+        # every gradient element now holds the SUM over ranks: (1 + 2) * (1 + i % 7)
+        for i, k in enumerate(ts.order):
+            expect = 3.0 * (1 + i % 7)
+            assert float(ts.G[k].min()) == expect == float(ts.G[k].max()), k
+        assert ts.engine.calls == ts.order
+        open(os.path.join(outdir, f"ok{rank}"), "w").write("1")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2_gloo(tmp_path):
+    world = 2
+    port = 29000 + os.getpid() % 2000
+    mp.spawn(_ddp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]

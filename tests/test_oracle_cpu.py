@@ -142,3 +142,17 @@ def test_rejects_bad_spatial_size(ref_params):
     import pytest
     with pytest.raises(RuntimeError):
         O.unet_forward(ref_params, torch.zeros(1, 1, 40, 40))
+
+
+def test_functional_torch_port_matches_reference(unet_golden, ref_params):
+    """oracle/unet_torch_ref.py (the timed CPU baseline) reproduces the reference module's fp32 numbers."""
+    from oracle import unet_torch_ref as T
+    A = unet_golden["A"]
+    P = T.make_params(ref_params)
+    loss, logits, grads = T.train_step(P, A["x"], A["t"])
+    assert float((logits - A["logits"]).abs().max()) < 1e-6
+    assert abs(float(loss) - A["loss"]) < 1e-6
+    names = [k for k, v in P.items() if v.requires_grad]
+    for k, g in zip(names, grads):
+        ref = A["grads"][k]
+        assert abs(float(g.double().norm()) - ref["norm"]) <= 1e-4 * ref["norm"] + 1e-9, k

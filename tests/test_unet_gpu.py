@@ -1,0 +1,261 @@
+"""Whole-network parity of the B200 path (drop-in UNet module + fused loss, through the C ABI) against
+  (1) the oracle run with q = bf16_round — the same storage-precision model as the kernels, so only fp32
+      accumulation order differs, and
+  (2) the golden vectors of the UNMODIFIED reference (fp32 CPU autograd run, tests/golden/unet_golden.pt).
+Tolerances for (2) follow SURVEY.md App. C: the reference's own bf16-autocast run differs from its fp32 run by
+mean |dlogit| ~1.2e-2 and 2-46 % relative L2 on gradients; we require <= 2x those floors.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def net(ref_params):
+    import b200seg  # noqa: F401
+    from b200seg.models.model import UNet
+    m = UNet()
+    m.load_state_dict(ref_params, strict=True)
+    return m.to(DEV)
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cosine(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def test_train_step_matches_oracle_and_reference(net, unet_golden, ref_params):
+    from b200seg.models.loss import BCEDiceLoss
+    A = unet_golden["A"]
+    net.load_state_dict(ref_params, strict=True)
+    net.train()
+    net.zero_grad(set_to_none=True)
+    x, t = A["x"].to(DEV), A["t"].to(DEV)
+    logits = net(x)
+    loss = BCEDiceLoss()(logits, t)
+    loss.backward()
+    torch.cuda.synchronize()
+
+    # (1) oracle with the kernels' precision model
+    P = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in ref_params.items()}
+    cache = {}
+    lq = O.unet_forward(P, A["x"].double(), train=True, q=O.bf16_round, cache=cache)
+    Lq = O.seg_loss(lq, A["t"].double())
+    Gq = O.unet_backward(P, cache, Lq["dlogits"], q=O.bf16_round)
+
+    lg = logits.detach().cpu().double()
+    d_or = (lg - lq).abs()
+    d_ref = (lg - A["logits"].double()).abs()
+    metrics = {"logits_vs_oracle_bf16": {"mean": float(d_or.mean()), "max": float(d_or.max())},
+               "logits_vs_reference_fp32": {"mean": float(d_ref.mean()), "max": float(d_ref.max())},
+               "loss": float(loss), "loss_oracle_bf16": float(Lq["total"]), "loss_reference": A["loss"], "grads": {}}
+    for k, p in net.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == torch.float32, k
+        ref = A["grads"][k]
+        g = p.grad.detach().cpu()
+        samp = g.flatten()[ref["idx"]]
+        metrics["grads"][k] = {"rel_l2_vs_oracle": rel_l2(g, Gq[k]), "cos_vs_oracle": cosine(g, Gq[k]),
+                               "norm": float(g.double().norm()), "ref_norm": ref["norm"],
+                               "cos_vs_reference_sample": cosine(samp, ref["vals"])}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/unet_parity_metrics.json", "w") as f:
+        json.dump(metrics, f, indent=1)
+
+    # logits: same precision model -> tight; vs fp32 reference -> within 2x the reference's own bf16 noise
+    assert metrics["logits_vs_oracle_bf16"]["mean"] < 6e-3, metrics["logits_vs_oracle_bf16"]
+    assert metrics["logits_vs_reference_fp32"]["mean"] < 2.5e-2, metrics["logits_vs_reference_fp32"]
+    assert abs(float(loss) - float(Lq["total"])) < 1e-3
+    assert abs(float(loss) - A["loss"]) < 5e-3          # bf16 loss tolerance (1.9e-4 observed)
+    # End-to-end gradients at init are ill-conditioned (the reference's OWN bf16-autocast run is
+    # 2-46 % rel. L2 away from its fp32 run at B=4 @ 256^2; this B=2 @ 32^2 case normalises the bottleneck over 8
+    # samples and is worse): ReLU / max-pool routing flips caused by accumulation-order noise dominate. The sharp
+    # backward check is test_backward_given_forward_state below; here we bound the statistical agreement.
+    head = {k: m for k, m in metrics["grads"].items() if k.startswith("final.")}
+    assert all(m["rel_l2_vs_oracle"] < 0.10 and m["cos_vs_oracle"] > 0.995 for m in head.values()), head
+    assert all(m["cos_vs_oracle"] > 0.70 for m in metrics["grads"].values()), metrics["grads"]
+    for k, m in metrics["grads"].items():
+        assert abs(m["norm"] - m["ref_norm"]) <= 0.5 * m["ref_norm"] + 1e-7, (k, m)
+
+    # BatchNorm running statistics after the step (reference values, fp32) and the step counter
+    sd = net.state_dict()
+    for k, v in A["running"].items():
+        if v.is_floating_point():
+            assert float((sd[k].cpu() - v).abs().max()) < 5e-3 * max(1.0, float(v.abs().max())), k
+        else:
+            assert int(sd[k]) == int(v)
+
+
+def _cache_from_plan(plan, x_img):
+    """Oracle backward cache rebuilt from the CUDA forward's saved tensors (all exactly representable in fp64)."""
+    def nchw(a):
+        return a.to_nchw_float().cpu().double()
+    cache = {}
+    for (name, idx), s in plan.stages.items():
+        xin = x_img.double() if s.x is None else nchw(s.x)
+        cache[f"{name}.{idx}"] = dict(x=xin, r=nchw(s.r), mean=s.mean.cpu().double(), invstd=s.invstd.cpu().double(),
+                                      scale=s.scale.cpu().double(), shift=s.shift.cpu().double())
+    for l, enc in enumerate(["encoder1", "encoder2", "encoder3", "encoder4"]):
+        y = nchw(plan.stages[(enc, 3)].y)
+        _, arg = O.maxpool2x2(y)
+        cache[f"{enc}.pool"] = dict(arg=arg, shape=y.shape)
+    for ct, src in (("middle.2", "middle.1"), ("decoder3.1", "decoder3.0"), ("decoder2.1", "decoder2.0"),
+                    ("decoder1.1", "decoder1.0")):
+        cache[ct] = dict(x=nchw(plan.stages[(src, 3)].y))
+    h = plan.stages[("final.0", 3)]
+    cache["head"] = dict(r=nchw(h.r), scale=h.scale.cpu().double(), shift=h.shift.cpu().double())
+    return cache
+
+
+@pytest.mark.parametrize("B,S", [(2, 32), (2, 64)])
+def test_backward_given_forward_state(net, ref_params, B, S):
+    """The backward pass is linear in dlogits once the forward state (ReLU masks, pool argmax, BN statistics) is
+    fixed. Feeding the oracle's explicit backward with the CUDA forward's own saved tensors removes the chaotic
+    routing flips, so every one of the 82 gradients must agree to bf16 rounding noise."""
+    net.load_state_dict(ref_params, strict=True)
+    net.train()
+    net.zero_grad(set_to_none=True)
+    x, t = O.synth_batch(B, S, S, seed=77)
+    xg = x.to(DEV)
+    logits = net(xg)
+    dl = O.seg_loss(logits.detach().cpu().double(), t.double())["dlogits"]
+    logits.backward(dl.float().to(DEV))
+    torch.cuda.synchronize()
+    plan = net._engine.plans[(B, S, S, str(xg.device))]
+    P = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in ref_params.items()}
+    Gq = O.unet_backward(P, _cache_from_plan(plan, x), dl, q=O.bf16_round)
+    res = {k: (rel_l2(p.grad, Gq[k]), cosine(p.grad, Gq[k])) for k, p in net.named_parameters()}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/backward_given_state_{B}x{S}.json", "w") as f:
+        json.dump(res, f, indent=1)
+    bad = {k: v for k, v in res.items() if v[0] > 0.05 or v[1] < 0.998}
+    assert not bad, bad
+
+
+def test_eval_logits_and_mask(net, unet_golden, ref_params):
+    """Inference path (utils/trainer.py:216-217): eval-mode BN with the reference's post-step running stats."""
+    A = unet_golden["A"]
+    sd = dict(ref_params)
+    sd.update(A["running"])
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    logits, mask = net.predict_mask(A["x"].to(DEV))
+    torch.cuda.synchronize()
+    lg = logits.cpu()
+    P = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    lq = O.unet_forward(P, A["x"].double(), train=False, q=O.bf16_round)
+    d = (lg.double() - lq).abs()
+    assert float(d.mean()) < 6e-3, (float(d.mean()), float(d.max()))
+    assert float((lg - A["eval_logits"]).abs().mean()) < 2.5e-2
+    # mask: bit-exact vs the threshold of OUR logits (fused kernel == reference expression on the same logits) ...
+    far = lg.abs() > 1e-6
+    assert torch.equal(mask.cpu().bool()[far], O.threshold_mask(lg)[far])
+    # ... and vs the reference's mask outside the declared bf16 guard band |logit_ref| <= 0.1
+    band = A["eval_logits"].abs() > 0.1
+    n_out = int(band.sum())
+    flips = int((mask.cpu().bool()[band] != A["eval_mask"][band]).sum())
+    assert flips == 0, f"{flips} mask flips outside the guard band ({n_out} pixels outside)"
+    # forward through the module in eval mode under no_grad returns the same logits
+    with torch.no_grad():
+        l2 = net(A["x"].to(DEV))
+    assert torch.equal(l2.cpu(), lg)
+
+
+def test_module_api_contract(net, unet_golden, ref_params):
+    """What utils/trainer.py and test.py touch."""
+    import b200seg  # noqa: F401
+    from b200seg.models.model import UNet
+    assert list(net.state_dict().keys()) == unet_golden["state_dict_keys"]
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == 31042369
+    m2 = UNet(in_channels=1, out_channels=1)
+    missing, unexpected = m2.load_state_dict(net.state_dict(), strict=True)
+    assert not missing and not unexpected
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-5)      # utils/trainer.py:41
+    net.train()
+    x = torch.rand(2, 1, 32, 32, device=DEV)
+    t = (torch.rand(2, 1, 32, 32, device=DEV) > 0.7).float()
+    before = net.final[1].weight.detach().clone()
+    opt.zero_grad()
+    logits = net(x)
+    assert logits.shape == (2, 1, 32, 32) and logits.dtype == torch.float32
+    loss = torch.nn.BCEWithLogitsLoss()(logits, t)           # stock torch loss on our logits (trainer.py:37)
+    (loss * 4.0).backward()                                  # GradScaler-style non-unit upstream gradient
+    opt.step()
+    assert not torch.equal(before, net.final[1].weight.detach())
+    assert float(loss) == float(loss) and float(loss) > 0
+    assert (torch.sigmoid(logits) > 0.5).dtype == torch.bool
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 40, 40, device=DEV))
+    with pytest.raises(RuntimeError):
+        net.cpu()(torch.zeros(1, 1, 32, 32))
+    net.to(DEV)
+
+
+def test_backward_is_linear_in_upstream_gradient(net, ref_params):
+    net.load_state_dict(ref_params, strict=True)
+    net.train()
+    x = torch.rand(2, 1, 32, 32, device=DEV, generator=torch.Generator(DEV).manual_seed(5))
+    go = torch.randn(2, 1, 32, 32, device=DEV, generator=torch.Generator(DEV).manual_seed(6))
+    grads = []
+    for s in (1.0, 3.0):
+        net.load_state_dict(ref_params, strict=True)
+        net.zero_grad(set_to_none=True)
+        net(x).backward(go * s)
+        grads.append({k: p.grad.detach().clone() for k, p in net.named_parameters()})
+    for k in grads[0]:
+        assert rel_l2(grads[1][k], 3.0 * grads[0][k]) < 2e-2, k
+
+
+def test_loss_modules_match_reference(ops_golden):
+    import b200seg  # noqa: F401
+    from b200seg.models.loss import DiceLoss, FocalTverskyLoss, BCEDiceLoss, CompositeLoss, BoundaryLoss
+    g = ops_golden["loss"]
+    lg = g["logits"].float().to(DEV).requires_grad_(True)
+    t = g["targets"].float().to(DEV)
+    assert abs(float(DiceLoss()(lg, t)) - float(g["dice"])) < 2e-6
+    assert abs(float(FocalTverskyLoss()(lg, t)) - float(g["ft"])) < 2e-6
+    total = BCEDiceLoss()(lg, t) + 0.5 * FocalTverskyLoss()(lg, t)
+    total.backward()
+    assert abs(float(total) - float(g["total"])) < 5e-6
+    assert float((lg.grad.cpu().double() - g["dlogits"]).abs().max()) < 1e-6
+    c = CompositeLoss(λ_ft=1.0, λ_b=0.0, λ_bce=1.0, λ_dice=1.0)(lg, t)
+    r = O.seg_loss(g["logits"], g["targets"], w_bce=1, w_dice=1, w_ft=1, ft_alpha=0.3, ft_beta=0.7, ft_gamma=0.75)
+    assert abs(float(c) - float(r["total"])) < 5e-6
+    assert float(BoundaryLoss()(lg, (t > 0.5).float())) >= 0.0
+
+
+def test_full_size_properties(net, ref_params):
+    """BASELINE config shapes (B=4 @ 256^2 here to bound memory/time): size-independent properties —
+    determinism (bit-identical re-run), finite outputs, BN-normalised activations, per-sample independence in eval."""
+    net.load_state_dict(ref_params, strict=True)
+    net.train()
+    x, t = O.synth_batch(4, 256, 256, seed=1234)
+    x, t = x.to(DEV), t.to(DEV)
+    outs = []
+    for _ in range(2):
+        net.load_state_dict(ref_params, strict=True)
+        net.zero_grad(set_to_none=True)
+        lg = net(x)
+        from b200seg.models.loss import BCEDiceLoss
+        BCEDiceLoss()(lg, t).backward()
+        outs.append((lg.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters()}))
+    assert torch.equal(outs[0][0], outs[1][0]), "forward is not deterministic"
+    for k in outs[0][1]:
+        assert torch.equal(outs[0][1][k], outs[1][1][k]), f"backward is not deterministic: {k}"
+        assert bool(torch.isfinite(outs[0][1][k]).all()), k
+    net.eval()
+    with torch.no_grad():
+        full = net(x)
+        half = net(x[:2].contiguous())
+    assert float((full[:2] - half).abs().max()) < 1e-5, "eval-mode samples must be independent of the batch"

@@ -658,9 +658,9 @@ static int wgrad_plan(int N, int H, int W, int Cin, int Cout, int num_taps, int 
   p->chunks_total = p->chunks_w * p->chunks_h * p->chunks_n;
   int splits = splits_req;
   if (splits <= 0) {
-    // fill ~2 CTAs per SM for 2 waves, keep >= 16 K-chunks per CTA
+    // about two CTAs per SM in flight, keep >= 16 K-chunks per CTA (every split costs a K-sized fp32 partial)
     const int base = p->m_tiles * p->tiles_nn;
-    splits = (4 * 148 + base - 1) / base;
+    splits = (2 * 148 + base / 2) / base;
     const int max_by_work = p->chunks_total / 16 > 0 ? p->chunks_total / 16 : 1;
     if (splits > max_by_work) splits = max_by_work;
     if (splits < 1) splits = 1;
@@ -684,7 +684,8 @@ extern "C" long long b2s_conv_wgrad_workspace(int N, int H, int W, int Cin, int 
     return -1;
   }
   if (splits_out) *splits_out = p.splits;
-  return static_cast<long long>(p.splits) * taps * Cin * Cout * 4;
+  // b2s_wgrad_reduce folds > 8 partials through an 8-slot tail region first
+  return static_cast<long long>(p.splits + (p.splits > 8 ? 8 : 0)) * taps * Cin * Cout * 4;
 }
 
 // 3x3 conv weight gradient partials: ws[split][tap*Cin+ci][co] = sum over the split's pixels.

@@ -25,35 +25,58 @@ __device__ __forceinline__ void stg16(void* p, const uint4& v) { *reinterpret_ca
 // ------------------------------------------------------------------------------------------------
 // generic deterministic row reduction: out[k] = sum_r in[r][k]
 // ------------------------------------------------------------------------------------------------
-__global__ void reduce_rows_kernel(const float* __restrict__ in, int rows, int K, int rows_per_slice,
-                                   float* __restrict__ out) {
-  // grid (ceil(K/32), slices); block (32, 8)
-  __shared__ double red[8][33];
+constexpr int kRedY = 32;  // row groups per block of the small reduction kernels (block = 32 x 32 threads)
+
+__global__ void __launch_bounds__(32 * kRedY)
+reduce_rows_kernel(const float* __restrict__ in, int rows, int K, int rows_per_slice, float* __restrict__ out) {
+  // grid (ceil(K/32), slices); block (32, kRedY): lane = column (coalesced), threadIdx.y strides over the rows
+  __shared__ double red[kRedY][33];
   const int k = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_slice;
   const int r1 = min(r0 + rows_per_slice, rows);
   double acc = 0.0;
   if (k < K)
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += static_cast<double>(in[static_cast<size_t>(r) * K + k]);
+    for (int r = r0 + threadIdx.y; r < r1; r += kRedY) acc += static_cast<double>(in[static_cast<size_t>(r) * K + k]);
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && k < K) {
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+    for (int j = 0; j < kRedY; ++j) s += red[j][threadIdx.x];
     out[static_cast<size_t>(blockIdx.y) * K + k] = static_cast<float>(s);
   }
 }
 
-// Reduce [rows][K] down to at most 64 rows (in scratch) when rows > 64; returns pointer/rows to finalize from.
+// Sum of partial[r][which][c] over r for which in {0,1}; block (32, kRedY), channel c = blockIdx.x*32 + threadIdx.x.
+// Result valid in threads with threadIdx.y == 0.
+__device__ __forceinline__ void block_sum_pairs(const float* __restrict__ partial, int rows, int C, int c, double& s,
+                                                double& q) {
+  __shared__ double red[2][kRedY][33];
+  double a0 = 0.0, a1 = 0.0;
+  if (c < C)
+    for (int r = threadIdx.y; r < rows; r += kRedY) {
+      a0 += static_cast<double>(partial[(static_cast<size_t>(r) * 2) * C + c]);
+      a1 += static_cast<double>(partial[(static_cast<size_t>(r) * 2 + 1) * C + c]);
+    }
+  red[0][threadIdx.y][threadIdx.x] = a0;
+  red[1][threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  s = 0.0; q = 0.0;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int j = 0; j < kRedY; ++j) { s += red[0][j][threadIdx.x]; q += red[1][j][threadIdx.x]; }
+  }
+}
+
+// Reduce [rows][K] down to at most 128 rows (in scratch) when rows > 1024; returns pointer/rows to finalize from.
 static int reduce_to_small(const float* in, int rows, int K, float* scratch, const float** out_ptr, int* out_rows,
                            cudaStream_t stream) {
-  if (rows <= 64) { *out_ptr = in; *out_rows = rows; return B2S_OK; }
-  if (!scratch) return set_error(B2S_ERR_ARG, "scratch buffer required for rows > 64");
-  const int slices = 64;
+  if (rows <= 1024) { *out_ptr = in; *out_rows = rows; return B2S_OK; }
+  if (!scratch) return set_error(B2S_ERR_ARG, "scratch buffer required for rows > 1024");
+  const int slices = 128;
   const int rps = (rows + slices - 1) / slices;
   const int used = (rows + rps - 1) / rps;
-  dim3 grid((K + 31) / 32, used), block(32, 8);
+  dim3 grid((K + 31) / 32, used), block(32, kRedY);
   count_launch();
   reduce_rows_kernel<<<grid, block, 0, stream>>>(in, rows, K, rps, scratch);
   int rc = check_launch("reduce_rows_kernel");
@@ -84,19 +107,20 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   float st[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) st[k] = 0.f;
-  const long long npix = static_cast<long long>(N) * H * W;
+  const unsigned npix = static_cast<unsigned>(N) * H * W;   // host guarantees N*H*W < 2^31
   const bool relu = flags & B2S_FLAG_RELU;
-  for (long long p0 = static_cast<long long>(blockIdx.x) * ppi; p0 < npix; p0 += static_cast<long long>(gridDim.x) * ppi) {
-    const long long p = p0 + pl;
+  for (unsigned p0 = blockIdx.x * ppi; p0 < npix; p0 += gridDim.x * ppi) {
+    const unsigned p = p0 + pl;
     if (p < npix) {
-      const int wq = static_cast<int>(p % W);
-      const int hq = static_cast<int>((p / W) % H);
-      const float* xi = x + (p - wq - static_cast<long long>(hq) * W);  // image base
+      const unsigned row = p / W;
+      const int wq = static_cast<int>(p - row * W);
+      const int hq = static_cast<int>(row % H);
+      const float* xi = x + (p - wq - static_cast<unsigned>(hq) * W);  // image base
       float xv[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
-        xv[t] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + static_cast<long long>(hh) * W + ww) : 0.f;
+        xv[t] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + hh * W + ww) : 0.f;
       }
       float acc[8];
 #pragma unroll
@@ -110,7 +134,7 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         st[k] += a;
         st[8 + k] = fmaf(a, a, st[8 + k]);
       }
-      stg16(r + p * Cout + cg * 8, pack8(acc));
+      stg16(r + static_cast<size_t>(p) * Cout + cg * 8, pack8(acc));
     }
   }
   if (stats_partial) {
@@ -143,19 +167,20 @@ conv3x3_c1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
-  const long long npix = static_cast<long long>(N) * H * W;
-  for (long long p0 = static_cast<long long>(blockIdx.x) * ppi; p0 < npix; p0 += static_cast<long long>(gridDim.x) * ppi) {
-    const long long p = p0 + pl;
+  const unsigned npix = static_cast<unsigned>(N) * H * W;
+  for (unsigned p0 = blockIdx.x * ppi; p0 < npix; p0 += gridDim.x * ppi) {
+    const unsigned p = p0 + pl;
     if (p < npix) {
-      const int wq = static_cast<int>(p % W);
-      const int hq = static_cast<int>((p / W) % H);
-      const float* xi = x + (p - wq - static_cast<long long>(hq) * W);
+      const unsigned row = p / W;
+      const int wq = static_cast<int>(p - row * W);
+      const int hq = static_cast<int>(row % H);
+      const float* xi = x + (p - wq - static_cast<unsigned>(hq) * W);
       float g[8];
-      unpack8(ldg16(dz + p * Cout + cg * 8), g);
+      unpack8(ldg16(dz + static_cast<size_t>(p) * Cout + cg * 8), g);
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
-        const float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + static_cast<long long>(hh) * W + ww) : 0.f;
+        const float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + hh * W + ww) : 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(xv, g[k], acc[t][k]);
       }
@@ -184,14 +209,12 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                                    float* scale, float* shift, float* mean_out, float* invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  block_sum_pairs(partial, rows, C, c, s, q);
+  if (threadIdx.y != 0) return;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s += static_cast<double>(partial[(static_cast<size_t>(r) * 2) * C + c]);
-    q += static_cast<double>(partial[(static_cast<size_t>(r) * 2 + 1) * C + c]);
-  }
   const double mean = s / count;
   double var = q / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -227,17 +250,18 @@ __global__ void __launch_bounds__(kThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __restrict__ scale,
                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int y_cs,
                 __nv_bfloat16* __restrict__ pooled, int N, int H, int W, int C) {
-  const int groups = C / 8;
+  const int groups = C / 8;               // power of two (host-checked)
+  const int gshift = __ffs(groups) - 1;
   const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * kThreads;  // multiple of groups
-  const int cg = static_cast<int>(tid % groups);
+  const int cg = static_cast<int>(tid & (groups - 1));
   float sc[8], sh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
   if (!POOL) {
     const long long total = static_cast<long long>(N) * H * W * groups;
     for (long long i = tid; i < total; i += stride) {
-      const long long pix = i / groups;
+      const long long pix = i >> gshift;
       float v[8];
       unpack8(ldg16(r + pix * r_cs + cg * 8), v);
 #pragma unroll
@@ -248,11 +272,12 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __re
     const int Ho = H / 2, Wo = W / 2;
     const long long total = static_cast<long long>(N) * Ho * Wo * groups;
     for (long long i = tid; i < total; i += stride) {
-      const long long pp = i / groups;
-      const int wo = static_cast<int>(pp % Wo);
-      const int ho = static_cast<int>((pp / Wo) % Ho);
-      const long long n = pp / (static_cast<long long>(Wo) * Ho);
-      const long long p00 = (n * H + 2 * ho) * W + 2 * wo;
+      const unsigned pp = static_cast<unsigned>(i >> gshift);   // pooled pixel index < 2^31
+      const unsigned prow = pp / Wo;
+      const int wo = static_cast<int>(pp - prow * Wo);
+      const unsigned n = prow / Ho;
+      const int ho = static_cast<int>(prow - n * Ho);
+      const long long p00 = (static_cast<long long>(n) * H + 2 * ho) * W + 2 * wo;
       float m[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -265,7 +290,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __re
 #pragma unroll
         for (int k = 0; k < 8; ++k) m[k] = q == 0 ? v[k] : fmaxf(m[k], v[k]);
       }
-      stg16(pooled + pp * C + cg * 8, pack8(m));
+      stg16(pooled + static_cast<size_t>(pp) * C + cg * 8, pack8(m));
     }
   }
 }
@@ -284,9 +309,10 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
               int N, int H, int W, int C) {
   __shared__ float red[kThreads * 16];
   const int groups = C / 8;
+  const int gshift = __ffs(groups) - 1;
   const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * kThreads;
-  const int cg = static_cast<int>(tid % groups);
+  const int cg = static_cast<int>(tid & (groups - 1));
   float sc[8], sh[8], mu[8], is[8], c0[8], c1[8], c2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -303,13 +329,14 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
   const int Ho = POOL ? H / 2 : H, Wo = POOL ? W / 2 : W;
   const long long total = static_cast<long long>(N) * Ho * Wo * groups;
   for (long long i = tid; i < total; i += stride) {
-    const long long pp = i / groups;
+    const unsigned pp = static_cast<unsigned>(i >> gshift);
     long long p00 = pp;
     if (POOL) {
-      const int wo = static_cast<int>(pp % Wo);
-      const int ho = static_cast<int>((pp / Wo) % Ho);
-      const long long n = pp / (static_cast<long long>(Wo) * Ho);
-      p00 = (n * H + 2 * ho) * W + 2 * wo;
+      const unsigned prow = pp / Wo;
+      const int wo = static_cast<int>(pp - prow * Wo);
+      const unsigned n = prow / Ho;
+      const int ho = static_cast<int>(prow - n * Ho);
+      p00 = (static_cast<long long>(n) * H + 2 * ho) * W + 2 * wo;
     }
     float rv[Q][8], g[Q][8];
 #pragma unroll
@@ -320,7 +347,7 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
     }
     if (POOL) {
       float dp[8];
-      unpack8(ldg16(dpool + pp * C + cg * 8), dp);
+      unpack8(ldg16(dpool + static_cast<size_t>(pp) * C + cg * 8), dp);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float best = bf16_round(fmaf(rv[0][k], sc[k], sh[k]));
@@ -379,13 +406,10 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        float* dgamma, float* dbeta, float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s += static_cast<double>(partial[(static_cast<size_t>(r) * 2) * C + c]);
-    q += static_cast<double>(partial[(static_cast<size_t>(r) * 2 + 1) * C + c]);
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, q;
+  block_sum_pairs(partial, rows, C, c, s, q);
+  if (threadIdx.y != 0 || c >= C) return;
   if (dgamma) dgamma[c] = static_cast<float>(q);
   if (dbeta) dbeta[c] = static_cast<float>(s);
   coef[c] = (gamma ? gamma[c] : 1.f) * invstd[c];
@@ -432,7 +456,7 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __re
       for (int off = groups >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
       if (cg == 0 && p < npix) {
         const float logit = acc + wf[O * C + o];
-        const long long n = p / HW, hw = p - n * HW;
+        const long long n = static_cast<unsigned>(p) / static_cast<unsigned>(HW), hw = p - n * HW;
         const long long oi = (n * O + o) * HW + hw;
         logits[oi] = logit;
         if (mask) mask[oi] = (1.f / (1.f + expf(-logit))) > 0.5f ? 1 : 0;
@@ -468,7 +492,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restri
          p0 += static_cast<long long>(gridDim.x) * ppi) {
       const long long p = p0 + threadIdx.x / groups;
       if (p < npix) {
-        const long long n = p / HW, hw = p - n * HW;
+        const long long n = static_cast<unsigned>(p) / static_cast<unsigned>(HW), hw = p - n * HW;
         const float g = dlogits[(n * O + o) * HW + hw];
         float v[8];
         unpack8(ldg16(r + p * r_cs + cg * 8), v);
@@ -701,41 +725,47 @@ __global__ void pack_convt_weight_kernel(const float* __restrict__ w, __nv_bfloa
   }
 }
 
-// ws [splits][taps][Cin][Cout] -> layout 0: dw[co][ci][t]; layout 1: dw[ci][co][t]
+// ws [splits][taps][Cin][Cout] -> layout 0: dw[co][ci][t]; layout 1: dw[ci][co][t].
+// Block = 8 ci x 128 co x all taps; each thread streams `taps` independent float4 columns over the splits.
 __global__ void __launch_bounds__(kThreads)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int Cin, int Cout, float* __restrict__ dw,
                     int layout) {
-  __shared__ float tile[9][32][33];
-  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const size_t split_stride = static_cast<size_t>(taps) * Cin * Cout;
-  for (int t = 0; t < taps; ++t)
-    for (int cil = ty; cil < 32; cil += 8) {
-      const int ci = ci0 + cil, co = co0 + tx;
-      float s = 0.f;
-      if (ci < Cin && co < Cout) {
-        const float* src = ws + (static_cast<size_t>(t) * Cin + ci) * Cout + co;
-        for (int sp = 0; sp < splits; ++sp) s += src[sp * split_stride];
-      }
-      tile[t][cil][tx] = s;
+  __shared__ float tile[9][8][129];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ci0 = blockIdx.x * 8, co0 = blockIdx.y * 128;
+  const int ci = ci0 + ty, co = co0 + tx * 4;
+  const size_t tap_stride = static_cast<size_t>(Cin) * Cout;
+  const size_t split_stride = static_cast<size_t>(taps) * tap_stride;
+  float4 acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ci < Cin && co < Cout) {
+    const float* base = ws + static_cast<size_t>(ci) * Cout + co;
+    for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        if (t < taps) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(base + sp * split_stride + t * tap_stride));
+          acc[t].x += v.x; acc[t].y += v.y; acc[t].z += v.z; acc[t].w += v.w;
+        }
     }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    tile[t][ty][tx * 4 + 0] = acc[t].x; tile[t][ty][tx * 4 + 1] = acc[t].y;
+    tile[t][ty][tx * 4 + 2] = acc[t].z; tile[t][ty][tx * 4 + 3] = acc[t].w;
+  }
   __syncthreads();
+  const int nci = min(8, Cin - ci0), nco = min(128, Cout - co0);
   if (layout == 0) {
-    // for each co: contiguous run of 32 ci x taps
-    for (int col = ty; col < 32; col += 8) {
-      const int co = co0 + col;
-      if (co >= Cout) continue;
-      float* dst = dw + (static_cast<size_t>(co) * Cin + ci0) * taps;
-      const int n = min(32, Cin - ci0) * taps;
-      for (int i = tx; i < n; i += 32) dst[i] = tile[i % taps][i / taps][col];
+    for (int col = ty; col < nco; col += 8) {         // one warp per output channel: nci*taps contiguous floats
+      float* dst = dw + (static_cast<size_t>(co0 + col) * Cin + ci0) * taps;
+      for (int i = tx; i < nci * taps; i += 32) dst[i] = tile[i % taps][i / taps][col];
     }
   } else {
-    for (int cil = ty; cil < 32; cil += 8) {
-      const int ci = ci0 + cil;
-      if (ci >= Cin) continue;
-      float* dst = dw + (static_cast<size_t>(ci) * Cout + co0) * taps;
-      const int n = min(32, Cout - co0) * taps;
-      for (int i = tx; i < n; i += 32) dst[i] = tile[i % taps][cil][i / taps];
+    if (ty < nci) {                                    // one warp per input channel: nco*taps contiguous floats
+      float* dst = dw + (static_cast<size_t>(ci0 + ty) * Cout + co0) * taps;
+      for (int i = tx; i < nco * taps; i += 32) dst[i] = tile[i % taps][ty][i / taps];
     }
   }
 }
@@ -764,7 +794,7 @@ copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_bfl
   const long long total = npix * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kThreads) {
-    const long long pix = i / groups;
+    const long long pix = static_cast<unsigned long long>(i) / static_cast<unsigned>(groups);
     const int cg = static_cast<int>(i - pix * groups);
     stg16(dst + pix * dst_cs + cg * 8, ldg16(src + pix * src_cs + cg * 8));
   }
@@ -792,7 +822,7 @@ extern "C" int b2s_reduce_rows(const float* in, int rows, int K, float* scratch,
   const float* src; int r;
   int rc = reduce_to_small(in, rows, K, scratch, &src, &r, STREAM(stream));
   if (rc) return rc;
-  dim3 grid((K + 31) / 32, 1), block(32, 8);
+  dim3 grid((K + 31) / 32, 1), block(32, kRedY);
   count_launch();
   reduce_rows_kernel<<<grid, block, 0, STREAM(stream)>>>(src, r, K, r, out);
   return check_launch("reduce_rows_kernel");
@@ -808,6 +838,7 @@ extern "C" int b2s_conv3x3_c1_fwd(const float* x, const float* w, const float* b
   if (!x || !w || !r) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: null pointer");
   if (!ew_channels_ok(Cout) || Cout > 128) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: unsupported Cout");
   if ((flags & B2S_FLAG_STATS) && !stats_partial) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: stats missing");
+  if (static_cast<long long>(N) * H * W >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: N*H*W >= 2^31");
   const int grid = b2s_c1_rows(N, H, W);
   count_launch();
   conv3x3_c1_fwd_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(
@@ -839,7 +870,7 @@ extern "C" int b2s_bn_finalize(const float* partial, int rows, int C, double cou
   int rc = reduce_to_small(partial, rows, 2 * C, scratch, &src, &r, STREAM(stream));
   if (rc) return rc;
   count_launch();
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM(stream)>>>(src, r, C, count, gamma, beta, running_mean,
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, STREAM(stream)>>>(src, r, C, count, gamma, beta, running_mean,
                                                                   running_var, num_batches_tracked, momentum, eps,
                                                                   scale, shift, mean, invstd);
   return check_launch("bn_finalize_kernel");
@@ -860,6 +891,7 @@ extern "C" int b2s_bn_apply(const void* r, int r_cstride, const float* scale, co
   if (!r || !scale || !shift || !y) return set_error(B2S_ERR_ARG, "b2s_bn_apply: null pointer");
   if (!ew_channels_ok(C)) return set_error(B2S_ERR_ARG, "b2s_bn_apply: C/8 must be a power of two <= 256");
   if (r_cstride % 8 || y_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_bn_apply: strides must be multiples of 8");
+  if (static_cast<long long>(N) * H * W >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_bn_apply: N*H*W >= 2^31");
   const auto* rp = static_cast<const __nv_bfloat16*>(r);
   auto* yp = static_cast<__nv_bfloat16*>(y);
   count_launch();
@@ -882,6 +914,7 @@ extern "C" int b2s_bn_bwd_reduce(const void* dy, int dy_cstride, const void* dpo
   if (!dy || !r || !mean || !invstd || !partial) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: null pointer");
   if (!ew_channels_ok(C)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: unsupported C");
   if (dpool && (!scale || !shift || H % 2 || W % 2)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: pool args");
+  if (static_cast<long long>(N) * H * W >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: N*H*W >= 2^31");
   const auto* dyp = static_cast<const __nv_bfloat16*>(dy);
   const auto* rp = static_cast<const __nv_bfloat16*>(r);
   count_launch();
@@ -904,7 +937,7 @@ extern "C" int b2s_bn_bwd_finalize(const float* partial, int rows, int C, double
   int rc = reduce_to_small(partial, rows, 2 * C, scratch, &src, &r, STREAM(stream));
   if (rc) return rc;
   count_launch();
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM(stream)>>>(src, r, C, count, gamma, invstd, dgamma, dbeta,
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, STREAM(stream)>>>(src, r, C, count, gamma, invstd, dgamma, dbeta,
                                                                       coef);
   return check_launch("bn_bwd_finalize_kernel");
 }
@@ -917,6 +950,7 @@ extern "C" int b2s_bn_bwd_apply(const void* dy, int dy_cstride, const void* dpoo
     return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: null pointer");
   if (!ew_channels_ok(C)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: unsupported C");
   if (dpool && (!scale || !shift || H % 2 || W % 2)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: pool args");
+  if (static_cast<long long>(N) * H * W >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: N*H*W >= 2^31");
   const auto* dyp = static_cast<const __nv_bfloat16*>(dy);
   const auto* rp = static_cast<const __nv_bfloat16*>(r);
   auto* dzp = static_cast<__nv_bfloat16*>(dz);
@@ -938,6 +972,7 @@ extern "C" int b2s_head_fwd(const void* r, int r_cstride, const float* scale, co
   if (!r || !w || !logits) return set_error(B2S_ERR_ARG, "b2s_head_fwd: null pointer");
   if (C % 8 || !pow2(C / 8) || C / 8 > 32) return set_error(B2S_ERR_ARG, "b2s_head_fwd: C/8 must be a power of 2 <= 32");
   if (O < 1 || O > 64) return set_error(B2S_ERR_ARG, "b2s_head_fwd: unsupported out_channels");
+  if (static_cast<long long>(N) * HW >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_head_fwd: N*H*W >= 2^31");
   const long long npix = static_cast<long long>(N) * HW;
   const int ppi = kThreads / (C / 8);
   count_launch();
@@ -952,6 +987,7 @@ extern "C" int b2s_head_bwd(const float* dlogits, const void* r, int r_cstride, 
   if (!dlogits || !r || !w || !dy || !partial) return set_error(B2S_ERR_ARG, "b2s_head_bwd: null pointer");
   if (C % 8 || !pow2(C / 8) || C / 8 > 32) return set_error(B2S_ERR_ARG, "b2s_head_bwd: C/8 must be a power of 2 <= 32");
   if (O < 1 || O > 64) return set_error(B2S_ERR_ARG, "b2s_head_bwd: unsupported out_channels");
+  if (static_cast<long long>(N) * HW >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_head_bwd: N*H*W >= 2^31");
   count_launch();
   head_bwd_kernel<<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(dlogits, static_cast<const __nv_bfloat16*>(r), r_cstride,
                                                              scale, shift, w, static_cast<__nv_bfloat16*>(dy),
@@ -1023,7 +1059,22 @@ extern "C" int b2s_wgrad_reduce(const float* ws, int splits, int taps, int Cin, 
                                 void* stream) {
   if (!ws || !dw) return set_error(B2S_ERR_ARG, "b2s_wgrad_reduce: null pointer");
   if (taps < 1 || taps > 9 || splits < 1) return set_error(B2S_ERR_ARG, "b2s_wgrad_reduce: bad taps/splits");
-  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
+  if (Cout % 4) return set_error(B2S_ERR_ARG, "b2s_wgrad_reduce: Cout must be a multiple of 4");
+  const long long K = static_cast<long long>(taps) * Cin * Cout;
+  if (splits > 8) {
+    // many small partials (shallow layers): first fold them 8-ways into the workspace tail [splits*K, (splits+8)*K)
+    const int rps = (splits + 7) / 8;
+    const int used = (splits + rps - 1) / rps;
+    float* tail = const_cast<float*>(ws) + static_cast<size_t>(splits) * K;
+    dim3 grid(static_cast<unsigned>((K + 31) / 32), used), block(32, kRedY);
+    count_launch();
+    reduce_rows_kernel<<<grid, block, 0, STREAM(stream)>>>(ws, splits, static_cast<int>(K), rps, tail);
+    int rc = check_launch("reduce_rows_kernel");
+    if (rc) return rc;
+    ws = tail;
+    splits = used;
+  }
+  dim3 grid((Cin + 7) / 8, (Cout + 127) / 128);
   count_launch();
   wgrad_reduce_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(ws, splits, taps, Cin, Cout, dw, layout);
   return check_launch("wgrad_reduce_kernel");

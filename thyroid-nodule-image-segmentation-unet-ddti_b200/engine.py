@@ -88,7 +88,7 @@ class UNetPlan:
         self.stats_partial = torch.empty(max(rows0 * 2 * 128, ops.c1_rows(N, H, W) * 2 * 64), **f32)
         self.ew_partial = torch.empty(ops.ew_rows() * 2 * 1024, **f32)
         self.c1_partial = torch.empty(ops.c1_rows(N, H, W) * 64 * 9, **f32)
-        self.scratch = torch.empty(64 * 2 * 1024, **f32)
+        self.scratch = torch.empty(128 * 2 * 2048, **f32)
         self.coef = torch.empty(3 * 1024, **f32)
         self.tmp_vec = torch.empty(2 * 1024, **f32)
         # loss
@@ -144,6 +144,11 @@ class UNetEngine:
         if train:
             p._alloc_train()
         return p
+
+    def invalidate_packed(self):
+        """Call after parameters were updated outside torch (e.g. by b2s_adamw_step, which does not bump tensor
+        version counters): forces the next forward to re-pack the bf16 operands."""
+        self._packed_versions = None
 
     def _pack_weights(self, P, need_dgrad):
         """fp32 parameters -> bf16 GEMM operands; cached on the parameters' version counters."""

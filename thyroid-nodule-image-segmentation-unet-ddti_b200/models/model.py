@@ -20,9 +20,8 @@ class _UNetFunction(torch.autograd.Function):
     """Whole-network autograd node: forward and backward are single passes through the engine."""
 
     @staticmethod
-    def forward(ctx, x, module, names, *params):
+    def forward(ctx, x, module, names, need_bwd, *params):
         P = module._tensor_dict()
-        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         logits, plan = module._engine.forward(P, x, train=module.training, need_backward=need_bwd)
         ctx.module, ctx.plan, ctx.generation, ctx.names = module, plan, plan.generation, names
         ctx.train_stats = module.training
@@ -40,7 +39,7 @@ class _UNetFunction(torch.autograd.Function):
         P = module._tensor_dict()
         G = {n: torch.empty_like(P[n], dtype=torch.float32) for n in ctx.names}
         module._engine.backward(P, plan, dlogits, G)
-        return (None, None, None) + tuple(G[n] for n in ctx.names)
+        return (None, None, None, None) + tuple(G[n] for n in ctx.names)
 
 
 class UNet(nn.Module):
@@ -85,7 +84,9 @@ class UNet(nn.Module):
             raise RuntimeError("UNet parameters and input are on different devices; call model.to(device)")
         if torch.is_autocast_enabled():
             x = x.float()
-        return _UNetFunction.apply(x, self, names, *params)
+        # grad mode is off inside Function.forward, so decide here whether backward buffers are needed
+        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _UNetFunction.apply(x, self, names, need_bwd, *params)
 
     @torch.no_grad()
     def predict_mask(self, x):

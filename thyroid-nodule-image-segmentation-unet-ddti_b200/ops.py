@@ -9,6 +9,21 @@ from ._lib import B2S_FLAG_RELU, B2S_FLAG_STATS, check
 
 BF16 = torch.bfloat16
 
+# When set to a list, every wrapper below appends (name, kind, work, start_event, end_event): kind "tensor" ->
+# work = algorithmic FLOPs, kind "hbm" -> work = algorithmic bytes. Used by bench.py's roofline pass.
+PROFILE = None
+
+
+def _timed(name, kind, work, fn):
+    if PROFILE is None:
+        return fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    r = fn()
+    e.record()
+    PROFILE.append((name, kind, float(work), s, e))
+    return r
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -86,7 +101,8 @@ def pack_conv_weight(w, want_dgrad=True):
     w = w.detach().contiguous().float()
     wf = torch.empty((k * k, Cout, Cin), dtype=BF16, device=w.device)
     wd = torch.empty((k * k, Cin, Cout), dtype=BF16, device=w.device) if want_dgrad else None
-    check(_lib.lib().b2s_pack_conv_weight(_p(w), _p(wf), _p(wd), Cout, Cin, k, _stream()), "pack_conv_weight")
+    _timed("pack_conv_weight", "hbm", w.numel() * (4.0 + 2.0 * (2 if want_dgrad else 1)), lambda: check(
+        _lib.lib().b2s_pack_conv_weight(_p(w), _p(wf), _p(wd), Cout, Cin, k, _stream()), "pack_conv_weight"))
     return wf, wd
 
 
@@ -97,7 +113,8 @@ def pack_convt_weight(w):
     w = w.detach().contiguous().float()
     wf = torch.empty((4 * Cout, Cin), dtype=BF16, device=w.device)
     wd = torch.empty((4 * Cin, Cout), dtype=BF16, device=w.device)
-    check(_lib.lib().b2s_pack_convt_weight(_p(w), _p(wf), _p(wd), Cin, Cout, _stream()), "pack_convt_weight")
+    _timed("pack_convt_weight", "hbm", w.numel() * 8.0, lambda: check(
+        _lib.lib().b2s_pack_convt_weight(_p(w), _p(wf), _p(wd), Cin, Cout, _stream()), "pack_convt_weight"))
     return wf, wd
 
 
@@ -108,8 +125,10 @@ def conv_fwd(x, w_packed, bias, y, ksize=3, relu=False, stats=None, tile_n=0):
     """y = conv(x, w) (+bias)(+ReLU); stats: fp32 [tiles_m, 2, Cout] partial buffer or None."""
     flags = (B2S_FLAG_RELU if relu else 0) | (B2S_FLAG_STATS if stats is not None else 0)
     Cout = y.C
-    check(_lib.lib().b2s_conv_fwd(x.ptr, x.cstride, _p(w_packed), _p(bias), y.ptr, y.cstride, _p(stats), x.N, x.H,
-                                  x.W, x.C, Cout, ksize, flags, tile_n, _stream()), "b2s_conv_fwd")
+    flops = 2.0 * x.N * x.H * x.W * x.C * Cout * ksize * ksize
+    _timed(f"conv{ksize}x{ksize}[{x.C}->{Cout}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
+        _lib.lib().b2s_conv_fwd(x.ptr, x.cstride, _p(w_packed), _p(bias), y.ptr, y.cstride, _p(stats), x.N, x.H,
+                                x.W, x.C, Cout, ksize, flags, tile_n, _stream()), "b2s_conv_fwd"))
 
 
 def conv_tiles_m(N, H, W):
@@ -117,13 +136,17 @@ def conv_tiles_m(N, H, W):
 
 
 def convt_fwd(x, w_packed, bias, y, tile_n=0):
-    check(_lib.lib().b2s_convt2x2_fwd(x.ptr, x.cstride, _p(w_packed), _p(bias), y.ptr, y.cstride, x.N, x.H, x.W, x.C,
-                                      y.C, tile_n, _stream()), "b2s_convt2x2_fwd")
+    flops = 8.0 * x.N * x.H * x.W * x.C * y.C
+    _timed(f"convT_fwd[{x.C}->{y.C}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
+        _lib.lib().b2s_convt2x2_fwd(x.ptr, x.cstride, _p(w_packed), _p(bias), y.ptr, y.cstride, x.N, x.H, x.W, x.C,
+                                    y.C, tile_n, _stream()), "b2s_convt2x2_fwd"))
 
 
 def convt_dgrad(dy, w_packed_d, dx, tile_n=0):
-    check(_lib.lib().b2s_convt2x2_dgrad(dy.ptr, dy.cstride, _p(w_packed_d), dx.ptr, dx.cstride, dx.N, dx.H, dx.W,
-                                        dx.C, dy.C, tile_n, _stream()), "b2s_convt2x2_dgrad")
+    flops = 8.0 * dx.N * dx.H * dx.W * dx.C * dy.C
+    _timed(f"convT_dgrad[{dx.C}<-{dy.C}@{dx.H}x{dx.W}]", "tensor", flops, lambda: check(
+        _lib.lib().b2s_convt2x2_dgrad(dy.ptr, dy.cstride, _p(w_packed_d), dx.ptr, dx.cstride, dx.N, dx.H, dx.W,
+                                      dx.C, dy.C, tile_n, _stream()), "b2s_convt2x2_dgrad"))
 
 
 def wgrad_workspace(N, H, W, Cin, Cout, taps, tile_n=0, splits=0):
@@ -140,9 +163,12 @@ def conv3x3_wgrad(x, dz, ws, dw, tile_n=0, splits=0):
     nbytes, s = wgrad_workspace(x.N, x.H, x.W, x.C, dz.C, 9, tile_n, splits)
     assert ws.numel() * 4 >= nbytes, "wgrad workspace too small"
     L = _lib.lib()
-    check(L.b2s_conv3x3_wgrad(x.ptr, x.cstride, dz.ptr, dz.cstride, _p(ws), x.N, x.H, x.W, x.C, dz.C, tile_n, splits,
-                              _stream()), "b2s_conv3x3_wgrad")
-    check(L.b2s_wgrad_reduce(_p(ws), s, 9, x.C, dz.C, _p(dw), 0, _stream()), "b2s_wgrad_reduce")
+    flops = 18.0 * x.N * x.H * x.W * x.C * dz.C
+    _timed(f"wgrad3x3[{x.C}->{dz.C}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
+        L.b2s_conv3x3_wgrad(x.ptr, x.cstride, dz.ptr, dz.cstride, _p(ws), x.N, x.H, x.W, x.C, dz.C, tile_n, splits,
+                            _stream()), "b2s_conv3x3_wgrad"))
+    _timed("wgrad_reduce", "hbm", 4.0 * 9 * x.C * dz.C * (s + 1), lambda: check(
+        L.b2s_wgrad_reduce(_p(ws), s, 9, x.C, dz.C, _p(dw), 0, _stream()), "b2s_wgrad_reduce"))
 
 
 def convt_wgrad(x, dy, ws, dw, tile_n=0, splits=0):
@@ -150,9 +176,12 @@ def convt_wgrad(x, dy, ws, dw, tile_n=0, splits=0):
     nbytes, s = wgrad_workspace(x.N, x.H, x.W, x.C, dy.C, 4, tile_n, splits)
     assert ws.numel() * 4 >= nbytes, "wgrad workspace too small"
     L = _lib.lib()
-    check(L.b2s_convt2x2_wgrad(x.ptr, x.cstride, dy.ptr, dy.cstride, _p(ws), x.N, x.H, x.W, x.C, dy.C, tile_n, splits,
-                               _stream()), "b2s_convt2x2_wgrad")
-    check(L.b2s_wgrad_reduce(_p(ws), s, 4, x.C, dy.C, _p(dw), 1, _stream()), "b2s_wgrad_reduce")
+    flops = 8.0 * x.N * x.H * x.W * x.C * dy.C
+    _timed(f"convT_wgrad[{x.C}->{dy.C}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
+        L.b2s_convt2x2_wgrad(x.ptr, x.cstride, dy.ptr, dy.cstride, _p(ws), x.N, x.H, x.W, x.C, dy.C, tile_n, splits,
+                             _stream()), "b2s_convt2x2_wgrad"))
+    _timed("wgrad_reduce", "hbm", 4.0 * 4 * x.C * dy.C * (s + 1), lambda: check(
+        L.b2s_wgrad_reduce(_p(ws), s, 4, x.C, dy.C, _p(dw), 1, _stream()), "b2s_wgrad_reduce"))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -167,15 +196,19 @@ def conv3x3_c1_fwd(x, w, bias, r, relu=True, stats=None):
     assert x.dtype == torch.float32 and x.is_contiguous()
     flags = (B2S_FLAG_RELU if relu else 0) | (B2S_FLAG_STATS if stats is not None else 0)
     assert r.c0 == 0 and r.C == r.cstride
-    check(_lib.lib().b2s_conv3x3_c1_fwd(_p(x), _p(w), _p(bias), r.ptr, _p(stats), r.N, r.H, r.W, r.C, flags,
-                                        _stream()), "b2s_conv3x3_c1_fwd")
+    npix = r.N * r.H * r.W
+    _timed("conv3x3_c1_fwd", "hbm", npix * (4.0 + 2.0 * r.C), lambda: check(
+        _lib.lib().b2s_conv3x3_c1_fwd(_p(x), _p(w), _p(bias), r.ptr, _p(stats), r.N, r.H, r.W, r.C, flags,
+                                      _stream()), "b2s_conv3x3_c1_fwd"))
 
 
 def conv3x3_c1_wgrad(x, dz, partial, scratch, dw):
     assert dz.c0 == 0 and dz.C == dz.cstride
     L = _lib.lib()
     rows = L.b2s_c1_rows(dz.N, dz.H, dz.W)
-    check(L.b2s_conv3x3_c1_wgrad(_p(x), dz.ptr, _p(partial), dz.N, dz.H, dz.W, dz.C, _stream()), "c1_wgrad")
+    npix = dz.N * dz.H * dz.W
+    _timed("conv3x3_c1_wgrad", "hbm", npix * (4.0 + 2.0 * dz.C), lambda: check(
+        L.b2s_conv3x3_c1_wgrad(_p(x), dz.ptr, _p(partial), dz.N, dz.H, dz.W, dz.C, _stream()), "c1_wgrad"))
     check(L.b2s_reduce_rows(_p(partial), rows, dz.C * 9, _p(scratch), _p(dw), _stream()), "reduce_rows")
 
 
@@ -200,9 +233,11 @@ def bn_eval_affine(gamma, beta, rm, rv, eps, scale, shift):
 
 
 def bn_apply(r, scale, shift, y, pooled=None):
-    check(_lib.lib().b2s_bn_apply(r.ptr, r.cstride, _p(scale), _p(shift), y.ptr, y.cstride,
-                                  pooled.ptr if pooled is not None else None, r.N, r.H, r.W, r.C, _stream()),
-          "b2s_bn_apply")
+    nbytes = r.N * r.H * r.W * r.C * 2.0 * (2.25 if pooled is not None else 2.0)
+    _timed("bn_apply_pool" if pooled is not None else "bn_apply", "hbm", nbytes, lambda: check(
+        _lib.lib().b2s_bn_apply(r.ptr, r.cstride, _p(scale), _p(shift), y.ptr, y.cstride,
+                                pooled.ptr if pooled is not None else None, r.N, r.H, r.W, r.C, _stream()),
+        "b2s_bn_apply"))
 
 
 def bn_bwd(dy, dpool, r, scale, shift, mean, invstd, gamma, count, dz, partial, scratch, coef, dgamma, dbeta, dbias):
@@ -211,29 +246,37 @@ def bn_bwd(dy, dpool, r, scale, shift, mean, invstd, gamma, count, dz, partial, 
     rows = L.b2s_ew_rows()
     C = r.C
     dp = dpool.ptr if dpool is not None else None
-    check(L.b2s_bn_bwd_reduce(dy.ptr, dy.cstride, dp, r.ptr, r.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
-                              _p(partial), r.N, r.H, r.W, C, _stream()), "b2s_bn_bwd_reduce")
+    nel = r.N * r.H * r.W * C * 2.0
+    extra = 0.25 if dpool is not None else 0.0
+    _timed("bn_bwd_reduce", "hbm", nel * (2.0 + extra), lambda: check(
+        L.b2s_bn_bwd_reduce(dy.ptr, dy.cstride, dp, r.ptr, r.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
+                            _p(partial), r.N, r.H, r.W, C, _stream()), "b2s_bn_bwd_reduce"))
     check(L.b2s_bn_bwd_finalize(_p(partial), rows, C, float(count), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta),
                                 _p(coef), _p(scratch), _stream()), "b2s_bn_bwd_finalize")
-    check(L.b2s_bn_bwd_apply(dy.ptr, dy.cstride, dp, r.ptr, r.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
-                             _p(coef), dz.ptr, dz.cstride, _p(partial), r.N, r.H, r.W, C, _stream()),
-          "b2s_bn_bwd_apply")
+    _timed("bn_bwd_apply", "hbm", nel * (3.0 + extra), lambda: check(
+        L.b2s_bn_bwd_apply(dy.ptr, dy.cstride, dp, r.ptr, r.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
+                           _p(coef), dz.ptr, dz.cstride, _p(partial), r.N, r.H, r.W, C, _stream()),
+        "b2s_bn_bwd_apply"))
     check(L.b2s_reduce_rows(_p(partial), rows, C, _p(scratch), _p(dbias), _stream()), "b2s_reduce_rows")
 
 
 def head_fwd(r, scale, shift, w, b, logits, mask=None):
     """logits [N,O,H,W] fp32 = conv1x1(BN(r)); mask uint8 optional."""
     O = logits.shape[1]
-    check(_lib.lib().b2s_head_fwd(r.ptr, r.cstride, _p(scale), _p(shift), _p(w), _p(b), _p(logits), _p(mask), r.N,
-                                  r.H * r.W, r.C, O, _stream()), "b2s_head_fwd")
+    npix = r.N * r.H * r.W
+    _timed("head_fwd", "hbm", npix * (2.0 * r.C + 4.0 * O + (O if mask is not None else 0)), lambda: check(
+        _lib.lib().b2s_head_fwd(r.ptr, r.cstride, _p(scale), _p(shift), _p(w), _p(b), _p(logits), _p(mask), r.N,
+                                r.H * r.W, r.C, O, _stream()), "b2s_head_fwd"))
 
 
 def head_bwd(dlogits, r, scale, shift, w, dy, partial, scratch, dw_db):
     """dy (Act) and dw_db fp32 [O*C+O] (weight grad then bias grad)."""
     L = _lib.lib()
     O = dlogits.shape[1]
-    check(L.b2s_head_bwd(_p(dlogits), r.ptr, r.cstride, _p(scale), _p(shift), _p(w), dy.ptr, dy.cstride, _p(partial),
-                         r.N, r.H * r.W, r.C, O, _stream()), "b2s_head_bwd")
+    npix = r.N * r.H * r.W
+    _timed("head_bwd", "hbm", npix * (4.0 * r.C + 4.0 * O), lambda: check(
+        L.b2s_head_bwd(_p(dlogits), r.ptr, r.cstride, _p(scale), _p(shift), _p(w), dy.ptr, dy.cstride, _p(partial),
+                       r.N, r.H * r.W, r.C, O, _stream()), "b2s_head_bwd"))
     check(L.b2s_reduce_rows(_p(partial), L.b2s_ew_rows(), O * r.C + O, _p(scratch), _p(dw_db), _stream()),
           "b2s_reduce_rows")
 
@@ -246,23 +289,26 @@ def seg_loss_fwd(logits, targets, partial, sums, out, dice_smooth=1.0, w_bce=1.0
                  ft_beta=0.6, ft_gamma=2.0, ft_smooth=1e-6):
     B = logits.shape[0]
     per = logits.numel() // B
-    check(_lib.lib().b2s_seg_loss_fwd(_p(logits), _p(targets), B, per, _p(partial), _p(sums), _p(out), dice_smooth,
-                                      w_bce, w_dice, w_ft, ft_alpha, ft_beta, ft_gamma, ft_smooth, _stream()),
-          "b2s_seg_loss_fwd")
+    _timed("seg_loss_fwd", "hbm", 8.0 * B * per, lambda: check(
+        _lib.lib().b2s_seg_loss_fwd(_p(logits), _p(targets), B, per, _p(partial), _p(sums), _p(out), dice_smooth,
+                                    w_bce, w_dice, w_ft, ft_alpha, ft_beta, ft_gamma, ft_smooth, _stream()),
+        "b2s_seg_loss_fwd"))
 
 
 def seg_loss_bwd(logits, targets, sums, ft_tot, grad_out, dlogits, dice_smooth=1.0, w_bce=1.0, w_dice=1.0, w_ft=0.0,
                  ft_alpha=0.4, ft_beta=0.6, ft_gamma=2.0, ft_smooth=1e-6):
     B = logits.shape[0]
     per = logits.numel() // B
-    check(_lib.lib().b2s_seg_loss_bwd(_p(logits), _p(targets), _p(sums), _p(ft_tot), B, per, B * per, B,
-                                      _p(grad_out), _p(dlogits), dice_smooth, w_bce, w_dice, w_ft, ft_alpha, ft_beta,
-                                      ft_gamma, ft_smooth, _stream()), "b2s_seg_loss_bwd")
+    _timed("seg_loss_bwd", "hbm", 12.0 * B * per, lambda: check(
+        _lib.lib().b2s_seg_loss_bwd(_p(logits), _p(targets), _p(sums), _p(ft_tot), B, per, B * per, B,
+                                    _p(grad_out), _p(dlogits), dice_smooth, w_bce, w_dice, w_ft, ft_alpha, ft_beta,
+                                    ft_gamma, ft_smooth, _stream()), "b2s_seg_loss_bwd"))
 
 
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
-    check(_lib.lib().b2s_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
-                                    grad_scale, _stream()), "b2s_adamw_step")
+    _timed("adamw", "hbm", 28.0 * p.numel(), lambda: check(
+        _lib.lib().b2s_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                  grad_scale, _stream()), "b2s_adamw_step"))
 
 
 def copy_channels(src, dst):

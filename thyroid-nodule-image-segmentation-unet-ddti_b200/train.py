@@ -1,0 +1,127 @@
+"""Data-parallel training step of the UNet hot path without autograd: forward -> fused Dice+BCE -> backward ->
+bucketed gradient all-reduce (NCCL over NVLink, overlapped with the remaining backward) -> fused AdamW over flat
+fp32 buckets. Replaces the body of the reference's Trainer.train_one_epoch loop between optimizer.zero_grad()
+and scaler.update() (utils/trainer.py:81-93) and its nn.DataParallel wrapper (utils/trainer.py:28-30) with one
+process per GPU. BatchNorm statistics stay per replica, as under DataParallel.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .engine import CONVT_INTO, DEC, ENC, UNetEngine
+
+
+def grad_ready_order():
+    """Parameter names in the order UNetEngine.backward finishes their gradients (reverse of forward use)."""
+    order = ["final.1.weight", "final.1.bias"]
+
+    def block(name):
+        for idx in (3, 0):
+            order.extend([f"{name}.{idx + 2}.weight", f"{name}.{idx + 2}.bias", f"{name}.{idx}.bias",
+                          f"{name}.{idx}.weight"])
+
+    for l in (0, 1, 2, 3):
+        block("final.0" if l == 0 else DEC[l])
+        order.extend([f"{CONVT_INTO[l]}.bias", f"{CONVT_INTO[l]}.weight"])
+    block("middle.1")
+    for l in (3, 2, 1, 0):
+        block(ENC[l])
+    return order
+
+
+def cosine_warm_restarts_lr(base_lr, epoch, T_0=20, T_mult=2, eta_min=0.0):
+    """torch CosineAnnealingWarmRestarts closed form (utils/trainer.py:42: T_0=20, T_mult=2, eta_min=0)."""
+    T_i, t = T_0, epoch
+    while t >= T_i:
+        t -= T_i
+        T_i *= T_mult
+    return eta_min + (base_lr - eta_min) * (1 + math.cos(math.pi * t / T_i)) / 2
+
+
+class TrainStep:
+    """Owns flat fp32 parameter / gradient / Adam-moment buckets laid out in gradient-ready order."""
+
+    def __init__(self, state_dict, device, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
+                 bucket_mb=16.0, w_bce=1.0, w_dice=1.0, process_group=None, use_dist=None, engine=None):
+        self.device = torch.device(device)
+        self.engine = engine if engine is not None else UNetEngine(out_channels=state_dict["final.1.bias"].numel())
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.w_bce, self.w_dice = w_bce, w_dice
+        self.step_count = 0
+        self.pg = process_group
+        self.use_dist = dist.is_available() and dist.is_initialized() if use_dist is None else use_dist
+        self.world = dist.get_world_size(self.pg) if self.use_dist else 1
+        order = grad_ready_order()
+        assert set(order) == {k for k, v in state_dict.items() if v.is_floating_point() and "running" not in k}
+        sizes = [state_dict[k].numel() for k in order]
+        # 16-byte aligned offsets inside one flat buffer
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 3) // 4 * 4
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.flat_p = torch.zeros(total, **f32)
+        self.flat_g = torch.zeros(total, **f32)
+        self.flat_m = torch.zeros(total, **f32)
+        self.flat_v = torch.zeros(total, **f32)
+        self.P, self.G = {}, {}
+        for k, o, n in zip(order, offs, sizes):
+            shape = state_dict[k].shape
+            self.P[k] = self.flat_p[o:o + n].view(shape)
+            self.G[k] = self.flat_g[o:o + n].view(shape)
+            self.P[k].copy_(state_dict[k])
+        for k, v in state_dict.items():
+            if k not in self.P:
+                self.P[k] = v.detach().clone().to(self.device)
+        # buckets: contiguous ranges of the flat gradient, closed when >= bucket_mb
+        limit = int(bucket_mb * (1 << 20) / 4)
+        self.buckets, self.bucket_of, self.bucket_last = [], {}, {}
+        start = 0
+        for i, (k, o, n) in enumerate(zip(order, offs, sizes)):
+            end = o + (n + 3) // 4 * 4
+            bi = len(self.buckets)
+            self.bucket_of[k] = bi
+            self.bucket_last[bi] = k              # overwritten until the bucket closes: its last-ready parameter
+            if end - start >= limit or i == len(order) - 1:
+                self.buckets.append((start, end))
+                start = end
+        self.order = order
+        self._works = []
+
+    # ---- parameter access -------------------------------------------------------------------------------------
+    def state_dict(self):
+        return {k: v.detach().clone() for k, v in self.P.items()}
+
+    def _on_grad_ready(self, name):
+        if self.world == 1:
+            return
+        b = self.bucket_of[name]
+        if self.bucket_last[b] == name:
+            s, e = self.buckets[b]
+            self._works.append(dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    # ---- one optimisation step ------------------------------------------------------------------------------------
+    def forward_backward(self, x, t):
+        """x [B,1,H,W] fp32, t [B,1,H,W] fp32 on the device. Returns the 8-float loss vector (device tensor)."""
+        eng = self.engine
+        _, pl = eng.forward(self.P, x, train=True)
+        out = eng.loss(pl, t, w_bce=self.w_bce, w_dice=self.w_dice)
+        dl = eng.loss_backward(pl, t, w_bce=self.w_bce, w_dice=self.w_dice)
+        self._works = []
+        eng.backward(self.P, pl, dl, self.G, on_grad_ready=self._on_grad_ready)
+        for w in self._works:
+            w.wait()
+        return out
+
+    def optimizer_step(self, lr=None):
+        self.step_count += 1
+        ops.adamw_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr if lr is not None else self.lr,
+                       self.betas[0], self.betas[1], self.eps, self.wd, self.step_count, 1.0 / self.world)
+        self.engine.invalidate_packed()      # the kernel updated flat_p behind torch's version counters
+
+    def step(self, x, t, lr=None):
+        out = self.forward_backward(x, t)
+        self.optimizer_step(lr)
+        return out
