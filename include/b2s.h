@@ -36,12 +36,13 @@ int b2s_version(void);
 /* nn.Conv2d(Cin,Cout,3,padding=1) / nn.Conv2d(Cin,Cout,1) forward (models/model.py:36,39; models/vnet.py:43,59)
  * and, with rotated weights from b2s_pack_conv_weight, the 3x3 input gradient (autograd of the same call sites).
  *   x [N,H,W,Cin] bf16, w_packed [ksize*ksize][Cout][Cin] bf16, bias [Cout] fp32 or NULL,
- *   y [N,H,W,Cout] bf16, stats_partial [b2s_conv_fwd_tiles_m(N,H,W)][2][Cout] fp32 when B2S_FLAG_STATS.
+ *   y [N,H,W,Cout] bf16, stats_partial [b2s_conv_stats_rows(N,H,W,Cout,tile_n)][2][Cout] fp32 when B2S_FLAG_STATS
+ *   (two rows per CTA row-group of the persistent grid; at most 2 * SM count rows).
  *   tile_n: 0 = auto, else 64/128/256 (must divide Cout). Cin, Cout multiples of 64. */
 int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y, int y_cstride,
                  float* stats_partial, int N, int H, int W, int Cin, int Cout, int ksize, int flags, int tile_n,
                  void* stream);
-int b2s_conv_fwd_tiles_m(int N, int H, int W);
+int b2s_conv_stats_rows(int N, int H, int W, int Cout, int tile_n);
 
 /* nn.ConvTranspose2d(Cin,Cout,2,stride=2) forward (models/model.py:19,49): x [N,Hi,Wi,Cin] -> y [N,2Hi,2Wi,Cout];
  * w_packed [(a*2+b)*Cout+co][Cin] bf16 (b2s_pack_convt_weight). */

@@ -100,8 +100,8 @@ def test_conv3x3_fwd_bias_relu_stats(ops, N, H, W, Cin, Cout, tile_n, relu):
     xa = act_from_nchw(ops, x)
     wf, _ = ops.pack_conv_weight(w.to(DEV), want_dgrad=False)
     y = ops.Act.empty(N, H, W, Cout, DEV)
-    rows = ops.conv_tiles_m(N, H, W)
-    stats = torch.zeros((rows, 2, Cout), dtype=torch.float32, device=DEV)
+    rows = ops.conv_stats_rows(N, H, W, Cout, tile_n)
+    stats = torch.full((rows, 2, Cout), float('nan'), dtype=torch.float32, device=DEV)
     ops.conv_fwd(xa, wf, b.to(DEV), y, ksize=3, relu=relu, stats=stats, tile_n=tile_n)
     torch.cuda.synchronize()
     ref = O.conv3x3(x.double(), w.double(), b.double())

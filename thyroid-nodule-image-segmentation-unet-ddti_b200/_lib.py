@@ -22,7 +22,7 @@ SIGNATURES = {
     "b2s_launch_count": (LL, []),
     "b2s_version": (I, []),
     "b2s_conv_fwd": (I, [P, I, P, P, P, I, P, I, I, I, I, I, I, I, I, P]),
-    "b2s_conv_fwd_tiles_m": (I, [I, I, I]),
+    "b2s_conv_stats_rows": (I, [I, I, I, I, I]),
     "b2s_convt2x2_fwd": (I, [P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "b2s_convt2x2_dgrad": (I, [P, I, P, P, I, I, I, I, I, I, I, P]),
     "b2s_conv_wgrad_workspace": (LL, [I, I, I, I, I, I, I, I, POINTER(c_int)]),

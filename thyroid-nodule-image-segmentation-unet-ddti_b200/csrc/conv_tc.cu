@@ -7,7 +7,9 @@
 //   wgrad_tc_kernel  : dW[(tap,ci), co] = sum_pix x[pix+tap, ci] * dz[pix, co]        (MN-major operands)
 //                      split-K over pixels, fp32 partials to a workspace, deterministic second-stage reduce.
 //
-// Warp roles (192 threads): warp0 = TMA producer (+TMEM alloc), warp1 = MMA issuer, warps2-5 = epilogue.
+// conv_tc_kernel is persistent (one CTA per SM, 320 threads): warp0 = TMA producer (+TMEM alloc), warp1 = MMA
+// issuer, warps 2-5 / 6-9 = two epilogue groups draining the two TMEM accumulators alternately.
+// wgrad_tc_kernel runs one long split-K tile per CTA (192 threads, one epilogue group).
 #include "ptx.cuh"
 #include "b2s_internal.h"
 
@@ -16,7 +18,7 @@ namespace b2s {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 192;   // wgrad kernel: warp0 TMA, warp1 MMA, warps 2-5 epilogue
 
 enum AMode : int { A_CONV3 = 0, A_1X1 = 1, A_CONVT_DGRAD = 2 };
 enum OutMode : int { OUT_4D = 0, OUT_CONVT_5D = 1 };
@@ -24,6 +26,7 @@ enum OutMode : int { OUT_4D = 0, OUT_CONVT_5D = 1 };
 struct ConvTcParams {
   int bw, bh, bn;                  // pixel box of one M tile, bw*bh*bn == 128
   int tiles_w, tiles_h, tiles_n;   // tiles over (W, H, N)
+  int tiles_m;                     // tiles_w * tiles_h * tiles_n
   int W, H, N;                     // pixel space of the GEMM rows
   int num_taps, k_chunks;          // K loop = taps x (Cin/64)
   int a_mode, out_mode;
@@ -32,24 +35,31 @@ struct ConvTcParams {
   int tiles_nn;                    // n_total / BLOCK_N
   int flags;                       // B2S_FLAG_*
   const float* bias;               // [cout_sub] or nullptr
-  float* stats;                    // [tiles_m][2][n_total] partial column sums, or nullptr
+  float* stats;                    // [2 * gridDim.x / tiles_nn][2][n_total] partial column sums, or nullptr
 };
+
+constexpr int kConvThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1
 
 template <int BLOCK_N, int STAGES>
 struct ConvSmem {
   static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kPipeBytes = STAGES * kStageBytes;
-  static constexpr int kBarOffset = kPipeBytes;                       // full[STAGES], empty[STAGES], tmem_full
-  static constexpr int kTmemPtrOffset = kBarOffset + (2 * STAGES + 1) * 8;
-  static constexpr int kStatsOffset = (kTmemPtrOffset + 4 + 15) / 16 * 16;  // [2 buf][4 warps][2][64] float
+  static constexpr int kStagingOffset = kPipeBytes;                    // one 16 KB store-staging tile per group
+  static constexpr int kBarOffset = kStagingOffset + 2 * kATileBytes;   // full[S], empty[S], tmem_full[2], tmem_empty[2]
+  static constexpr int kTmemPtrOffset = kBarOffset + (2 * STAGES + 4) * 8;
+  static constexpr int kStatsOffset = (kTmemPtrOffset + 4 + 15) / 16 * 16;  // [2 groups][4 warps][2][64] float
   static constexpr int kTotal = kStatsOffset + 2 * 4 * 2 * 64 * 4;
   static constexpr int kDynBytes = kTotal + 1024;  // slack for manual 1024-B alignment
-  static_assert((BLOCK_N / 64) * kATileBytes <= kPipeBytes, "epilogue staging must fit in the pipeline smem");
+  static_assert(kDynBytes <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
+// Persistent kernel: CTA c owns column tile n_tile = c % tiles_nn and the row tiles m = c / tiles_nn + i * groups.
+// Three pipelines: smem ring (TMA -> MMA), two TMEM accumulators (MMA -> epilogue), one staging tile per epilogue
+// group (epilogue -> TMA store). The producer runs ahead across tile boundaries; the two epilogue groups alternate
+// tiles so that TMEM drain + bias/ReLU/statistics + store of tile i overlap the MMAs of tiles i+1, i+2.
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kNumThreads)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const ConvTcParams p) {
   using L = ConvSmem<BLOCK_N, STAGES>;
@@ -59,21 +69,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem_b = smem + STAGES * kATileBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOffset);
   float* stats_smem = reinterpret_cast<float*>(smem + L::kStatsOffset);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- tile coordinates -------------------------------------------------------------------
+  // ---- static tile schedule -----------------------------------------------------------------
   const int n_tile = blockIdx.x % p.tiles_nn;
-  const int m_tile = blockIdx.x / p.tiles_nn;
-  const int tw = m_tile % p.tiles_w;
-  const int th = (m_tile / p.tiles_w) % p.tiles_h;
-  const int tn = m_tile / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+  const int mgroup = blockIdx.x / p.tiles_nn;
+  const int num_mgroups = gridDim.x / p.tiles_nn;
   const int ncol0 = n_tile * BLOCK_N;  // first GEMM column of this CTA
+  const int my_tiles = (p.tiles_m - mgroup + num_mgroups - 1) / num_mgroups;   // >= 1 by construction
+  const int k_iters = p.num_taps * p.k_chunks;
 
   // ---- one-time setup -----------------------------------------------------------------------
   if (warp == 0) {
@@ -82,47 +92,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&tmB);
       tma_prefetch_desc(&tmOut);
     }
-    tmem_alloc(tmem_ptr_smem, BLOCK_N);
+    tmem_alloc(tmem_ptr_smem, 2 * BLOCK_N);
     tmem_relinquish();
   } else if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&tmem_full_bar[g], 1);
+      mbar_init(&tmem_empty_bar[g], 4);   // one arrival per epilogue warp of the group
+    }
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_ptr_smem;
-
-  const int k_iters = p.num_taps * p.k_chunks;
+  const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer: runs ahead of the MMA warp across tile boundaries =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        const int tap = it / p.k_chunks;
-        const int kc = it - tap * p.k_chunks;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-        uint8_t* a_dst = smem_a + stage * kATileBytes;
-        uint8_t* b_dst = smem_b + stage * L::kBTileBytes;
-        if (p.a_mode == A_CONV3) {
-          const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;
-          tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0 + dw, h0 + dh, n0);
-        } else if (p.a_mode == A_1X1) {
-          tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0, h0, n0);
-        } else {  // A_CONVT_DGRAD: dY viewed as (C, b, j, a, i*N)
-          const int a = tap >> 1, b = tap & 1;
-          tma_load_5d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, b, w0, a, n0 * p.H + h0);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int m_tile = mgroup + i * num_mgroups;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / p.k_chunks;
+          const int kc = it - tap * p.k_chunks;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          uint8_t* a_dst = smem_a + stage * kATileBytes;
+          uint8_t* b_dst = smem_b + stage * L::kBTileBytes;
+          if (p.a_mode == A_CONV3) {
+            const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;
+            tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0 + dw, h0 + dh, n0);
+          } else if (p.a_mode == A_1X1) {
+            tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0, h0, n0);
+          } else {  // A_CONVT_DGRAD: dY viewed as (C, b, j, a, i*N)
+            const int a = tap >> 1, b = tap & 1;
+            tma_load_5d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, b, w0, a, n0 * p.H + h0);
+          }
+          // B rows: [tap][n_total] x Cin; the host encodes the box as (64, BLOCK_N)
+          tma_load_2d(&tmB, &full_bar[stage], b_dst, kc * kBlockK, tap * p.n_total + ncol0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        // B rows: [tap][n_total] x Cin; the host encodes the box as (64, BLOCK_N)
-        tma_load_2d(&tmB, &full_bar[stage], b_dst, kc * kBlockK, tap * p.n_total + ncol0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -131,113 +149,147 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int acc = i & 1;
+        const uint32_t acc_phase = (i >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a + stage * kATileBytes);
-        const uint32_t b_addr = smem_u32(smem_b + stage * L::kBTileBytes);
+        const uint32_t tmem_acc = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * kATileBytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * L::kBTileBytes);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_acc, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_acc, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> regs -> (+bias, ReLU) -> bf16 -> swizzled smem -> TMA store; BN partial sums =====
+    // ===== epilogue groups: TMEM -> regs -> (+bias, ReLU) -> bf16 -> swizzled smem -> TMA store; BN partial sums =====
+    const int g = (warp - 2) >> 2;   // group 0: warps 2-5, group 1: warps 6-9; group g drains accumulator g
     const int q = warp & 3;          // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;   // tile row == TMEM lane
-    const int ethread = row;         // 0..127 linear epilogue thread id (for stats write-out)
+    const int row = q * 32 + lane;   // tile row == TMEM lane == linear thread id inside the group
+    const bool do_relu = p.flags & B2S_FLAG_RELU;
+    const bool do_stats = (p.flags & B2S_FLAG_STATS) && p.stats != nullptr;
+    uint8_t* stage_buf = smem + L::kStagingOffset + g * kATileBytes;
+    const int bar_id = 1 + g;
     const int wl = row % p.bw;
     const int hl = (row / p.bw) % p.bh;
     const int nl = row / (p.bw * p.bh);
-    const bool valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
-    const bool do_relu = p.flags & B2S_FLAG_RELU;
-    const bool do_stats = (p.flags & B2S_FLAG_STATS) && p.stats != nullptr;
-
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-
-#pragma unroll 1
-    for (int s = 0; s < BLOCK_N / 64; ++s) {
-      uint32_t v0[32], v1[32];
-      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + s * 64;
-      tmem_ld_32x32(taddr, v0);
-      tmem_ld_32x32(taddr + 32, v1);
-      tmem_ld_wait();
-
-      uint8_t* stage_buf = smem + s * kATileBytes;  // pipeline smem is idle now
-      const int col_base = ncol0 + s * 64;           // GEMM column of v0[0]
-      const int bias_base = col_base % p.cout_sub;
-      uint32_t packed[32];
+    float st_acc[BLOCK_N / 64][4];   // per chunk: sum, sum of the two columns (2*lane, 2*lane+1), then squares
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float a = __uint_as_float(j < 16 ? v0[2 * j] : v1[2 * j - 32]);
-        float b = __uint_as_float(j < 16 ? v0[2 * j + 1] : v1[2 * j - 31]);
-        if (p.bias != nullptr) {
-          a += __ldg(p.bias + bias_base + 2 * j);
-          b += __ldg(p.bias + bias_base + 2 * j + 1);
+    for (int s = 0; s < BLOCK_N / 64; ++s) st_acc[s][0] = st_acc[s][1] = st_acc[s][2] = st_acc[s][3] = 0.f;
+
+    for (int i = g; i < my_tiles; i += 2) {
+      const int m_tile = mgroup + i * num_mgroups;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+      const bool valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
+      mbar_wait(&tmem_full_bar[g], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + g * BLOCK_N;
+
+#pragma unroll
+      for (int s = 0; s < BLOCK_N / 64; ++s) {
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + s * 64;
+        tmem_ld_32x32(taddr, v0);
+        tmem_ld_32x32(taddr + 32, v1);
+        tmem_ld_wait();
+        if (s == BLOCK_N / 64 - 1) {
+          // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
         }
-        if (do_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-        if (!valid) { a = 0.f; b = 0.f; }
-        packed[j] = pack_bf16x2(a, b);
-      }
-      // 128-B row, 16-B chunk c stored at chunk (c ^ (row & 7)): the SWIZZLE_128B pattern of tmOut
+        const int col_base = ncol0 + s * 64;           // GEMM column of v0[0]
+        const int bias_base = col_base % p.cout_sub;
+        uint32_t packed[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-        *reinterpret_cast<uint4*>(stage_buf + row * 128 + ((c ^ (row & 7)) << 4)) = val;
-      }
-      if (do_stats) {
-        // column sums over this warp's own 32 rows, taken from the bf16-rounded values actually stored
-        __syncwarp();
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        const int chunk = lane >> 2, within = (lane & 3) * 4;  // lane <-> column pair (2*lane, 2*lane+1)
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(j < 16 ? v0[2 * j] : v1[2 * j - 32]);
+          float b = __uint_as_float(j < 16 ? v0[2 * j + 1] : v1[2 * j - 31]);
+          if (p.bias != nullptr) {
+            a += __ldg(p.bias + bias_base + 2 * j);
+            b += __ldg(p.bias + bias_base + 2 * j + 1);
+          }
+          if (do_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          if (!valid) { a = 0.f; b = 0.f; }
+          packed[j] = pack_bf16x2(a, b);
+        }
+        // the previous TMA store of this group must have finished READING the staging tile
+        if (row == 0) tma_store_wait_read<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        // 128-B row, 16-B chunk c stored at chunk (c ^ (row & 7)): the SWIZZLE_128B pattern of tmOut
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+          *reinterpret_cast<uint4*>(stage_buf + row * 128 + ((c ^ (row & 7)) << 4)) = val;
+        }
+        if (do_stats) {
+          // column sums over this warp's own 32 rows, taken from the bf16-rounded values actually stored
+          __syncwarp();
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const int chunk = lane >> 2, within = (lane & 3) * 4;  // lane <-> column pair (2*lane, 2*lane+1)
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const int rr = q * 32 + r;
-          const uint32_t u = *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
-          const float x0 = bf16_lo(u), x1 = bf16_hi(u);
-          s0 += x0; s1 += x1;
-          q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+          for (int r = 0; r < 32; ++r) {
+            const int rr = q * 32 + r;
+            const uint32_t u =
+                *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
+            const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+            s0 += x0; s1 += x1;
+            q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+          }
+          st_acc[s][0] += s0; st_acc[s][1] += s1; st_acc[s][2] += q0; st_acc[s][3] += q1;
         }
-        float* sb = stats_smem + (s & 1) * (4 * 2 * 64) + q * (2 * 64);
-        sb[2 * lane] = s0; sb[2 * lane + 1] = s1;
-        sb[64 + 2 * lane] = q0; sb[64 + 2 * lane + 1] = q1;
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (ethread == 0) {
-        if (p.out_mode == OUT_4D) {
-          tma_store_4d(&tmOut, stage_buf, col_base, w0, h0, n0);
-        } else {  // convT forward: column block belongs to one (a,b) sub-position
-          const int ab = col_base / p.cout_sub;
-          tma_store_5d(&tmOut, stage_buf, col_base - ab * p.cout_sub, ab & 1, w0, ab >> 1, n0 * p.H + h0);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (row == 0) {
+          if (p.out_mode == OUT_4D) {
+            tma_store_4d(&tmOut, stage_buf, col_base, w0, h0, n0);
+          } else {  // convT forward: column block belongs to one (a,b) sub-position
+            const int ab = col_base / p.cout_sub;
+            tma_store_5d(&tmOut, stage_buf, col_base - ab * p.cout_sub, ab & 1, w0, ab >> 1, n0 * p.H + h0);
+          }
+          tma_store_commit();
         }
-        tma_store_commit();
       }
-      if (do_stats) {
-        const float* sb = stats_smem + (s & 1) * (4 * 2 * 64);
-        // 128 threads: thread e -> (which = e/64, column = e%64)
-        const int which = ethread >> 6, col = ethread & 63;
+    }
+    if (row == 0) tma_store_wait_read<0>();
+    if (do_stats) {
+      // one partial row per (CTA row-group, epilogue group): [2*mgroup + g][2][n_total]
+      float* sb = stats_smem + g * (4 * 2 * 64);
+      float* out_row = p.stats + static_cast<size_t>(2 * mgroup + g) * 2 * p.n_total;
+#pragma unroll
+      for (int s = 0; s < BLOCK_N / 64; ++s) {
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        sb[q * 128 + 2 * lane] = st_acc[s][0]; sb[q * 128 + 2 * lane + 1] = st_acc[s][1];
+        sb[q * 128 + 64 + 2 * lane] = st_acc[s][2]; sb[q * 128 + 64 + 2 * lane + 1] = st_acc[s][3];
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const int which = row >> 6, col = row & 63;   // 128 threads: (sum | sumsq) x 64 columns
         float acc = 0.f;
 #pragma unroll
         for (int wq = 0; wq < 4; ++wq) acc += sb[wq * 128 + which * 64 + col];
-        p.stats[(static_cast<size_t>(m_tile) * 2 + which) * p.n_total + col_base + col] = acc;
+        out_row[which * p.n_total + ncol0 + s * 64 + col] = acc;
       }
     }
-    if (ethread == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, BLOCK_N);
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
   }
 }
 
@@ -488,9 +540,28 @@ static int make_up_map5(CUtensorMap* m, const void* base, int C, int Wi, int Hi,
   return make_tmap(m, base, 5, dims, str, box);
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// Persistent grid: one CTA per SM, rounded down to a multiple of the column-tile count.
+static int conv_grid(int tiles_m, int tiles_nn) {
+  long long total = static_cast<long long>(tiles_m) * tiles_nn;
+  int grid = static_cast<int>(total < num_sms() ? total : num_sms());
+  grid = grid / tiles_nn * tiles_nn;
+  if (grid < tiles_nn) grid = tiles_nn;
+  return grid;
+}
+
 template <int BLOCK_N, int STAGES>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                       const ConvTcParams& p, int grid, cudaStream_t stream) {
+                       const ConvTcParams& p, cudaStream_t stream) {
   using L = ConvSmem<BLOCK_N, STAGES>;
   auto kfn = conv_tc_kernel<BLOCK_N, STAGES>;
   static bool attr_set = false;
@@ -499,17 +570,18 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
     attr_set = true;
   }
-  kfn<<<grid, kNumThreads, L::kDynBytes, stream>>>(tmA, tmB, tmOut, p);
+  kfn<<<conv_grid(p.tiles_m, p.tiles_nn), kConvThreads, L::kDynBytes, stream>>>(tmA, tmB, tmOut, p);
   return check_launch("conv_tc_kernel");
 }
 
 static int dispatch_conv(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                         const ConvTcParams& p, int grid, cudaStream_t stream) {
+                         ConvTcParams& p, cudaStream_t stream) {
+  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   count_launch();
   switch (block_n) {
-    case 64:  return launch_conv<64, 4>(tmA, tmB, tmOut, p, grid, stream);    // 4 x 24 KB
-    case 128: return launch_conv<128, 3>(tmA, tmB, tmOut, p, grid, stream);   // 3 x 32 KB -> 2 CTAs / SM
-    case 256: return launch_conv<256, 4>(tmA, tmB, tmOut, p, grid, stream);   // 4 x 48 KB -> 1 CTA / SM
+    case 64:  return launch_conv<64, 7>(tmA, tmB, tmOut, p, stream);    // 7 x 24 KB + 32 KB staging
+    case 128: return launch_conv<128, 5>(tmA, tmB, tmOut, p, stream);   // 5 x 32 KB + 32 KB staging
+    case 256: return launch_conv<256, 3>(tmA, tmB, tmOut, p, stream);   // 3 x 48 KB + 32 KB staging (all 512 TMEM cols)
     default:  return set_error(B2S_ERR_ARG, "unsupported tile_n");
   }
 }
@@ -556,14 +628,18 @@ extern "C" int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, 
     if ((rc = make_tmap(&tmB, w_packed, 2, dims, str, box))) return rc;
   }
   if ((rc = make_act_map4(&tmOut, y, Cout, W, H, N, y_cstride, p.bw, p.bh, p.bn))) return rc;
-  const int grid = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nn;
-  return dispatch_conv(block_n, tmA, tmB, tmOut, p, grid, stream);
+  return dispatch_conv(block_n, tmA, tmB, tmOut, p, stream);
 }
 
-extern "C" int b2s_conv_fwd_tiles_m(int N, int H, int W) {
+// Rows of the stats_partial buffer b2s_conv_fwd writes for this shape: 2 per CTA row-group of the persistent grid.
+extern "C" int b2s_conv_stats_rows(int N, int H, int W, int Cout, int tile_n) {
   int bw, bh, bn;
   pick_box(W, H, N, kBlockM, &bw, &bh, &bn);
-  return ((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((N + bn - 1) / bn);
+  const int tiles_m = ((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((N + bn - 1) / bn);
+  const int block_n = auto_block_n(Cout, Cout, tile_n);
+  if (block_n <= 0 || Cout % block_n) return -1;
+  const int tiles_nn = Cout / block_n;
+  return 2 * (conv_grid(tiles_m, tiles_nn) / tiles_nn);
 }
 
 // ConvTranspose2d(k=2,s=2) forward: x [N,Hi,Wi,Cin] -> y [N,2Hi,2Wi,Cout]; w_packed [(a*2+b)*Cout+co][Cin].
@@ -593,8 +669,7 @@ extern "C" int b2s_convt2x2_fwd(const void* x, int x_cstride, const void* w_pack
     if ((rc = make_tmap(&tmB, w_packed, 2, dims, str, box))) return rc;
   }
   if ((rc = make_up_map5(&tmOut, y, Cout, Wi, Hi, N, y_cstride, p.bw, p.bh * p.bn))) return rc;
-  const int grid = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nn;
-  return dispatch_conv(block_n, tmA, tmB, tmOut, p, grid, stream);
+  return dispatch_conv(block_n, tmA, tmB, tmOut, p, stream);
 }
 
 // ConvTranspose2d(k=2,s=2) input gradient: dy [N,2Hi,2Wi,Cout] -> dx [N,Hi,Wi,Cin]; w_packed [(a*2+b)*Cin+ci][Cout].
@@ -624,8 +699,7 @@ extern "C" int b2s_convt2x2_dgrad(const void* dy, int dy_cstride, const void* w_
     if ((rc = make_tmap(&tmB, w_packed, 2, dims, str, box))) return rc;
   }
   if ((rc = make_act_map4(&tmOut, dx, Cin, Wi, Hi, N, dx_cstride, p.bw, p.bh, p.bn))) return rc;
-  const int grid = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nn;
-  return dispatch_conv(block_n, tmA, tmB, tmOut, p, grid, stream);
+  return dispatch_conv(block_n, tmA, tmB, tmOut, p, stream);
 }
 
 // ---- wgrad -----------------------------------------------------------------------------------
@@ -684,8 +758,7 @@ extern "C" long long b2s_conv_wgrad_workspace(int N, int H, int W, int Cin, int 
     return -1;
   }
   if (splits_out) *splits_out = p.splits;
-  // b2s_wgrad_reduce folds > 8 partials through an 8-slot tail region first
-  return static_cast<long long>(p.splits + (p.splits > 8 ? 8 : 0)) * taps * Cin * Cout * 4;
+  return static_cast<long long>(p.splits) * taps * Cin * Cout * 4;
 }
 
 // 3x3 conv weight gradient partials: ws[split][tap*Cin+ci][co] = sum over the split's pixels.

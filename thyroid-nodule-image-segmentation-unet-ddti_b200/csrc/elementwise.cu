@@ -726,14 +726,18 @@ __global__ void pack_convt_weight_kernel(const float* __restrict__ w, __nv_bfloa
 }
 
 // ws [splits][taps][Cin][Cout] -> layout 0: dw[co][ci][t]; layout 1: dw[ci][co][t].
-// Block = 8 ci x 128 co x all taps; each thread streams `taps` independent float4 columns over the splits.
+// Block = 8 warps x (32 lanes = 128 co as float4). The warps are split into (8/sgroups) input channels x sgroups
+// split groups, so that shallow layers (tiny K, many K-splits) and deep layers (huge K, 1-2 splits) both stream with
+// `taps` independent float4 loads in flight per thread.
 __global__ void __launch_bounds__(kThreads)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int Cin, int Cout, float* __restrict__ dw,
-                    int layout) {
+                    int layout, int sgroups) {
   __shared__ float tile[9][8][129];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int ci0 = blockIdx.x * 8, co0 = blockIdx.y * 128;
-  const int ci = ci0 + ty, co = co0 + tx * 4;
+  const int cpb = 8 / sgroups;                       // input channels per block
+  const int cil = ty / sgroups, sg = ty - cil * sgroups;
+  const int ci0 = blockIdx.x * cpb, co0 = blockIdx.y * 128;
+  const int ci = ci0 + cil, co = co0 + tx * 4;
   const size_t tap_stride = static_cast<size_t>(Cin) * Cout;
   const size_t split_stride = static_cast<size_t>(taps) * tap_stride;
   float4 acc[9];
@@ -741,7 +745,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int Cin,
   for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ci < Cin && co < Cout) {
     const float* base = ws + static_cast<size_t>(ci) * Cout + co;
-    for (int sp = 0; sp < splits; ++sp) {
+    for (int sp = sg; sp < splits; sp += sgroups) {
 #pragma unroll
       for (int t = 0; t < 9; ++t)
         if (t < taps) {
@@ -756,16 +760,26 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int Cin,
     tile[t][ty][tx * 4 + 2] = acc[t].z; tile[t][ty][tx * 4 + 3] = acc[t].w;
   }
   __syncthreads();
-  const int nci = min(8, Cin - ci0), nco = min(128, Cout - co0);
+  const int nci = min(cpb, Cin - ci0), nco = min(128, Cout - co0);
   if (layout == 0) {
-    for (int col = ty; col < nco; col += 8) {         // one warp per output channel: nci*taps contiguous floats
-      float* dst = dw + (static_cast<size_t>(co0 + col) * Cin + ci0) * taps;
-      for (int i = tx; i < nci * taps; i += 32) dst[i] = tile[i % taps][i / taps][col];
+    // dw[co][ci0 .. ci0+nci)[t]: nci*taps contiguous floats per output channel; thread <-> (col, i)
+    const int run = nci * taps;
+    for (int e = threadIdx.x; e < nco * run; e += kThreads) {
+      const int col = e / run, i = e - col * run;
+      const int c = i / taps, t = i - c * taps;
+      float v = 0.f;
+      for (int g = 0; g < sgroups; ++g) v += tile[t][c * sgroups + g][col];
+      dw[(static_cast<size_t>(co0 + col) * Cin + ci0) * taps + i] = v;
     }
   } else {
-    if (ty < nci) {                                    // one warp per input channel: nco*taps contiguous floats
-      float* dst = dw + (static_cast<size_t>(ci0 + ty) * Cout + co0) * taps;
-      for (int i = tx; i < nco * taps; i += 32) dst[i] = tile[i % taps][ty][i / taps];
+    // dw[ci][co0 .. co0+nco)[t]: nco*taps contiguous floats per input channel
+    const int run = nco * taps;
+    for (int e = threadIdx.x; e < nci * run; e += kThreads) {
+      const int c = e / run, i = e - c * run;
+      const int col = i / taps, t = i - col * taps;
+      float v = 0.f;
+      for (int g = 0; g < sgroups; ++g) v += tile[t][c * sgroups + g][col];
+      dw[(static_cast<size_t>(ci0 + c) * Cout + co0) * taps + i] = v;
     }
   }
 }
@@ -1060,23 +1074,11 @@ extern "C" int b2s_wgrad_reduce(const float* ws, int splits, int taps, int Cin, 
   if (!ws || !dw) return set_error(B2S_ERR_ARG, "b2s_wgrad_reduce: null pointer");
   if (taps < 1 || taps > 9 || splits < 1) return set_error(B2S_ERR_ARG, "b2s_wgrad_reduce: bad taps/splits");
   if (Cout % 4) return set_error(B2S_ERR_ARG, "b2s_wgrad_reduce: Cout must be a multiple of 4");
-  const long long K = static_cast<long long>(taps) * Cin * Cout;
-  if (splits > 8) {
-    // many small partials (shallow layers): first fold them 8-ways into the workspace tail [splits*K, (splits+8)*K)
-    const int rps = (splits + 7) / 8;
-    const int used = (splits + rps - 1) / rps;
-    float* tail = const_cast<float*>(ws) + static_cast<size_t>(splits) * K;
-    dim3 grid(static_cast<unsigned>((K + 31) / 32), used), block(32, kRedY);
-    count_launch();
-    reduce_rows_kernel<<<grid, block, 0, STREAM(stream)>>>(ws, splits, static_cast<int>(K), rps, tail);
-    int rc = check_launch("reduce_rows_kernel");
-    if (rc) return rc;
-    ws = tail;
-    splits = used;
-  }
-  dim3 grid((Cin + 7) / 8, (Cout + 127) / 128);
+  const int sgroups = splits >= 8 ? 8 : splits >= 4 ? 4 : splits >= 2 ? 2 : 1;
+  const int cpb = 8 / sgroups;
+  dim3 grid((Cin + cpb - 1) / cpb, (Cout + 127) / 128);
   count_launch();
-  wgrad_reduce_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(ws, splits, taps, Cin, Cout, dw, layout);
+  wgrad_reduce_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(ws, splits, taps, Cin, Cout, dw, layout, sgroups);
   return check_launch("wgrad_reduce_kernel");
 }
 

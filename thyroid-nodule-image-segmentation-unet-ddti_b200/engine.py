@@ -84,8 +84,7 @@ class UNetPlan:
         self.logits = torch.empty((N, out_channels, H, W), **f32)
         self.mask = torch.empty((N, out_channels, H, W), dtype=torch.uint8, device=device)
         # partial / scratch buffers
-        rows0 = ops.conv_tiles_m(N, H, W)
-        self.stats_partial = torch.empty(max(rows0 * 2 * 128, ops.c1_rows(N, H, W) * 2 * 64), **f32)
+        self.stats_partial = torch.empty(max(2 * 160 * 2 * 2048, ops.c1_rows(N, H, W) * 2 * 64), **f32)
         self.ew_partial = torch.empty(ops.ew_rows() * 2 * 1024, **f32)
         self.c1_partial = torch.empty(ops.c1_rows(N, H, W) * 64 * 9, **f32)
         self.scratch = torch.empty(128 * 2 * 2048, **f32)
@@ -193,7 +192,7 @@ class UNetEngine:
                 wf, _ = self._packed[f"{name}.{idx}.weight"]
                 ops.conv_fwd(xin, wf, P[f"{name}.{idx}.bias"], s.r, ksize=3, relu=True,
                              stats=pl.stats_partial if train else None)
-                rows = ops.conv_tiles_m(N, s.r.H, s.r.W)
+                rows = ops.conv_stats_rows(N, s.r.H, s.r.W, s.cout)
             if train:
                 ops.bn_finalize(pl.stats_partial, rows, s.cout, count(s.level), P[f"{bn}.weight"], P[f"{bn}.bias"],
                                 P[f"{bn}.running_mean"], P[f"{bn}.running_var"], P[f"{bn}.num_batches_tracked"],
@@ -285,7 +284,7 @@ class UNetEngine:
             block_bwd(name, dy, pl.dcat[l], dx_stats=True)
             # transposed conv writing cat[l][:, :C]: bias grad = column sums of dcat[l][..., :C] (dgrad epilogue)
             ct = CONVT_INTO[l]
-            rows = ops.conv_tiles_m(N, pl.dims[l][0], pl.dims[l][1])
+            rows = ops.conv_stats_rows(N, pl.dims[l][0], pl.dims[l][1], 2 * C)
             ops.reduce_rows(pl.stats_partial, rows, 2 * 2 * C, pl.scratch, pl.tmp_vec)
             G[f"{ct}.bias"].copy_(pl.tmp_vec[:C])
             ready(f"{ct}.bias")

@@ -122,7 +122,7 @@ def pack_convt_weight(w):
 # tensor-core convs
 # ---------------------------------------------------------------------------------------------------------
 def conv_fwd(x, w_packed, bias, y, ksize=3, relu=False, stats=None, tile_n=0):
-    """y = conv(x, w) (+bias)(+ReLU); stats: fp32 [tiles_m, 2, Cout] partial buffer or None."""
+    """y = conv(x, w) (+bias)(+ReLU); stats: fp32 [conv_stats_rows(...), 2, Cout] partial buffer or None."""
     flags = (B2S_FLAG_RELU if relu else 0) | (B2S_FLAG_STATS if stats is not None else 0)
     Cout = y.C
     flops = 2.0 * x.N * x.H * x.W * x.C * Cout * ksize * ksize
@@ -131,8 +131,12 @@ def conv_fwd(x, w_packed, bias, y, ksize=3, relu=False, stats=None, tile_n=0):
                                 x.W, x.C, Cout, ksize, flags, tile_n, _stream()), "b2s_conv_fwd"))
 
 
-def conv_tiles_m(N, H, W):
-    return _lib.lib().b2s_conv_fwd_tiles_m(N, H, W)
+def conv_stats_rows(N, H, W, Cout, tile_n=0):
+    """rows of the [rows, 2, Cout] partial-statistics buffer conv_fwd(..., stats=...) fills for this shape"""
+    r = _lib.lib().b2s_conv_stats_rows(N, H, W, Cout, tile_n)
+    if r <= 0:
+        raise _lib.B2SError("b2s_conv_stats_rows: unsupported shape")
+    return r
 
 
 def convt_fwd(x, w_packed, bias, y, tile_n=0):
@@ -167,7 +171,7 @@ def conv3x3_wgrad(x, dz, ws, dw, tile_n=0, splits=0):
     _timed(f"wgrad3x3[{x.C}->{dz.C}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
         L.b2s_conv3x3_wgrad(x.ptr, x.cstride, dz.ptr, dz.cstride, _p(ws), x.N, x.H, x.W, x.C, dz.C, tile_n, splits,
                             _stream()), "b2s_conv3x3_wgrad"))
-    _timed("wgrad_reduce", "hbm", 4.0 * 9 * x.C * dz.C * (s + 1), lambda: check(
+    _timed(f"wgrad_reduce[{x.C}->{dz.C},s={s}]", "hbm", 4.0 * 9 * x.C * dz.C * (s + 1), lambda: check(
         L.b2s_wgrad_reduce(_p(ws), s, 9, x.C, dz.C, _p(dw), 0, _stream()), "b2s_wgrad_reduce"))
 
 
@@ -180,7 +184,7 @@ def convt_wgrad(x, dy, ws, dw, tile_n=0, splits=0):
     _timed(f"convT_wgrad[{x.C}->{dy.C}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
         L.b2s_convt2x2_wgrad(x.ptr, x.cstride, dy.ptr, dy.cstride, _p(ws), x.N, x.H, x.W, x.C, dy.C, tile_n, splits,
                              _stream()), "b2s_convt2x2_wgrad"))
-    _timed("wgrad_reduce", "hbm", 4.0 * 4 * x.C * dy.C * (s + 1), lambda: check(
+    _timed(f"wgradT_reduce[{x.C}->{dy.C},s={s}]", "hbm", 4.0 * 4 * x.C * dy.C * (s + 1), lambda: check(
         L.b2s_wgrad_reduce(_p(ws), s, 4, x.C, dy.C, _p(dw), 1, _stream()), "b2s_wgrad_reduce"))
 
 
