@@ -116,6 +116,88 @@ def test_conv3x3_fwd_bias_relu_stats(ops, N, H, W, Cin, Cout, tile_n, relu):
     report("stats.sumsq", s[1], (g64 * g64).sum(dim=(0, 2, 3)), rel=1e-5, abs_frac=1e-5)
 
 
+PAIR, HALO, LEGACY = 1 << 10, 1 << 11, 1 << 12   # kernel-variant bits of tile_n (csrc/conv_common.cuh)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,tile_n,relu", [
+    (2, 16, 16, 64, 64, PAIR, True),            # tile-pair kernel, two sets of two accumulators
+    (3, 8, 8, 64, 128, PAIR + 64, True),        # odd tile count: the last pair has one out-of-range tile
+    (2, 16, 16, 256, 512, PAIR + 256, True),    # 256-wide tiles: one accumulator set (no epilogue overlap)
+    (2, 16, 16, 256, 512, PAIR + 128, True),
+    (1, 24, 40, 64, 64, PAIR, True),            # non power-of-two extent
+    (5, 32, 32, 128, 128, PAIR, False),         # several items per CTA row-group? no: 40 tiles; phases still wrap
+    (1, 2, 128, 64, 64, HALO, True),            # halo kernel: one item (two rows, one strip)
+    (2, 4, 256, 64, 64, HALO, True),            # two strips per row
+    (1, 6, 128, 128, 128, HALO, True),          # two K chunks, 128-wide tile
+    (1, 4, 256, 128, 64, HALO, False),
+    (3, 8, 128, 64, 256, HALO, True),           # Cout 256 = two column tiles
+    (2, 16, 16, 64, 64, LEGACY, True),
+])
+def test_conv3x3_variants(ops, N, H, W, Cin, Cout, tile_n, relu):
+    """every kernel variant behind b2s_conv_fwd, forced through the variant bits of tile_n"""
+    x = bf(rnd((N, Cin, H, W), 111))
+    w = bf(rnd((Cout, Cin, 3, 3), 112, 0.05))
+    b = rnd((Cout,), 113, 0.5)
+    xa = act_from_nchw(ops, x, ctot=Cin + 64, c0=64)
+    wf, _ = ops.pack_conv_weight(w.to(DEV), want_dgrad=False)
+    ybuf = torch.full((N, H, W, Cout + 64), 5.0, dtype=torch.bfloat16, device=DEV)
+    y = ops.Act(ybuf, 0, Cout)
+    rows = ops.conv_stats_rows(N, H, W, Cout, tile_n)
+    stats = torch.full((rows, 2, Cout), float('nan'), dtype=torch.float32, device=DEV)
+    ops.conv_fwd(xa, wf, b.to(DEV), y, ksize=3, relu=relu, stats=stats, tile_n=tile_n)
+    torch.cuda.synchronize()
+    ref = O.conv3x3(x.double(), w.double(), b.double())
+    if relu:
+        ref = ref.clamp_min(0)
+    got = y.to_nchw_float()
+    report("conv3x3", got, ref)
+    assert bool((ybuf[..., Cout:] == 5.0).all()), "kernel wrote outside its channel slice"
+    s = stats.double().sum(dim=0).cpu()
+    g64 = got.double().cpu()
+    report("stats.sum", s[0], g64.sum(dim=(0, 2, 3)), rel=1e-5, abs_frac=1e-5)
+    report("stats.sumsq", s[1], (g64 * g64).sum(dim=(0, 2, 3)), rel=1e-5, abs_frac=1e-5)
+
+
+def test_conv3x3_halo_many_items(ops):
+    """halo kernel with more work items than SMs (ring phases wrap, both accumulator sets reused) vs torch fp32"""
+    N, H, W, Cin, Cout = 6, 64, 128, 64, 64
+    x = bf(rnd((N, Cin, H, W), 121)).to(DEV)
+    w = bf(rnd((Cout, Cin, 3, 3), 122, 0.05)).to(DEV)
+    b = rnd((Cout,), 123).to(DEV)
+    wf, wd = ops.pack_conv_weight(w)
+    y = ops.Act.empty(N, H, W, Cout, DEV)
+    ops.conv_fwd(ops.Act.from_nchw(x), wf, b, y, ksize=3, relu=True, tile_n=HALO)
+    ref = torch.nn.functional.conv2d(x, w, b, padding=1).clamp_min(0)
+    report("halo conv3x3 large", y.to_nchw_float(), ref)
+    y2 = ops.Act.empty(N, H, W, Cout, DEV)
+    ops.conv_fwd(ops.Act.from_nchw(x), wf, b, y2, ksize=3, relu=True, tile_n=PAIR)
+    report("pair conv3x3 large", y2.to_nchw_float(), ref)
+
+
+@pytest.mark.parametrize("tile_n", [PAIR, PAIR + 64, LEGACY])
+def test_conv1x1_and_convt_variants(ops, tile_n):
+    N, H, W, Cin, Cout = 2, 16, 16, 128, 128
+    x = bf(rnd((N, Cin, H, W), 131))
+    w = bf(rnd((Cout, Cin, 1, 1), 132, 0.1))
+    wf, _ = ops.pack_conv_weight(w.to(DEV), want_dgrad=False)
+    y = ops.Act.empty(N, H, W, Cout, DEV)
+    ops.conv_fwd(act_from_nchw(ops, x), wf, None, y, ksize=1, tile_n=tile_n)
+    torch.cuda.synchronize()
+    report("conv1x1", y.to_nchw_float(), O.conv1x1(x.double(), w.double(), None))
+    wt = bf(rnd((Cin, 64, 2, 2), 133, 0.05))
+    bt = rnd((64,), 134, 0.5)
+    dy = bf(rnd((N, 64, 2 * H, 2 * W), 135))
+    tf, td = ops.pack_convt_weight(wt.to(DEV))
+    yt = ops.Act.empty(N, 2 * H, 2 * W, 64, DEV)
+    ops.convt_fwd(act_from_nchw(ops, x), tf, bt.to(DEV), yt, tile_n=(tile_n & ~1023) + 64)
+    dx = ops.Act.empty(N, H, W, Cin, DEV)
+    ops.convt_dgrad(act_from_nchw(ops, dy), td, dx, tile_n=tile_n)
+    torch.cuda.synchronize()
+    report("convT fwd", yt.to_nchw_float(), O.conv_transpose2x2(x.double(), wt.double(), bt.double()))
+    rdx, _, _ = O.conv_transpose2x2_bwd(x.double(), wt.double(), dy.double())
+    report("convT dgrad", dx.to_nchw_float(), rdx)
+
+
 def test_conv3x3_channel_slices(ops):
     """input read from, and output written into, channel slices of wider (concat) buffers"""
     N, H, W, Cin, Cout = 1, 16, 16, 64, 64

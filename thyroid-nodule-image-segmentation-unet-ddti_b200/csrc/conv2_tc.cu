@@ -1,0 +1,403 @@
+// Tile-pair and row-halo implicit-GEMM convolution kernels (tcgen05 + TMEM + TMA, sm_100a).
+//
+// Both kernels raise the FLOPs done per byte moved L2 -> shared memory, which is what bounds conv_tc_kernel
+// (one 128-pixel tile per weight stage: 64 FLOP/B, ~45 B/clk/SM of L2 bandwidth = ~45 % of the tensor pipe):
+//
+//   PAIR  (HALO=false): every weight (B) stage is multiplied with TWO 128-pixel A tiles into two TMEM accumulators
+//                       (an M=256 tile per CTA): 87 FLOP/B at BLOCK_N=128, 131 FLOP/B at BLOCK_N=256.
+//   HALO  (HALO=true) : for images at least 128 pixels wide. A work item is two output rows x 128 pixels. The four
+//                       input rows it needs (130 pixels each, zero-filled by TMA outside the image) are staged ONCE
+//                       per 64-channel chunk; the nine filter taps are nine UMMA descriptors whose start address is
+//                       shifted by whole 128-byte pixel rows inside that staging area. Activation traffic drops
+//                       from 9x to 2x, weight traffic is shared by the two rows.
+//
+// Replaces the same reference call sites as conv_tc_kernel: nn.Conv2d(k=3,p=1) forward / input gradient and the
+// 1x1 / transposed-conv GEMMs of models/model.py:36,39,49.
+//
+// Warp roles (352 threads): warp0 = TMEM alloc + halo producer, warp1 = MMA issuer, warp2 = ring producer,
+// warps 3-6 / 7-10 = two epilogue groups (TMEM -> +bias, ReLU -> bf16 -> swizzled smem -> TMA store; BN partial sums).
+#include "conv_common.cuh"
+
+namespace b2s {
+
+constexpr int kConv2Threads = 352;
+constexpr int kHaloPix = 130;               // 128 output pixels + one halo pixel each side
+constexpr int kHaloRowBytes = 17 * 1024;    // 130 x 128 B = 16640 B, padded so every row slot stays 1024-B aligned
+
+template <int BLOCK_N, int MT, bool HALO, int STAGES, int STAGES_A>
+struct Conv2Cfg {
+  static constexpr int kSets = (2 * MT * BLOCK_N <= 512) ? 2 : 1;   // accumulator sets (double-buffered epilogue)
+  static constexpr int kTmemCols = kSets * MT * BLOCK_N;
+  static constexpr int kBTile = BLOCK_N * 128;
+  static constexpr int kAInStage = HALO ? 0 : MT * kATileBytes;
+  static constexpr int kStageBytes = kAInStage + kBTile;
+  static constexpr int kHaloStage = (MT + 2) * kHaloRowBytes;
+  static constexpr int kHaloOffset = STAGES * kStageBytes;
+  static constexpr int kStagingOffset = kHaloOffset + (HALO ? STAGES_A * kHaloStage : 0);
+  static constexpr int kBarOffset = kStagingOffset + 2 * kATileBytes;
+  static constexpr int kNumBars = 2 * STAGES + 2 * STAGES_A + 2 * kSets;
+  static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtrOffset + 16;
+  static constexpr int kDynBytes = kTotal + 1024;  // slack for manual 1024-B alignment
+  static_assert(kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns");
+  static_assert(kDynBytes <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA may use");
+  static_assert(MT == 1 || MT == 2, "one or two M tiles per work item");
+};
+
+// Row-shifted operands: the tensor core applies the SWIZZLE_128B XOR to the absolute shared-memory address bits, the
+// same function TMA used when it wrote the 1024-B aligned row slots, so a descriptor may start at any 128-byte pixel
+// row of a slot with base_offset = 0 (measured on B200: base_offset = (addr >> 7) & 7 gives wrong results).
+template <int BLOCK_N, int MT, bool HALO, int STAGES, int STAGES_A>
+__global__ void __launch_bounds__(kConv2Threads, 1)
+conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const ConvTcParams p) {
+  using L = Conv2Cfg<BLOCK_N, MT, HALO, STAGES, STAGES_A>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* halo = smem + L::kHaloOffset;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* afull_bar = empty_bar + STAGES;
+  uint64_t* aempty_bar = afull_bar + STAGES_A;
+  uint64_t* tmem_full_bar = aempty_bar + STAGES_A;     // [kSets]
+  uint64_t* tmem_empty_bar = tmem_full_bar + L::kSets;  // [kSets]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- static schedule: CTA c owns column tile c % tiles_nn and the work items mgroup + i * num_mgroups -------
+  const int n_tile = blockIdx.x % p.tiles_nn;
+  const int mgroup = blockIdx.x / p.tiles_nn;
+  const int num_mgroups = gridDim.x / p.tiles_nn;
+  const int ncol0 = n_tile * BLOCK_N;
+  const int my_items = (p.items_m - mgroup + num_mgroups - 1) / num_mgroups;
+  const int k_iters = p.num_taps * p.k_chunks;
+  const int strips = p.tiles_w;          // HALO: 128-pixel strips per row
+  const int hpairs = p.H >> 1;           // HALO: row pairs per image
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      tma_prefetch_desc(&tmOut);
+    }
+    tmem_alloc(tmem_ptr_smem, L::kTmemCols);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < STAGES_A; ++i) {
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
+    }
+    for (int s = 0; s < L::kSets; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], MT == 2 ? 8 : 4);   // one arrival per epilogue warp that drains the set
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (HALO && lane == 0) {
+      // ===== halo producer: (MT + 2) input rows x 130 pixels per (work item, 64-channel chunk) =====
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int i = 0; i < my_items; ++i) {
+        const int item = mgroup + i * num_mgroups;
+        const int ws = item % strips;
+        const int hp = (item / strips) % hpairs;
+        const int n = item / (strips * hpairs);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&aempty_bar[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&afull_bar[sa], (MT + 2) * kHaloPix * 128);
+          uint8_t* dst = halo + sa * L::kHaloStage;
+#pragma unroll
+          for (int r = 0; r < MT + 2; ++r)
+            tma_load_4d(&tmA, &afull_bar[sa], dst + r * kHaloRowBytes, kc * kBlockK, ws * 128 - 1, 2 * hp - 1 + r, n);
+          if (++sa == STAGES_A) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ===== ring producer: weight tiles (HALO) or MT activation tiles + one weight tile per stage =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_items; ++i) {
+        const int item = mgroup + i * num_mgroups;
+        if (HALO) {
+          for (int kc = 0; kc < p.k_chunks; ++kc)
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], L::kBTile);
+              tma_load_2d(&tmB, &full_bar[stage], ring + stage * L::kStageBytes, kc * kBlockK, tap * p.n_total + ncol0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        } else {
+          int w0[MT], h0[MT], n0[MT];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int m_tile = item * MT + mt;
+            w0[mt] = (m_tile % p.tiles_w) * p.bw;
+            h0[mt] = ((m_tile / p.tiles_w) % p.tiles_h) * p.bh;
+            n0[mt] = (m_tile / (p.tiles_w * p.tiles_h)) * p.bn;
+          }
+          for (int it = 0; it < k_iters; ++it) {
+            const int tap = it / p.k_chunks;
+            const int kc = it - tap * p.k_chunks;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            uint8_t* st = ring + stage * L::kStageBytes;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              uint8_t* a_dst = st + mt * kATileBytes;
+              if (p.a_mode == A_CONV3) {
+                const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;
+                tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0[mt] + dw, h0[mt] + dh, n0[mt]);
+              } else if (p.a_mode == A_1X1) {
+                tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0[mt], h0[mt], n0[mt]);
+              } else {  // A_CONVT_DGRAD: dY viewed as (C, b, j, a, i*N)
+                tma_load_5d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, tap & 1, w0[mt], tap >> 1,
+                            n0[mt] * p.H + h0[mt]);
+              }
+            }
+            tma_load_2d(&tmB, &full_bar[stage], st + L::kAInStage, kc * kBlockK, tap * p.n_total + ncol0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (single thread) =====
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int stage = 0, sa = 0;
+      uint32_t phase = 0, pa = 0;
+      for (int i = 0; i < my_items; ++i) {
+        const int set = i % L::kSets;
+        mbar_wait(&tmem_empty_bar[set], ((i / L::kSets) & 1) ^ 1);   // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + set * MT * BLOCK_N;
+        if (HALO) {
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(&afull_bar[sa], pa);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(halo + sa * L::kHaloStage);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int th = tap / 3, tw = tap - th * 3;   // input row offset th (= dh + 1), pixel offset tw (= dw + 1)
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(ring + stage * L::kStageBytes);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t a_row = a_base + (mt + th) * kHaloRowBytes + tw * 128;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  const uint64_t adesc = umma_smem_desc_sw128(a_row + k * 32, 16, 1024);
+                  const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                  umma_bf16(acc0 + mt * BLOCK_N, adesc, bdesc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                }
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&aempty_bar[sa]);
+            if (++sa == STAGES_A) { sa = 0; pa ^= 1; }
+          }
+        } else {
+          for (int it = 0; it < k_iters; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(ring + stage * L::kStageBytes);
+            const uint32_t b_addr = a_addr + L::kAInStage;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                const uint64_t adesc = umma_smem_desc_sw128(a_addr + mt * kATileBytes + k * 32, 16, 1024);
+                const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                umma_bf16(acc0 + mt * BLOCK_N, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full_bar[set]);
+      }
+    }
+  } else {
+    // ===== epilogue groups =====
+    const int g = (warp - 3) >> 2;   // group 0: warps 3-6, group 1: warps 7-10
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;   // tile row == TMEM lane
+    const bool do_relu = p.flags & B2S_FLAG_RELU;
+    const bool do_stats = (p.flags & B2S_FLAG_STATS) && p.stats != nullptr;
+    uint8_t* stage_buf = smem + L::kStagingOffset + g * kATileBytes;
+    const int bar_id = 1 + g;
+    const int wl = row % p.bw;
+    const int hl = (row / p.bw) % p.bh;
+    const int nl = row / (p.bw * p.bh);
+    float st_acc[BLOCK_N / 64][4];
+#pragma unroll
+    for (int s = 0; s < BLOCK_N / 64; ++s) st_acc[s][0] = st_acc[s][1] = st_acc[s][2] = st_acc[s][3] = 0.f;
+
+    for (int i = (MT == 2 ? 0 : g); i < my_items; i += (MT == 2 ? 1 : 2)) {
+      const int item = mgroup + i * num_mgroups;
+      const int set = MT == 2 ? i % L::kSets : g;
+      const uint32_t par = MT == 2 ? (i / L::kSets) & 1 : (i >> 1) & 1;
+      int w0, h0, n0;
+      bool valid;
+      if (HALO) {
+        w0 = (item % strips) * 128;
+        h0 = 2 * ((item / strips) % hpairs) + g;
+        n0 = item / (strips * hpairs);
+        valid = true;
+      } else {
+        const int m_tile = MT == 2 ? item * 2 + g : item;
+        w0 = (m_tile % p.tiles_w) * p.bw;
+        h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.bh;
+        n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.bn;
+        valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
+      }
+      mbar_wait(&tmem_full_bar[set], par);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (set * MT + (MT == 2 ? g : 0)) * BLOCK_N;
+
+#pragma unroll
+      for (int s = 0; s < BLOCK_N / 64; ++s) {
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + s * 64;
+        tmem_ld_32x32(taddr, v0);
+        tmem_ld_32x32(taddr + 32, v1);
+        tmem_ld_wait();
+        if (s == BLOCK_N / 64 - 1) {
+          // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[set]);
+        }
+        const int col_base = ncol0 + s * 64;
+        const int bias_base = col_base % p.cout_sub;
+        uint32_t packed[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(j < 16 ? v0[2 * j] : v1[2 * j - 32]);
+          float b = __uint_as_float(j < 16 ? v0[2 * j + 1] : v1[2 * j - 31]);
+          if (p.bias != nullptr) {
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + bias_base) + j);
+            a += bb.x;
+            b += bb.y;
+          }
+          if (do_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          if (!valid) { a = 0.f; b = 0.f; }
+          packed[j] = pack_bf16x2(a, b);
+        }
+        // the previous TMA store of this group must have finished READING the staging tile
+        if (row == 0) tma_store_wait_read<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 val = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+          *reinterpret_cast<uint4*>(stage_buf + row * 128 + ((c ^ (row & 7)) << 4)) = val;
+        }
+        if (do_stats) {
+          // column sums over this warp's own 32 rows, taken from the bf16-rounded values actually stored
+          __syncwarp();
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const int chunk = lane >> 2, within = (lane & 3) * 4;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const int rr = q * 32 + r;
+            const uint32_t u =
+                *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
+            const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+            s0 += x0; s1 += x1;
+            q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+          }
+          st_acc[s][0] += s0; st_acc[s][1] += s1; st_acc[s][2] += q0; st_acc[s][3] += q1;
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (row == 0) {
+          if (p.out_mode == OUT_4D) {
+            tma_store_4d(&tmOut, stage_buf, col_base, w0, h0, n0);
+          } else {  // convT forward: the 64-column block belongs to one (a,b) sub-position
+            const int ab = col_base / p.cout_sub;
+            tma_store_5d(&tmOut, stage_buf, col_base - ab * p.cout_sub, ab & 1, w0, ab >> 1, n0 * p.H + h0);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    if (row == 0) tma_store_wait_read<0>();
+    if (do_stats) {
+      // one partial row per (CTA row-group, epilogue group): [2*mgroup + g][2][n_total]; scratch aliases the
+      // group's staging tile (its last TMA store has been read out above)
+      float* sb = reinterpret_cast<float*>(stage_buf);
+      float* out_row = p.stats + static_cast<size_t>(2 * mgroup + g) * 2 * p.n_total;
+#pragma unroll
+      for (int s = 0; s < BLOCK_N / 64; ++s) {
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        sb[q * 128 + 2 * lane] = st_acc[s][0]; sb[q * 128 + 2 * lane + 1] = st_acc[s][1];
+        sb[q * 128 + 64 + 2 * lane] = st_acc[s][2]; sb[q * 128 + 64 + 2 * lane + 1] = st_acc[s][3];
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const int which = row >> 6, col = row & 63;
+        float acc = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) acc += sb[wq * 128 + which * 64 + col];
+        out_row[which * p.n_total + ncol0 + s * 64 + col] = acc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, L::kTmemCols);
+  }
+}
+
+template <int BLOCK_N, int MT, bool HALO, int STAGES, int STAGES_A>
+static int launch_conv2_t(int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                          const ConvTcParams& p, cudaStream_t stream) {
+  using L = Conv2Cfg<BLOCK_N, MT, HALO, STAGES, STAGES_A>;
+  auto kfn = conv2_tc_kernel<BLOCK_N, MT, HALO, STAGES, STAGES_A>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv2_tc_kernel)");
+    attr_set = true;
+  }
+  kfn<<<grid, kConv2Threads, L::kDynBytes, stream>>>(tmA, tmB, tmOut, p);
+  return check_launch("conv2_tc_kernel");
+}
+
+int launch_conv2(const ConvPlan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                 const ConvTcParams& p, cudaStream_t stream) {
+  count_launch();
+  if (pl.kind == CONV_HALO) {
+    switch (pl.block_n) {
+      case 64:  return launch_conv2_t<64, 2, true, 6, 2>(pl.grid, tmA, tmB, tmOut, p, stream);
+      case 128: return launch_conv2_t<128, 2, true, 3, 2>(pl.grid, tmA, tmB, tmOut, p, stream);
+    }
+  } else if (pl.kind == CONV_PAIR) {
+    switch (pl.block_n) {
+      case 64:  return launch_conv2_t<64, 2, false, 4, 0>(pl.grid, tmA, tmB, tmOut, p, stream);
+      case 128: return launch_conv2_t<128, 2, false, 4, 0>(pl.grid, tmA, tmB, tmOut, p, stream);
+      case 256: return launch_conv2_t<256, 2, false, 3, 0>(pl.grid, tmA, tmB, tmOut, p, stream);
+    }
+  }
+  return set_error(B2S_ERR_ARG, "launch_conv2: unsupported variant / tile_n");
+}
+
+}  // namespace b2s

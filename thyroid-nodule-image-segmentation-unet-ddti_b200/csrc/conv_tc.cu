@@ -10,33 +10,12 @@
 // conv_tc_kernel is persistent (one CTA per SM, 320 threads): warp0 = TMA producer (+TMEM alloc), warp1 = MMA
 // issuer, warps 2-5 / 6-9 = two epilogue groups draining the two TMEM accumulators alternately.
 // wgrad_tc_kernel runs one long split-K tile per CTA (192 threads, one epilogue group).
-#include "ptx.cuh"
-#include "b2s_internal.h"
+#include "conv_common.cuh"
 
 namespace b2s {
 
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kNumThreads = 192;   // wgrad kernel: warp0 TMA, warp1 MMA, warps 2-5 epilogue
 
-enum AMode : int { A_CONV3 = 0, A_1X1 = 1, A_CONVT_DGRAD = 2 };
-enum OutMode : int { OUT_4D = 0, OUT_CONVT_5D = 1 };
-
-struct ConvTcParams {
-  int bw, bh, bn;                  // pixel box of one M tile, bw*bh*bn == 128
-  int tiles_w, tiles_h, tiles_n;   // tiles over (W, H, N)
-  int tiles_m;                     // tiles_w * tiles_h * tiles_n
-  int W, H, N;                     // pixel space of the GEMM rows
-  int num_taps, k_chunks;          // K loop = taps x (Cin/64)
-  int a_mode, out_mode;
-  int n_total;                     // GEMM N (= Cout; 4*Cout for convT forward)
-  int cout_sub;                    // convT forward: Cout per (a,b) sub-position; else n_total
-  int tiles_nn;                    // n_total / BLOCK_N
-  int flags;                       // B2S_FLAG_*
-  const float* bias;               // [cout_sub] or nullptr
-  float* stats;                    // [2 * gridDim.x / tiles_nn][2][n_total] partial column sums, or nullptr
-};
 
 constexpr int kConvThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-5 epilogue group 0, warps 6-9 epilogue group 1
 
@@ -466,99 +445,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Host side
-// ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* ptr = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  return fn;
-}
-
-// bf16 tensor map, SWIZZLE_128B, inner box = 64 elements. dims/strides innermost first; strides in BYTES for
-// dims 1..rank-1.
-static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                     const uint32_t* box) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return set_error(B2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t gdim[5], gstr[4];
-  cuuint32_t bdim[5], estr[5];
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
-  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_b[i];
-  if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(B2S_ERR_ARG, "tensor base not 16-B aligned");
-  for (int i = 0; i + 1 < rank; ++i)
-    if (gstr[i] & 15) return set_error(B2S_ERR_ARG, "tensor stride not a multiple of 16 B");
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char msg[256];
-    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu %llu box %u %u %u %u)",
-             (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1],
-             (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0), bdim[0],
-             bdim[1], rank > 2 ? bdim[2] : 0, rank > 3 ? bdim[3] : 0);
-    return set_error(B2S_ERR_CUDA, msg);
-  }
-  return B2S_OK;
-}
-
-static int pow2_ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
-
-// Split `total` (power of two) pixels of one tile over (w, h, n).
-static void pick_box(int W, int H, int N, int total, int* bw, int* bh, int* bn) {
-  int w = pow2_ceil(W); if (w > total) w = total;
-  int h = pow2_ceil(H); if (h > total / w) h = total / w;
-  int n = total / (w * h);
-  (void)N;
-  *bw = w; *bh = h; *bn = n;
-}
-
-// NHWC activation map (C, W, H, N) over a channel slice of a buffer whose pixel stride is cstride elements.
-static int make_act_map4(CUtensorMap* m, const void* base, int C, int W, int H, int N, int cstride, int bw, int bh,
-                         int bn) {
-  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-  uint64_t str[3] = {(uint64_t)cstride * 2, (uint64_t)W * cstride * 2, (uint64_t)H * W * cstride * 2};
-  uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
-  return make_tmap(m, base, 4, dims, str, box);
-}
-// 2x-upsampled NHWC tensor [N, 2Hi, 2Wi, C] viewed as (C, b, j, a, i*N) so that one (a,b) sub-lattice is a box.
-static int make_up_map5(CUtensorMap* m, const void* base, int C, int Wi, int Hi, int N, int cstride, int bw,
-                        int bhn) {
-  const uint64_t Wo = 2ull * Wi;
-  uint64_t dims[5] = {(uint64_t)C, 2, (uint64_t)Wi, 2, (uint64_t)Hi * N};
-  uint64_t str[4] = {(uint64_t)cstride * 2, 2ull * cstride * 2, Wo * cstride * 2, 2ull * Wo * cstride * 2};
-  uint32_t box[5] = {64, 1, (uint32_t)bw, 1, (uint32_t)bhn};
-  return make_tmap(m, base, 5, dims, str, box);
-}
-
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
-
-// Persistent grid: one CTA per SM, rounded down to a multiple of the column-tile count.
-static int conv_grid(int tiles_m, int tiles_nn) {
-  long long total = static_cast<long long>(tiles_m) * tiles_nn;
-  int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-  grid = grid / tiles_nn * tiles_nn;
-  if (grid < tiles_nn) grid = tiles_nn;
-  return grid;
-}
-
 template <int BLOCK_N, int STAGES>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                        const ConvTcParams& p, cudaStream_t stream) {
@@ -574,11 +460,15 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return check_launch("conv_tc_kernel");
 }
 
-static int dispatch_conv(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+// Routes a planned conv to conv_tc_kernel (one tile per stage) or to the tile-pair / halo kernels of conv2_tc.cu.
+static int dispatch_conv(const ConvPlan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                          ConvTcParams& p, cudaStream_t stream) {
-  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.bw = pl.bw; p.bh = pl.bh; p.bn = pl.bn;
+  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.tiles_n = pl.tiles_n; p.tiles_m = pl.tiles_m;
+  p.tiles_nn = pl.tiles_nn; p.items_m = pl.items_m;
+  if (pl.kind != CONV_LEGACY) return launch_conv2(pl, tmA, tmB, tmOut, p, stream);
   count_launch();
-  switch (block_n) {
+  switch (pl.block_n) {
     case 64:  return launch_conv<64, 7>(tmA, tmB, tmOut, p, stream);    // 7 x 24 KB + 32 KB staging
     case 128: return launch_conv<128, 5>(tmA, tmB, tmOut, p, stream);   // 5 x 32 KB + 32 KB staging
     case 256: return launch_conv<256, 3>(tmA, tmB, tmOut, p, stream);   // 3 x 48 KB + 32 KB staging (all 512 TMEM cols)
@@ -586,10 +476,11 @@ static int dispatch_conv(int block_n, const CUtensorMap& tmA, const CUtensorMap&
   }
 }
 
-static int auto_block_n(int n_total, int cout_sub, int tile_n) {
-  if (tile_n == 0) tile_n = (cout_sub >= 128) ? 128 : 64;
-  if (tile_n > cout_sub) tile_n = cout_sub;
-  return tile_n;
+static int make_weight_map(CUtensorMap* m, const void* w_packed, int K, int rows, int block_n) {
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  uint64_t str[1] = {(uint64_t)K * 2};
+  uint32_t box[2] = {64, (uint32_t)block_n};
+  return make_tmap(m, w_packed, 2, dims, str, box);
 }
 
 }  // namespace b2s
@@ -606,40 +497,35 @@ extern "C" int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, 
   if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: Cin and Cout must be multiples of 64");
   if (N <= 0 || H <= 0 || W <= 0) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: empty tensor");
   if ((flags & B2S_FLAG_STATS) && !stats_partial) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: stats buffer missing");
-  const int block_n = auto_block_n(Cout, Cout, tile_n);
-  if (Cout % block_n) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: tile_n must divide Cout");
-
   ConvTcParams p{};
-  pick_box(W, H, N, kBlockM, &p.bw, &p.bh, &p.bn);
-  p.tiles_w = (W + p.bw - 1) / p.bw; p.tiles_h = (H + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.a_mode = ksize == 3 ? A_CONV3 : A_1X1; p.out_mode = OUT_4D;
+  ConvPlan pl;
+  if (conv_plan(N, H, W, Cout, Cout, p.a_mode, p.out_mode, tile_n, &pl))
+    return set_error(B2S_ERR_ARG, "b2s_conv_fwd: tile_n must be 64/128/256, divide Cout and suit the forced variant");
   p.W = W; p.H = H; p.N = N;
   p.num_taps = ksize * ksize; p.k_chunks = Cin / 64;
-  p.a_mode = ksize == 3 ? A_CONV3 : A_1X1; p.out_mode = OUT_4D;
-  p.n_total = Cout; p.cout_sub = Cout; p.tiles_nn = Cout / block_n;
+  p.n_total = Cout; p.cout_sub = Cout;
   p.flags = flags; p.bias = bias; p.stats = stats_partial;
 
   CUtensorMap tmA, tmB, tmOut;
   int rc;
-  if ((rc = make_act_map4(&tmA, x, Cin, W, H, N, x_cstride, p.bw, p.bh, p.bn))) return rc;
-  {
-    uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)p.num_taps * Cout};
-    uint64_t str[1] = {(uint64_t)Cin * 2};
-    uint32_t box[2] = {64, (uint32_t)block_n};
-    if ((rc = make_tmap(&tmB, w_packed, 2, dims, str, box))) return rc;
+  if (pl.kind == CONV_HALO) {
+    // one input row of 130 pixels (128 + halo) per load; out-of-image pixels are zero-filled by TMA
+    if ((rc = make_act_map4(&tmA, x, Cin, W, H, N, x_cstride, 130, 1, 1))) return rc;
+  } else {
+    if ((rc = make_act_map4(&tmA, x, Cin, W, H, N, x_cstride, pl.bw, pl.bh, pl.bn))) return rc;
   }
-  if ((rc = make_act_map4(&tmOut, y, Cout, W, H, N, y_cstride, p.bw, p.bh, p.bn))) return rc;
-  return dispatch_conv(block_n, tmA, tmB, tmOut, p, stream);
+  if ((rc = make_weight_map(&tmB, w_packed, Cin, p.num_taps * Cout, pl.block_n))) return rc;
+  if ((rc = make_act_map4(&tmOut, y, Cout, W, H, N, y_cstride, pl.bw, pl.bh, pl.bn))) return rc;
+  return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
 }
 
-// Rows of the stats_partial buffer b2s_conv_fwd writes for this shape: 2 per CTA row-group of the persistent grid.
+// Rows of the stats_partial buffer b2s_conv_fwd (ksize 3) writes for this shape: 2 per CTA row-group of the
+// persistent grid of whichever kernel variant conv_plan picks.
 extern "C" int b2s_conv_stats_rows(int N, int H, int W, int Cout, int tile_n) {
-  int bw, bh, bn;
-  pick_box(W, H, N, kBlockM, &bw, &bh, &bn);
-  const int tiles_m = ((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((N + bn - 1) / bn);
-  const int block_n = auto_block_n(Cout, Cout, tile_n);
-  if (block_n <= 0 || Cout % block_n) return -1;
-  const int tiles_nn = Cout / block_n;
-  return 2 * (conv_grid(tiles_m, tiles_nn) / tiles_nn);
+  ConvPlan pl;
+  if (conv_plan(N, H, W, Cout, Cout, A_CONV3, OUT_4D, tile_n, &pl)) return -1;
+  return pl.stats_rows;
 }
 
 // ConvTranspose2d(k=2,s=2) forward: x [N,Hi,Wi,Cin] -> y [N,2Hi,2Wi,Cout]; w_packed [(a*2+b)*Cout+co][Cin].
@@ -648,28 +534,22 @@ extern "C" int b2s_convt2x2_fwd(const void* x, int x_cstride, const void* w_pack
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !w_packed || !y) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: null pointer");
   if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: channels must be multiples of 64");
-  const int block_n = auto_block_n(4 * Cout, Cout, tile_n);
-  if (Cout % block_n) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: tile_n must divide Cout");
   ConvTcParams p{};
-  pick_box(Wi, Hi, N, kBlockM, &p.bw, &p.bh, &p.bn);
-  if (p.bn > 1 && p.bh != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: unsupported tiny non-pow2 image");
-  p.tiles_w = (Wi + p.bw - 1) / p.bw; p.tiles_h = (Hi + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.a_mode = A_1X1; p.out_mode = OUT_CONVT_5D;
+  ConvPlan pl;
+  if (conv_plan(N, Hi, Wi, 4 * Cout, Cout, p.a_mode, p.out_mode, tile_n, &pl))
+    return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: tile_n must be 64/128/256 and divide Cout");
+  if (pl.bn > 1 && pl.bh != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: unsupported tiny non-pow2 image");
   p.W = Wi; p.H = Hi; p.N = N;
   p.num_taps = 1; p.k_chunks = Cin / 64;
-  p.a_mode = A_1X1; p.out_mode = OUT_CONVT_5D;
-  p.n_total = 4 * Cout; p.cout_sub = Cout; p.tiles_nn = 4 * Cout / block_n;
+  p.n_total = 4 * Cout; p.cout_sub = Cout;
   p.flags = 0; p.bias = bias; p.stats = nullptr;
   CUtensorMap tmA, tmB, tmOut;
   int rc;
-  if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hi, N, x_cstride, p.bw, p.bh, p.bn))) return rc;
-  {
-    uint64_t dims[2] = {(uint64_t)Cin, 4ull * Cout};
-    uint64_t str[1] = {(uint64_t)Cin * 2};
-    uint32_t box[2] = {64, (uint32_t)block_n};
-    if ((rc = make_tmap(&tmB, w_packed, 2, dims, str, box))) return rc;
-  }
-  if ((rc = make_up_map5(&tmOut, y, Cout, Wi, Hi, N, y_cstride, p.bw, p.bh * p.bn))) return rc;
-  return dispatch_conv(block_n, tmA, tmB, tmOut, p, stream);
+  if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hi, N, x_cstride, pl.bw, pl.bh, pl.bn))) return rc;
+  if ((rc = make_weight_map(&tmB, w_packed, Cin, 4 * Cout, pl.block_n))) return rc;
+  if ((rc = make_up_map5(&tmOut, y, Cout, Wi, Hi, N, y_cstride, pl.bw, pl.bh * pl.bn))) return rc;
+  return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
 }
 
 // ConvTranspose2d(k=2,s=2) input gradient: dy [N,2Hi,2Wi,Cout] -> dx [N,Hi,Wi,Cin]; w_packed [(a*2+b)*Cin+ci][Cout].
@@ -678,28 +558,22 @@ extern "C" int b2s_convt2x2_dgrad(const void* dy, int dy_cstride, const void* w_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!dy || !w_packed || !dx) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: null pointer");
   if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: channels must be multiples of 64");
-  const int block_n = auto_block_n(Cin, Cin, tile_n);
-  if (Cin % block_n) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: tile_n must divide Cin");
   ConvTcParams p{};
-  pick_box(Wi, Hi, N, kBlockM, &p.bw, &p.bh, &p.bn);
-  if (p.bn > 1 && p.bh != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: unsupported tiny non-pow2 image");
-  p.tiles_w = (Wi + p.bw - 1) / p.bw; p.tiles_h = (Hi + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+  p.a_mode = A_CONVT_DGRAD; p.out_mode = OUT_4D;
+  ConvPlan pl;
+  if (conv_plan(N, Hi, Wi, Cin, Cin, p.a_mode, p.out_mode, tile_n, &pl))
+    return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: tile_n must be 64/128/256 and divide Cin");
+  if (pl.bn > 1 && pl.bh != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: unsupported tiny non-pow2 image");
   p.W = Wi; p.H = Hi; p.N = N;
   p.num_taps = 4; p.k_chunks = Cout / 64;
-  p.a_mode = A_CONVT_DGRAD; p.out_mode = OUT_4D;
-  p.n_total = Cin; p.cout_sub = Cin; p.tiles_nn = Cin / block_n;
+  p.n_total = Cin; p.cout_sub = Cin;
   p.flags = 0; p.bias = nullptr; p.stats = nullptr;
   CUtensorMap tmA, tmB, tmOut;
   int rc;
-  if ((rc = make_up_map5(&tmA, dy, Cout, Wi, Hi, N, dy_cstride, p.bw, p.bh * p.bn))) return rc;
-  {
-    uint64_t dims[2] = {(uint64_t)Cout, 4ull * Cin};
-    uint64_t str[1] = {(uint64_t)Cout * 2};
-    uint32_t box[2] = {64, (uint32_t)block_n};
-    if ((rc = make_tmap(&tmB, w_packed, 2, dims, str, box))) return rc;
-  }
-  if ((rc = make_act_map4(&tmOut, dx, Cin, Wi, Hi, N, dx_cstride, p.bw, p.bh, p.bn))) return rc;
-  return dispatch_conv(block_n, tmA, tmB, tmOut, p, stream);
+  if ((rc = make_up_map5(&tmA, dy, Cout, Wi, Hi, N, dy_cstride, pl.bw, pl.bh * pl.bn))) return rc;
+  if ((rc = make_weight_map(&tmB, w_packed, Cout, 4 * Cin, pl.block_n))) return rc;
+  if ((rc = make_act_map4(&tmOut, dx, Cin, Wi, Hi, N, dx_cstride, pl.bw, pl.bh, pl.bn))) return rc;
+  return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
 }
 
 // ---- wgrad -----------------------------------------------------------------------------------
@@ -732,9 +606,12 @@ static int wgrad_plan(int N, int H, int W, int Cin, int Cout, int num_taps, int 
   p->chunks_total = p->chunks_w * p->chunks_h * p->chunks_n;
   int splits = splits_req;
   if (splits <= 0) {
-    // about two CTAs per SM in flight, keep >= 16 K-chunks per CTA (every split costs a K-sized fp32 partial)
+    // keep >= 16 K-chunks per CTA (every split costs a K-sized fp32 partial) and
+    // the grid must fit in ONE wave: CTAs resident per SM follow from the shared memory of the instantiation
+    // (block_n 64: 6 x 24 KB, 128: 3 x 32 KB, 256: 4 x 48 KB -> 1, 2, 1 CTAs per SM)
     const int base = p->m_tiles * p->tiles_nn;
-    splits = (2 * 148 + base / 2) / base;
+    const int resident = num_sms() * (block_n == 128 ? 2 : 1);
+    splits = resident / base;
     const int max_by_work = p->chunks_total / 16 > 0 ? p->chunks_total / 16 : 1;
     if (splits > max_by_work) splits = max_by_work;
     if (splits < 1) splits = 1;
