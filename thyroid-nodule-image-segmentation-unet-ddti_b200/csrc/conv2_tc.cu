@@ -176,63 +176,71 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (single thread) =====
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
-      int stage = 0, sa = 0;
-      uint32_t phase = 0, pa = 0;
-      for (int i = 0; i < my_items; ++i) {
-        const int set = i % L::kSets;
-        mbar_wait(&tmem_empty_bar[set], ((i / L::kSets) & 1) ^ 1);   // epilogue has drained this accumulator set
-        tc_fence_after();
-        const uint32_t acc0 = tmem_base + set * MT * BLOCK_N;
-        if (HALO) {
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(&afull_bar[sa], pa);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(halo + sa * L::kHaloStage);
-            for (int tap = 0; tap < 9; ++tap) {
-              const int th = tap / 3, tw = tap - th * 3;   // input row offset th (= dh + 1), pixel offset tw (= dw + 1)
-              mbar_wait(&full_bar[stage], phase);
-              tc_fence_after();
-              const uint32_t b_addr = smem_u32(ring + stage * L::kStageBytes);
+    // ===== MMA issuer: the whole warp walks the pipeline so that every address stays in uniform registers; one
+    // elected lane issues tcgen05.mma / tcgen05.commit. Descriptors are advanced by adding to their low word. =====
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    const uint32_t tbase = __reduce_or_sync(0xffffffffu, tmem_base);   // warp-uniform copy
+    const bool leader = elect_one();
+    const uint32_t desc_hi = static_cast<uint32_t>(umma_smem_desc_sw128(0, 16, 1024) >> 32);
+    const uint32_t desc_lo0 = static_cast<uint32_t>(umma_smem_desc_sw128(0, 16, 1024));   // LBO field, address 0
+    const uint32_t ring_lo = desc_lo0 + (smem_u32(ring) >> 4);
+    const uint32_t halo_lo = desc_lo0 + (smem_u32(halo) >> 4);
+    int stage = 0, sa = 0;
+    uint32_t phase = 0, pa = 0;
+    for (int i = 0; i < my_items; ++i) {
+      const int set = i % L::kSets;
+      mbar_wait(&tmem_empty_bar[set], ((i / L::kSets) & 1) ^ 1);   // epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t acc0 = tbase + set * MT * BLOCK_N;
+      if (HALO) {
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&afull_bar[sa], pa);
+          const uint32_t a_lo = halo_lo + sa * (L::kHaloStage >> 4);
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t a_row = a_base + (mt + th) * kHaloRowBytes + tw * 128;
-#pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                  const uint64_t adesc = umma_smem_desc_sw128(a_row + k * 32, 16, 1024);
-                  const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                  umma_bf16(acc0 + mt * BLOCK_N, adesc, bdesc, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-                }
-              }
-              umma_commit(&empty_bar[stage]);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-            umma_commit(&aempty_bar[sa]);
-            if (++sa == STAGES_A) { sa = 0; pa ^= 1; }
-          }
-        } else {
-          for (int it = 0; it < k_iters; ++it) {
+          for (int tap = 0; tap < 9; ++tap) {
+            constexpr int kRow16 = kHaloRowBytes >> 4;
+            const int th = tap / 3, tw = tap - th * 3;   // input row offset (dh + 1), pixel offset (dw + 1)
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(ring + stage * L::kStageBytes);
-            const uint32_t b_addr = a_addr + L::kAInStage;
+            const uint32_t b_lo = ring_lo + stage * (L::kStageBytes >> 4);
+            if (leader) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_bf16_lohi(acc0 + mt * BLOCK_N, a_lo + (mt + th) * kRow16 + tw * 8 + k * 2, desc_hi, b_lo + k * 2,
+                                 desc_hi, idesc, (tap | k) != 0 ? 1u : static_cast<uint32_t>(kc != 0));
+              }
+              umma_commit(&empty_bar[stage]);
+              if (tap == 8) umma_commit(&aempty_bar[sa]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++sa == STAGES_A) { sa = 0; pa ^= 1; }
+        }
+      } else {
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = ring_lo + stage * (L::kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + (L::kAInStage >> 4);
+          if (leader) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                const uint64_t adesc = umma_smem_desc_sw128(a_addr + mt * kATileBytes + k * 32, 16, 1024);
-                const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                umma_bf16(acc0 + mt * BLOCK_N, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16_lohi(acc0 + mt * BLOCK_N, a_lo + mt * (kATileBytes >> 4) + k * 2, desc_hi, b_lo + k * 2, desc_hi,
+                               idesc, k != 0 ? 1u : static_cast<uint32_t>(it != 0));
             }
             umma_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[set]);
       }
+      if (leader) umma_commit(&tmem_full_bar[set]);
+      __syncwarp();
     }
   } else {
     // ===== epilogue groups =====
