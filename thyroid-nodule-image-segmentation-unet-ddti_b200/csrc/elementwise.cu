@@ -202,6 +202,148 @@ conv3x3_c1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
   }
 }
 
+// Four-pixels-per-thread variants (W % 4 == 0): each thread owns 8 output channels of 4 consecutive pixels of one
+// image row, so the 3x6 input window is read once (three aligned float4 + six scalars) for 288 FMAs.
+__device__ __forceinline__ void c1_load_window(const float* __restrict__ xi, int hq, int wq, int H, int W,
+                                               float (&xv)[3][6]) {
+#pragma unroll
+  for (int dr = 0; dr < 3; ++dr) {
+    const int hh = hq + dr - 1;
+    if (hh >= 0 && hh < H) {
+      const float* rowp = xi + static_cast<long long>(hh) * W + wq;
+      const float4 c = __ldg(reinterpret_cast<const float4*>(rowp));
+      xv[dr][0] = wq > 0 ? __ldg(rowp - 1) : 0.f;
+      xv[dr][1] = c.x; xv[dr][2] = c.y; xv[dr][3] = c.z; xv[dr][4] = c.w;
+      xv[dr][5] = wq + 4 < W ? __ldg(rowp + 4) : 0.f;
+    } else {
+#pragma unroll
+      for (int dc = 0; dc < 6; ++dc) xv[dr][dc] = 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       __nv_bfloat16* __restrict__ r, float* __restrict__ stats_partial, int N, int H, int W, int Cout,
+                       int flags) {
+  __shared__ float red[kThreads * 16];
+  const int groups = Cout / 8;
+  const int qpi = kThreads / groups;        // pixel quads per block iteration
+  const int cg = threadIdx.x % groups;
+  const int ql = threadIdx.x / groups;
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int co = cg * 8 + k;
+    br[k] = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][k] = w[co * 9 + t];
+  }
+  float st[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) st[k] = 0.f;
+  const unsigned nquads = static_cast<unsigned>(N) * H * W / 4;
+  const bool relu = flags & B2S_FLAG_RELU;
+  for (unsigned q0 = blockIdx.x * qpi; q0 < nquads; q0 += gridDim.x * qpi) {
+    const unsigned qd = q0 + ql;
+    if (qd < nquads) {
+      const unsigned p = qd * 4;
+      const unsigned row = p / W;
+      const int wq = static_cast<int>(p - row * W);
+      const int hq = static_cast<int>(row % H);
+      const float* xi = x + (p - wq - static_cast<unsigned>(hq) * W);  // image base
+      float xv[3][6];
+      c1_load_window(xi, hq, wq, H, W, xv);
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float a = br[k];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) a = fmaf(xv[t / 3][px + t % 3], wr[t][k], a);
+          if (relu) a = fmaxf(a, 0.f);
+          a = bf16_round(a);
+          acc[k] = a;
+          st[k] += a;
+          st[8 + k] = fmaf(a, a, st[8 + k]);
+        }
+        stg16(r + static_cast<size_t>(p + px) * Cout + cg * 8, pack8(acc));
+      }
+    }
+  }
+  if (stats_partial) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) red[threadIdx.x * 16 + k] = st[k];
+    __syncthreads();
+    float* row = stats_partial + static_cast<size_t>(blockIdx.x) * 2 * Cout;
+    for (int o = threadIdx.x; o < 2 * Cout; o += kThreads) {
+      const int which = o / Cout, ch = o - which * Cout;
+      const int g = ch / 8, k = ch % 8;
+      float acc = 0.f;
+      for (int t = 0; t < qpi; ++t) acc += red[(t * groups + g) * 16 + which * 8 + k];
+      row[o] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+conv3x3_c1_wgrad4_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                         float* __restrict__ partial, int N, int H, int W, int Cout) {
+  __shared__ float red[kThreads * 8];
+  const int groups = Cout / 8;
+  const int qpi = kThreads / groups;
+  const int cg = threadIdx.x % groups;
+  const int ql = threadIdx.x / groups;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  const unsigned nquads = static_cast<unsigned>(N) * H * W / 4;
+  for (unsigned q0 = blockIdx.x * qpi; q0 < nquads; q0 += gridDim.x * qpi) {
+    const unsigned qd = q0 + ql;
+    if (qd < nquads) {
+      const unsigned p = qd * 4;
+      const unsigned row = p / W;
+      const int wq = static_cast<int>(p - row * W);
+      const int hq = static_cast<int>(row % H);
+      const float* xi = x + (p - wq - static_cast<unsigned>(hq) * W);
+      uint4 graw[4];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) graw[px] = ldg16(dz + static_cast<size_t>(p + px) * Cout + cg * 8);
+      float xv[3][6];
+      c1_load_window(xi, hq, wq, H, W, xv);
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        float g[8];
+        unpack8(graw[px], g);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float v = xv[t / 3][px + t % 3];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(v, g[k], acc[t][k]);
+        }
+      }
+    }
+  }
+  float* row = partial + static_cast<size_t>(blockIdx.x) * Cout * 9;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[t][k];
+    __syncthreads();
+    for (int o = threadIdx.x; o < Cout; o += kThreads) {
+      const int g = o / 8, k = o % 8;
+      float s = 0.f;
+      for (int tt = 0; tt < qpi; ++tt) s += red[(tt * groups + g) * 8 + k];
+      row[o * 9 + t] = s;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // BatchNorm statistics
 // ------------------------------------------------------------------------------------------------
@@ -325,62 +467,77 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
 
-  constexpr int Q = POOL ? 4 : 1;
+  constexpr int Q = POOL ? 4 : 1;      // pixels per work item (one 2x2 pooling window, or one pixel)
+  constexpr int U = 1;                 // work items per loop trip (more loads in flight per thread measured no gain)
   const int Ho = POOL ? H / 2 : H, Wo = POOL ? W / 2 : W;
   const long long total = static_cast<long long>(N) * Ho * Wo * groups;
-  for (long long i = tid; i < total; i += stride) {
-    const unsigned pp = static_cast<unsigned>(i >> gshift);
-    long long p00 = pp;
-    if (POOL) {
-      const unsigned prow = pp / Wo;
-      const int wo = static_cast<int>(pp - prow * Wo);
-      const unsigned n = prow / Ho;
-      const int ho = static_cast<int>(prow - n * Ho);
-      p00 = (static_cast<long long>(n) * H + 2 * ho) * W + 2 * wo;
-    }
-    float rv[Q][8], g[Q][8];
+  for (long long i0 = tid; i0 < total; i0 += stride * U) {
+    uint4 rraw[U][Q], graw[U][Q], praw[U];
+    long long p00[U];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const long long pix = POOL ? p00 + (q >> 1) * W + (q & 1) : p00;
-      unpack8(ldg16(r + pix * r_cs + cg * 8), rv[q]);
-      unpack8(ldg16(dy + pix * dy_cs + cg * 8), g[q]);
-    }
-    if (POOL) {
-      float dp[8];
-      unpack8(ldg16(dpool + static_cast<size_t>(pp) * C + cg * 8), dp);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      const bool on = i < total;
+      const unsigned pp = static_cast<unsigned>((on ? i : i0) >> gshift);
+      p00[u] = pp;
+      if (POOL) {
+        const unsigned prow = pp / Wo;
+        const int wo = static_cast<int>(pp - prow * Wo);
+        const unsigned n = prow / Ho;
+        const int ho = static_cast<int>(prow - n * Ho);
+        p00[u] = (static_cast<long long>(n) * H + 2 * ho) * W + 2 * wo;
+        praw[u] = ldg16(dpool + static_cast<size_t>(pp) * C + cg * 8);
+      }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float best = bf16_round(fmaf(rv[0][k], sc[k], sh[k]));
-        int arg = 0;
-#pragma unroll
-        for (int q = 1; q < Q; ++q) {
-          const float yv = bf16_round(fmaf(rv[q][k], sc[k], sh[k]));
-          if (yv > best) { best = yv; arg = q; }
-        }
-#pragma unroll
-        for (int q = 0; q < Q; ++q) g[q][k] += (arg == q) ? dp[k] : 0.f;
+      for (int q = 0; q < Q; ++q) {
+        const long long pix = POOL ? p00[u] + (q >> 1) * W + (q & 1) : p00[u];
+        rraw[u][q] = ldg16(r + pix * r_cs + cg * 8);
+        graw[u][q] = ldg16(dy + pix * dy_cs + cg * 8);
       }
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      float out[8];
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= total) break;
+      float rv[Q][8], g[Q][8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float xh = (rv[q][k] - mu[k]) * is[k];
-        if (!APPLY) {
-          acc[k] += g[q][k];
-          acc[8 + k] = fmaf(g[q][k], xh, acc[8 + k]);
-        } else {
-          float d = c0[k] * (g[q][k] - c1[k] - xh * c2[k]);
-          d = rv[q][k] > 0.f ? d : 0.f;
-          d = bf16_round(d);
-          out[k] = d;
-          acc[k] += d;
+      for (int q = 0; q < Q; ++q) { unpack8(rraw[u][q], rv[q]); unpack8(graw[u][q], g[q]); }
+      if (POOL) {
+        float dp[8];
+        unpack8(praw[u], dp);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float best = bf16_round(fmaf(rv[0][k], sc[k], sh[k]));
+          int arg = 0;
+#pragma unroll
+          for (int q = 1; q < Q; ++q) {
+            const float yv = bf16_round(fmaf(rv[q][k], sc[k], sh[k]));
+            if (yv > best) { best = yv; arg = q; }
+          }
+#pragma unroll
+          for (int q = 0; q < Q; ++q) g[q][k] += (arg == q) ? dp[k] : 0.f;
         }
       }
-      if (APPLY) {
-        const long long pix = POOL ? p00 + (q >> 1) * W + (q & 1) : p00;
-        stg16(dz + pix * dz_cs + cg * 8, pack8(out));
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        float out[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (rv[q][k] - mu[k]) * is[k];
+          if (!APPLY) {
+            acc[k] += g[q][k];
+            acc[8 + k] = fmaf(g[q][k], xh, acc[8 + k]);
+          } else {
+            float d = c0[k] * (g[q][k] - c1[k] - xh * c2[k]);
+            d = rv[q][k] > 0.f ? d : 0.f;
+            d = bf16_round(d);
+            out[k] = d;
+            acc[k] += d;
+          }
+        }
+        if (APPLY) {
+          const long long pix = POOL ? p00[u] + (q >> 1) * W + (q & 1) : p00[u];
+          stg16(dz + pix * dz_cs + cg * 8, pack8(out));
+        }
       }
     }
   }
@@ -401,6 +558,9 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
     for (int t = 0; t < per_group; ++t) s += red[(t * groups + gi) * NV + which * 8 + k];
     row[o] = s;
   }
+  // the partial buffer always has kEwBlocks rows; rows beyond the (occupancy-sized) grid are zero-filled
+  for (int rr = blockIdx.x + gridDim.x; rr < kEwBlocks; rr += gridDim.x)
+    for (int o = threadIdx.x; o < nout; o += kThreads) partial[static_cast<size_t>(rr) * nout + o] = 0.f;
 }
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
@@ -821,6 +981,15 @@ static int grid_for(long long work_items, int per_block) {
   return static_cast<int>(blocks);
 }
 static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+// One full wave: SM count x resident blocks of this kernel (at most kEwBlocks = 4 per SM), so that a grid-stride
+// kernel whose every block does the same amount of work has no partial last wave.
+template <typename K>
+static int one_wave_grid(K kernel) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+  if (occ > kEwBlocks / kSMs) occ = kEwBlocks / kSMs;
+  return kSMs * occ;
+}
 // channel counts the vectorised element-wise kernels accept: C/8 must divide 256
 static bool ew_channels_ok(int C) { return C >= 8 && C % 8 == 0 && pow2(C / 8) && C / 8 <= kThreads; }
 
@@ -855,9 +1024,9 @@ extern "C" int b2s_conv3x3_c1_fwd(const float* x, const float* w, const float* b
   if (static_cast<long long>(N) * H * W >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: N*H*W >= 2^31");
   const int grid = b2s_c1_rows(N, H, W);
   count_launch();
-  conv3x3_c1_fwd_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(
-      x, w, bias, static_cast<__nv_bfloat16*>(r), (flags & B2S_FLAG_STATS) ? stats_partial : nullptr, N, H, W, Cout,
-      flags);
+  auto kfn = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? conv3x3_c1_fwd4_kernel : conv3x3_c1_fwd_kernel;
+  kfn<<<grid, kThreads, 0, STREAM(stream)>>>(x, w, bias, static_cast<__nv_bfloat16*>(r),
+                                             (flags & B2S_FLAG_STATS) ? stats_partial : nullptr, N, H, W, Cout, flags);
   return check_launch("conv3x3_c1_fwd_kernel");
 }
 
@@ -867,8 +1036,8 @@ extern "C" int b2s_conv3x3_c1_wgrad(const float* x, const void* dz, float* parti
   if (!ew_channels_ok(Cout) || Cout > 128) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_wgrad: unsupported Cout");
   const int grid = b2s_c1_rows(N, H, W);
   count_launch();
-  conv3x3_c1_wgrad_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(x, static_cast<const __nv_bfloat16*>(dz), partial, N,
-                                                                H, W, Cout);
+  auto kfn = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? conv3x3_c1_wgrad4_kernel : conv3x3_c1_wgrad_kernel;
+  kfn<<<grid, kThreads, 0, STREAM(stream)>>>(x, static_cast<const __nv_bfloat16*>(dz), partial, N, H, W, Cout);
   return check_launch("conv3x3_c1_wgrad_kernel");
 }
 
@@ -932,13 +1101,15 @@ extern "C" int b2s_bn_bwd_reduce(const void* dy, int dy_cstride, const void* dpo
   const auto* dyp = static_cast<const __nv_bfloat16*>(dy);
   const auto* rp = static_cast<const __nv_bfloat16*>(r);
   count_launch();
-  // every block must write its partial row: launch exactly kEwBlocks blocks
+  // one full wave of blocks; the kernel zero-fills the partial rows beyond its grid
+  static const int grid_pool = one_wave_grid(bn_bwd_kernel<true, false>);
+  static const int grid_flat = one_wave_grid(bn_bwd_kernel<false, false>);
   if (dpool)
-    bn_bwd_kernel<true, false><<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
+    bn_bwd_kernel<true, false><<<grid_pool, kThreads, 0, STREAM(stream)>>>(
         dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, nullptr,
         nullptr, 0, partial, N, H, W, C);
   else
-    bn_bwd_kernel<false, false><<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
+    bn_bwd_kernel<false, false><<<grid_flat, kThreads, 0, STREAM(stream)>>>(
         dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, nullptr, nullptr, 0, partial, N, H, W, C);
   return check_launch("bn_bwd_kernel<reduce>");
 }
@@ -969,12 +1140,14 @@ extern "C" int b2s_bn_bwd_apply(const void* dy, int dy_cstride, const void* dpoo
   const auto* rp = static_cast<const __nv_bfloat16*>(r);
   auto* dzp = static_cast<__nv_bfloat16*>(dz);
   count_launch();
+  static const int grid_pool = one_wave_grid(bn_bwd_kernel<true, true>);
+  static const int grid_flat = one_wave_grid(bn_bwd_kernel<false, true>);
   if (dpool)
-    bn_bwd_kernel<true, true><<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
+    bn_bwd_kernel<true, true><<<grid_pool, kThreads, 0, STREAM(stream)>>>(
         dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, coef, dzp,
         dz_cstride, dbias_partial, N, H, W, C);
   else
-    bn_bwd_kernel<false, true><<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
+    bn_bwd_kernel<false, true><<<grid_flat, kThreads, 0, STREAM(stream)>>>(
         dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, coef, dzp, dz_cstride, dbias_partial, N, H,
         W, C);
   return check_launch("bn_bwd_kernel<apply>");
