@@ -234,6 +234,12 @@ def test_conv3x3_dgrad(ops, N, H, W, Cin, Cout):
     (2, 16, 16, 128, 128, 0, 0),
     (2, 8, 8, 256, 256, 256, 0),
     (1, 24, 40, 64, 128, 0, 2),     # partial pixel chunks
+    (1, 4, 128, 64, 64, 0, 0),      # row-halo kernel (W % 128 == 0): tap pairs, one CTA group
+    (2, 6, 256, 64, 64, 0, 5),      # two strips per row, uneven split of the row tiles
+    (1, 4, 128, 128, 64, 0, 0),     # Cin 128: one tap per tile, two CTA groups (5 + 4 taps)
+    (1, 4, 128, 64, 128, 0, 3),     # Cout 128: two CTA groups (3 + 2 tiles)
+    (2, 6, 128, 128, 128, 0, 0),    # three CTA groups, one tap row each
+    (1, 4, 128, 64, 64, 1 << 12, 0),  # same shape through the legacy kernel
 ])
 def test_conv3x3_wgrad(ops, N, H, W, Cin, Cout, tile_n, splits):
     x = bf(rnd((N, Cin, H, W), 41))

@@ -181,6 +181,12 @@ static inline int conv_plan(int N, int H, int W, int n_total, int cout_sub, int 
   return 0;
 }
 
+// wgrad2_tc.cu: row-halo weight-gradient kernel (W % 128 == 0, Cin and Cout in {64, 128})
+bool wgrad_halo_eligible(int N, int H, int W, int Cin, int Cout);
+int wgrad_halo_splits(int N, int H, int W, int Cin, int Cout, int splits_req);
+int launch_wgrad_halo(const void* x, int x_cstride, const void* dz, int dz_cstride, float* ws, int N, int H, int W,
+                      int Cin, int Cout, int splits_req, cudaStream_t stream);
+
 // conv2_tc.cu: tile-pair and halo kernels
 int launch_conv2(const ConvPlan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                  const ConvTcParams& p, cudaStream_t stream);

@@ -630,6 +630,12 @@ extern "C" long long b2s_conv_wgrad_workspace(int N, int H, int W, int Cin, int 
   WgradParams p{};
   int block_n;
   const int taps = ksize_or_taps == 3 ? 9 : ksize_or_taps;
+  if (taps == 9 && !(tile_n & kVarLegacy) && wgrad_halo_eligible(N, H, W, Cin, Cout)) {
+    const int s = wgrad_halo_splits(N, H, W, Cin, Cout, splits);
+    if (splits_out) *splits_out = s;
+    return static_cast<long long>(s) * taps * Cin * Cout * 4;
+  }
+  tile_n &= kTileNMask;
   if (Cin % 64 || Cout % 64 || wgrad_plan(N, H, W, Cin, Cout, taps, tile_n, splits, &p, &block_n)) {
     set_error(B2S_ERR_ARG, "b2s_conv_wgrad_workspace: unsupported shape");
     return -1;
@@ -644,6 +650,9 @@ extern "C" int b2s_conv3x3_wgrad(const void* x, int x_cstride, const void* dz, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !dz || !ws) return set_error(B2S_ERR_ARG, "b2s_conv3x3_wgrad: null pointer");
   if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_conv3x3_wgrad: channels must be multiples of 64");
+  if (!(tile_n & kVarLegacy) && wgrad_halo_eligible(N, H, W, Cin, Cout))
+    return launch_wgrad_halo(x, x_cstride, dz, dz_cstride, ws, N, H, W, Cin, Cout, splits, stream);
+  tile_n &= kTileNMask;
   WgradParams p{};
   int block_n;
   if (wgrad_plan(N, H, W, Cin, Cout, 9, tile_n, splits, &p, &block_n))
