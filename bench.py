@@ -96,8 +96,18 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(B, S, world):
+    """config block shared by both arms (the reference arm adds what it sampled)"""
+    return {"workload": f"UNet bf16 training, batch {B} at {S}x{S} per GPU (BASELINE configs[1]; "
+                        f"global batch {B * world})", "batch_per_gpu": B, "global_batch": B * world,
+            "image": f"1x{S}x{S}", "loss": "BCE+Dice (fused)", "optimizer": "AdamW lr 1e-5 (fused, flat buckets)",
+            "parallelism": f"dp{world}", "precision": "bf16 storage / fp32 accumulate, fp32 master weights",
+            "l2": "working set (>= 6 GB of activations per step) is far larger than the 126 MB L2"}
+
+
 def cpu_reference_step_time(batch, size, steps, warmup, threads):
-    """Times the reference's CPU path (oracle/unet_torch_ref.py: the same torch CPU ops as the reference modules)."""
+    """Times the reference's CPU path (oracle/unet_torch_ref.py: the same torch CPU ops the reference's nn.Modules
+    dispatch to) for one optimisation step: forward + BCE + Dice + backward + AdamW (utils/trainer.py:81-93)."""
     import torch
     from oracle import unet_oracle as O, unet_torch_ref as T
     import b200seg  # noqa: F401
@@ -105,32 +115,48 @@ def cpu_reference_step_time(batch, size, steps, warmup, threads):
     torch.set_num_threads(threads)
     torch.manual_seed(42)
     P = T.make_params(UNet().state_dict())
+    params = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-5)
     x, t = O.synth_batch(batch, size, size, seed=1234)
+
+    def step():
+        _, _, grads = T.train_step(P, x, t)
+        for prm, g in zip(params, grads):
+            prm.grad = g
+        opt.step()
+
     for _ in range(warmup):
-        T.train_step(P, x, t)
+        step()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        T.train_step(P, x, t)
+        step()
         times.append(time.perf_counter() - t0)
     return times
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (it ships no GPU kernels and no build
+    system; its hot path is torch CPU/cuDNN ops). Runs on rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    batch = 4
-    times = cpu_reference_step_time(batch, args.size, args.steps, max(args.warmup, 1), threads)
+    batch = 4   # bounded sample of the batch-64 workload: 4 images per step (= BASELINE configs[0]'s batch)
+    steps = min(args.steps, 8)
+    warm = 1
+    times = cpu_reference_step_time(batch, args.size, steps, warm, threads)
     ms = 1e3 * sum(times) / len(times)
     value = batch / (ms / 1e3)
-    sample = f"fp32 fwd+BCE/Dice+bwd of the reference UNet graph, batch {batch} at {args.size}x{args.size} per step (BASELINE configs[0]), no optimiser step"
+    sample = (f"each step = fp32 forward + BCE/Dice + backward + AdamW of the reference UNet graph on {batch} of the "
+              f"{args.batch} images of a batch ({args.size}x{args.size}), torch CPU ops on {threads} threads; "
+              f"{steps} timed steps after {warm} warm-up")
+    cfg = workload_config(args.batch, args.size, 1)
+    cfg["sample"] = sample
+    cfg["precision"] = "fp32 (the reference's CPU path)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "UNet training step at 1x256x256 on host CPU cores (torch CPU ops = the reference's own path)",
-                       "batch": batch, "image": f"1x{args.size}x{args.size}", "loss": "BCE+Dice"},
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -237,11 +263,35 @@ def run_b200(args):
     tc_ms, tc_flops = sum(r[3] for r in tc), sum(r[2] for r in tc)
     hb_ms, hb_bytes = sum(r[3] for r in hb), sum(r[2] for r in hb)
     achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel + wgrad_tc_kernel (all tcgen05 launches of one step)",
-                "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sustained"], "peak_source": f"{peaks['source']} bf16_tflops_sustained",
-                "traffic": None, "launches": len(tc), "ms_per_step_in_kernel": tc_ms,
-                "share_of_step": tc_ms / (tc_ms + hb_ms) if tc_ms + hb_ms > 0 else None,
+    # dominant kernel: conv2_tc_kernel = every 3x3 conv forward and input-gradient launch (ops.conv_fwd)
+    dom = [r for r in tc if r[0].startswith("conv3x3[")]
+    dom_ms, dom_flops = sum(r[3] for r in dom), sum(r[2] for r in dom)
+    dom_tf = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    traffic, traffic_note = None, "no ncu capture found under profiles/"
+    try:   # DRAM bytes of one launch from the committed `ncu --set full` capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_conv_full.json")) as f:
+            for d in json.load(f):
+                if d["kernel"].startswith("void conv2_tc_kernel<256, 2, 0, 3, 0>"):
+                    def to_bytes(v):
+                        x, u = v.split()
+                        return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+                    traffic = to_bytes(d["dram_read"]) + to_bytes(d["dram_write"])
+                    traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one conv2_tc_kernel<256,2,0,3,0> launch "
+                                    "(512->512 @32x32, batch 64; algorithmic 2 x 67.1 MB activations + 4.7 MB weights), "
+                                    "profiles/r1_ncu_conv_full.json")
+                    break
+    except (OSError, KeyError, ValueError):
+        pass
+    roofline = {"bound": "tensor",
+                "kernel": "conv2_tc_kernel: all 3x3 conv forward + input-gradient launches of one step (tcgen05 implicit GEMM)",
+                "achieved": dom_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": dom_tf / peaks["tf_sustained"], "peak_source": f"{peaks['source']} bf16_tflops_sustained",
+                "traffic": traffic, "traffic_note": traffic_note, "launches": len(dom), "ms_per_step_in_kernel": dom_ms,
+                "share_of_step": dom_ms / (tc_ms + hb_ms) if tc_ms + hb_ms > 0 else None,
+                "all_tcgen05": {"kernels": "conv2_tc_kernel + wgrad_halo_kernel + wgrad_tc_kernel (conv, transposed conv, "
+                                           "weight gradients)", "achieved": achieved_tf,
+                                "frac": achieved_tf / peaks["tf_sustained"], "launches": len(tc), "ms_per_step": tc_ms,
+                                "share_of_step": tc_ms / (tc_ms + hb_ms) if tc_ms + hb_ms > 0 else None},
                 "step_frac_of_peak": (B * FLOP_PER_IMG_TRAIN_256 * (S / 256) ** 2) / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"],
                 "hbm_kernels": {"achieved_gbs": hb_bytes / (hb_ms * 1e-3) / 1e9 if hb_ms > 0 else 0.0,
                                 "peak_gbs": peaks["hbm_gbs"], "ms_per_step": hb_ms, "launches": len(hb)}}
@@ -261,11 +311,12 @@ def run_b200(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        times = cpu_reference_step_time(4, S, 2, 1, threads)
+        times = cpu_reference_step_time(4, S, 3, 1, threads)
         v = 4 / (sum(times) / len(times))
         cpu_baseline = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-                        "sample": f"2 timed steps (1 warm-up) of fp32 fwd+BCE/Dice+bwd, batch 4 at {S}x{S} "
-                                  "(BASELINE configs[0]) with the reference's own torch CPU ops (oracle/unet_torch_ref.py)"}
+                        "sample": f"3 timed steps (1 warm-up) of fp32 forward + BCE/Dice + backward + AdamW on 4 images "
+                                  f"at {S}x{S} (BASELINE configs[0]) with the reference's own torch CPU ops "
+                                  "(oracle/unet_torch_ref.py)"}
 
     if world > 1:
         dist.barrier()
@@ -274,11 +325,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"UNet bf16 training, batch {B} at {S}x{S} per GPU (BASELINE configs[1]; "
-                                       f"global batch {B * world})", "batch_per_gpu": B, "global_batch": B * world,
-                           "image": f"1x{S}x{S}", "loss": "BCE+Dice (fused)", "optimizer": "AdamW lr 1e-5 (fused, flat buckets)",
-                           "parallelism": f"dp{world}", "precision": "bf16 storage / fp32 accumulate, fp32 master weights",
-                           "l2": "working set (>= 6 GB of activations per step) is far larger than the 126 MB L2"},
+                "config": workload_config(B, S, world),
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/s",
                                           "h2d_bytes_per_step": x_pin.numel() * 4 + t_pin.numel() * 4,
                                           "d2h_bytes_per_step": 32},

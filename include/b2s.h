@@ -38,7 +38,9 @@ int b2s_version(void);
  *   x [N,H,W,Cin] bf16, w_packed [ksize*ksize][Cout][Cin] bf16, bias [Cout] fp32 or NULL,
  *   y [N,H,W,Cout] bf16, stats_partial [b2s_conv_stats_rows(N,H,W,Cout,tile_n)][2][Cout] fp32 when B2S_FLAG_STATS
  *   (two rows per CTA row-group of the persistent grid; at most 2 * SM count rows).
- *   tile_n: 0 = auto, else 64/128/256 (must divide Cout). Cin, Cout multiples of 64. */
+ *   tile_n: 0 = auto, else 64/128/256 (must divide Cout); the bits above bit 9 force a kernel variant (tests):
+ *   +1024 tile-pair kernel, +2048 row-halo kernel (W % 128 == 0, even H, ksize 3), +4096 single-tile kernel.
+ *   Cin, Cout multiples of 64. */
 int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y, int y_cstride,
                  float* stats_partial, int N, int H, int W, int Cin, int Cout, int ksize, int flags, int tile_n,
                  void* stream);
