@@ -144,6 +144,56 @@ int b2s_adamw_step(float* p, const float* g, float* m, float* v, long long n, fl
 int b2s_copy_channels(const void* src, int src_cstride, void* dst, int dst_cstride, long long npix, int C,
                       void* stream);
 
+/* ---- V-Net variant (models/vnet.py) ------------------------------------------------------------------------- */
+
+/* nn.Conv2d(C,2C,3,stride=2,padding=1) forward (models/vnet.py:97): x [N,H,W,Cin] -> y [N,H/2,W/2,Cout] (+bias);
+ * the A tiles are TMA boxes with elementStrides = 2. Its input and weight gradients are b2s_conv_fwd (rotated
+ * weights) and b2s_conv3x3_wgrad applied to the zero-inserted output gradient from b2s_upsample_zero2x. */
+int b2s_conv3x3_s2_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y, int y_cstride,
+                       int N, int H, int W, int Cin, int Cout, int tile_n, void* stream);
+/* dst [N,2Hs,2Ws,C]: dst[n,2i,2j,:] = src[n,i,j,:], zero elsewhere. */
+int b2s_upsample_zero2x(const void* src, int src_cstride, void* dst, int dst_cstride, int N, int Hs, int Ws, int C,
+                        void* stream);
+/* nn.Conv2d(Cin,Cout,1) weight gradient (residual projections, models/vnet.py:46,58): ws[split][ci][co]; workspace
+ * from b2s_conv_wgrad_workspace(..., ksize_or_taps = 1, ...), reduced by b2s_wgrad_reduce(taps = 1, layout 0). */
+int b2s_conv1x1_wgrad(const void* x, int x_cstride, const void* dz, int dz_cstride, float* ws, int N, int H, int W,
+                      int Cin, int Cout, int tile_n, int splits, void* stream);
+
+/* BatchNorm -> ReLU -> Dropout (+ residual) of ConvBlock (models/vnet.py:51-59):
+ * out = dropout_p(relu(z*scale + shift)) + res; scale/shift/res may be NULL, relu is a flag. The dropout mask is a
+ * counter-based hash of (seed, NHWC element index): P(keep) = 1-p, kept values scaled by 1/(1-p); p = 0 disables it. */
+int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale, const float* shift, const void* res,
+                     int res_cstride, void* out, int out_cstride, long long npix, int C, int relu, float dropout_p,
+                     unsigned seed, void* stream);
+/* its backward in two passes (same finalize as the UNet path, b2s_bn_bwd_finalize): pass 1 partial [b2s_ew_rows][2][C]
+ * = sum dy, sum dy*xhat with dy = da * mask/(1-p) * (z*scale+shift > 0); pass 2 dz = c0 (dy - c1 - xhat c2) and the
+ * conv-bias gradient partials [b2s_ew_rows][C]. */
+int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void* z, int z_cstride, const float* scale,
+                          const float* shift, const float* mean, const float* invstd, float* partial, long long npix,
+                          int C, int relu, float dropout_p, unsigned seed, void* stream);
+int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* z, int z_cstride, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, const float* coef, void* dz,
+                         int dz_cstride, float* dbias_partial, long long npix, int C, int relu, float dropout_p,
+                         unsigned seed, void* stream);
+/* partial [b2s_ew_rows][C] = per-channel sums over pixels (bias gradient of a conv that is not followed by BN). */
+int b2s_channel_sums(const void* x, int x_cstride, float* partial, long long npix, int C, void* stream);
+
+/* SEBlock (models/vnet.py:5-26). b2s_se_pool: partial [N][b2s_se_chunks(HW)][C] = sums over pixels of x (y NULL) or
+ * of x*y; b2s_se_fc_fwd: mean = pooled/HW, hidden = relu(W1 mean + b1), gate = sigmoid(W2 hidden + b2), all fp32
+ * [N][C] / [N][C/r]; b2s_se_scale: y = x*gate[n][c] (+ add[n][c]*add_scale when add != NULL: the backward's
+ * dx = dy*gate + dmean/HW); b2s_se_fc_bwd: from partial = sum_hw dy*x: ds, dh, dmean per sample and the batch-summed
+ * dW1 [C/r][C], db1, dW2 [C][C/r], db2. */
+int b2s_se_chunks(long long HW);
+int b2s_se_pool(const void* x, int x_cstride, const void* y, int y_cstride, float* partial, int N, long long HW, int C,
+                void* stream);
+int b2s_se_fc_fwd(const float* partial, int chunks, long long HW, const float* w1, const float* b1, const float* w2,
+                  const float* b2, float* mean, float* hidden, float* gate, int N, int C, int Cr, void* stream);
+int b2s_se_scale(const void* x, int x_cstride, const float* gate, const float* add, float add_scale, void* y,
+                 int y_cstride, int N, long long HW, int C, void* stream);
+int b2s_se_fc_bwd(const float* partial, int chunks, const float* gate, const float* hidden, const float* mean,
+                  const float* w1, const float* w2, float* ds, float* dh, float* dmean, float* dw1, float* db1,
+                  float* dw2, float* db2, int N, int C, int Cr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

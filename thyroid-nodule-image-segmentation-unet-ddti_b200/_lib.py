@@ -49,6 +49,18 @@ SIGNATURES = {
     "b2s_seg_loss_bwd": (I, [P, P, P, P, I, LL, LL, I, P, P, F, F, F, F, F, F, F, F, P]),
     "b2s_adamw_step": (I, [P, P, P, P, LL, F, F, F, F, F, I, F, P]),
     "b2s_copy_channels": (I, [P, I, P, I, LL, I, P]),
+    "b2s_conv3x3_s2_fwd": (I, [P, I, P, P, P, I, I, I, I, I, I, I, P]),
+    "b2s_upsample_zero2x": (I, [P, I, P, I, I, I, I, I, P]),
+    "b2s_conv1x1_wgrad": (I, [P, I, P, I, P, I, I, I, I, I, I, I, P]),
+    "b2s_bn_act_apply": (I, [P, I, P, P, P, I, P, I, LL, I, I, F, ctypes.c_uint, P]),
+    "b2s_bn_act_bwd_reduce": (I, [P, I, P, I, P, P, P, P, P, LL, I, I, F, ctypes.c_uint, P]),
+    "b2s_bn_act_bwd_apply": (I, [P, I, P, I, P, P, P, P, P, P, I, P, LL, I, I, F, ctypes.c_uint, P]),
+    "b2s_channel_sums": (I, [P, I, P, LL, I, P]),
+    "b2s_se_chunks": (I, [LL]),
+    "b2s_se_pool": (I, [P, I, P, I, P, I, LL, I, P]),
+    "b2s_se_fc_fwd": (I, [P, I, LL, P, P, P, P, P, P, P, I, I, I, P]),
+    "b2s_se_scale": (I, [P, I, P, P, F, P, I, I, LL, I, P]),
+    "b2s_se_fc_bwd": (I, [P, I, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
 }
 
 

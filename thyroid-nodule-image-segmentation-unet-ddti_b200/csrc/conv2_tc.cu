@@ -162,6 +162,9 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (p.a_mode == A_CONV3) {
                 const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;
                 tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0[mt] + dw, h0[mt] + dh, n0[mt]);
+              } else if (p.a_mode == A_CONV3_S2) {   // stride 2: the map steps two input pixels per box element
+                const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;
+                tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, 2 * w0[mt] + dw, 2 * h0[mt] + dh, n0[mt]);
               } else if (p.a_mode == A_1X1) {
                 tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0[mt], h0[mt], n0[mt]);
               } else {  // A_CONVT_DGRAD: dY viewed as (C, b, j, a, i*N)

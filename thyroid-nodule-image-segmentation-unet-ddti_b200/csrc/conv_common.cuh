@@ -10,7 +10,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 
-enum AMode : int { A_CONV3 = 0, A_1X1 = 1, A_CONVT_DGRAD = 2 };
+enum AMode : int { A_CONV3 = 0, A_1X1 = 1, A_CONVT_DGRAD = 2, A_CONV3_S2 = 3 };
 enum OutMode : int { OUT_4D = 0, OUT_CONVT_5D = 1 };
 
 struct ConvTcParams {
@@ -50,12 +50,12 @@ static inline EncodeTiledFn get_encode_fn() {
 // bf16 tensor map, SWIZZLE_128B, inner box = 64 elements. dims/strides innermost first; strides in BYTES for
 // dims 1..rank-1.
 static inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                     const uint32_t* box) {
+                     const uint32_t* box, const uint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(B2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_b[i];
   if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(B2S_ERR_ARG, "tensor base not 16-B aligned");
   for (int i = 0; i + 1 < rank; ++i)
@@ -92,6 +92,16 @@ static inline int make_act_map4(CUtensorMap* m, const void* base, int C, int W, 
   uint64_t str[3] = {(uint64_t)cstride * 2, (uint64_t)W * cstride * 2, (uint64_t)H * W * cstride * 2};
   uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
   return make_tmap(m, base, 4, dims, str, box);
+}
+// Same, traversing every second pixel in W and H (stride-2 convolution input): a box of (bw, bh) OUTPUT pixels is
+// encoded as boxDim = 2 * (bw, bh) with elementStrides = 2 (TMA loads ceil(boxDim / elementStride) elements).
+static inline int make_act_map4_s2(CUtensorMap* m, const void* base, int C, int W, int H, int N, int cstride, int bw,
+                                   int bh, int bn) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)cstride * 2, (uint64_t)W * cstride * 2, (uint64_t)H * W * cstride * 2};
+  uint32_t box[4] = {64, (uint32_t)(2 * bw), (uint32_t)(2 * bh), (uint32_t)bn};
+  uint32_t es[4] = {1, 2, 2, 1};
+  return make_tmap(m, base, 4, dims, str, box, es);
 }
 // 2x-upsampled NHWC tensor [N, 2Hi, 2Wi, C] viewed as (C, b, j, a, i*N) so that one (a,b) sub-lattice is a box.
 static inline int make_up_map5(CUtensorMap* m, const void* base, int C, int Wi, int Hi, int N, int cstride, int bw,

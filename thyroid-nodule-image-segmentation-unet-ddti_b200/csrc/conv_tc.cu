@@ -275,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // wgrad: D[(tap,ci), co] = sum_pix A[pix, (tap,ci)] * B[pix, co], both operands MN-major in smem
 // ------------------------------------------------------------------------------------------------
-enum WgMode : int { WG_CONV3 = 0, WG_CONVT = 1 };
+enum WgMode : int { WG_CONV3 = 0, WG_CONVT = 1, WG_1X1 = 2 };
 
 struct WgradParams {
   int pw, ph, pn;                 // pixel box of one K chunk, pw*ph*pn == 64
@@ -375,7 +375,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (p.mode == WG_CONV3) { dh = tap_j[j] / 3 - 1; dw = tap_j[j] % 3 - 1; }
           tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 8192, cib_j[j] * 64, w0 + dw, h0 + dh, n0);
         }
-        if (p.mode == WG_CONV3) {
+        if (p.mode != WG_CONVT) {
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_4d(&tmB, &full_bar[stage], b_dst + j * 8192, n_tile * BLOCK_N + j * 64, w0, h0, n0);
@@ -517,6 +517,31 @@ extern "C" int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, 
   }
   if ((rc = make_weight_map(&tmB, w_packed, Cin, p.num_taps * Cout, pl.block_n))) return rc;
   if ((rc = make_act_map4(&tmOut, y, Cout, W, H, N, y_cstride, pl.bw, pl.bh, pl.bn))) return rc;
+  return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
+}
+
+// nn.Conv2d(Cin,Cout,3,stride=2,padding=1) forward (models/vnet.py:97): x [N,H,W,Cin] -> y [N,H/2,W/2,Cout].
+extern "C" int b2s_conv3x3_s2_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y,
+                                  int y_cstride, int N, int H, int W, int Cin, int Cout, int tile_n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !w_packed || !y) return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_fwd: null pointer");
+  if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_fwd: channels must be multiples of 64");
+  if (N <= 0 || H < 2 || W < 2 || H % 2 || W % 2) return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_fwd: H and W must be even");
+  const int Ho = H / 2, Wo = W / 2;
+  ConvTcParams p{};
+  p.a_mode = A_CONV3_S2; p.out_mode = OUT_4D;
+  ConvPlan pl;
+  if (conv_plan(N, Ho, Wo, Cout, Cout, p.a_mode, p.out_mode, (tile_n & kTileNMask) | kVarPair, &pl))
+    return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_fwd: tile_n must be 64/128/256 and divide Cout");
+  p.W = Wo; p.H = Ho; p.N = N;
+  p.num_taps = 9; p.k_chunks = Cin / 64;
+  p.n_total = Cout; p.cout_sub = Cout;
+  p.flags = 0; p.bias = bias; p.stats = nullptr;
+  CUtensorMap tmA, tmB, tmOut;
+  int rc;
+  if ((rc = make_act_map4_s2(&tmA, x, Cin, W, H, N, x_cstride, pl.bw, pl.bh, pl.bn))) return rc;
+  if ((rc = make_weight_map(&tmB, w_packed, Cin, 9 * Cout, pl.block_n))) return rc;
+  if ((rc = make_act_map4(&tmOut, y, Cout, Wo, Ho, N, y_cstride, pl.bw, pl.bh, pl.bn))) return rc;
   return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
 }
 
@@ -670,6 +695,32 @@ extern "C" int b2s_conv3x3_wgrad(const void* x, int x_cstride, const void* dz, i
     case 256: return launch_wgrad<256, 4>(tmA, tmB, p, grid, stream);   // 4 x 48 KB
   }
   return set_error(B2S_ERR_ARG, "b2s_conv3x3_wgrad: unsupported tile_n");
+}
+
+// 1x1 conv weight gradient partials (residual projections of models/vnet.py:46): ws[split][ci][co].
+extern "C" int b2s_conv1x1_wgrad(const void* x, int x_cstride, const void* dz, int dz_cstride, float* ws, int N, int H,
+                                 int W, int Cin, int Cout, int tile_n, int splits, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !dz || !ws) return set_error(B2S_ERR_ARG, "b2s_conv1x1_wgrad: null pointer");
+  if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_conv1x1_wgrad: channels must be multiples of 64");
+  tile_n &= kTileNMask;
+  WgradParams p{};
+  int block_n;
+  if (wgrad_plan(N, H, W, Cin, Cout, 1, tile_n, splits, &p, &block_n))
+    return set_error(B2S_ERR_ARG, "b2s_conv1x1_wgrad: bad tile_n");
+  p.mode = WG_1X1; p.ws = ws;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_act_map4(&tmA, x, Cin, W, H, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
+  if ((rc = make_act_map4(&tmB, dz, Cout, W, H, N, dz_cstride, p.pw, p.ph, p.pn))) return rc;
+  const int grid = p.m_tiles * p.tiles_nn * p.splits;
+  count_launch();
+  switch (block_n) {
+    case 64:  return launch_wgrad<64, 6>(tmA, tmB, p, grid, stream);
+    case 128: return launch_wgrad<128, 3>(tmA, tmB, p, grid, stream);
+    case 256: return launch_wgrad<256, 4>(tmA, tmB, p, grid, stream);
+  }
+  return set_error(B2S_ERR_ARG, "b2s_conv1x1_wgrad: unsupported tile_n");
 }
 
 // ConvTranspose2d(k2,s2) weight gradient partials: ws[split][(a*2+b)*Cin+ci][co]; x [N,Hi,Wi,Cin], dy [N,2Hi,2Wi,Cout].

@@ -2,25 +2,9 @@
 // backward, 2x2 max-pool (fused into BN apply and BN backward), 1x1 head + threshold, Dice+BCE(+FocalTversky)
 // loss and gradient, weight packing, wgrad second-stage reduce, AdamW. All activations NHWC bf16, 16-byte
 // vectorised (8 channels per thread), grids sized in multiples of the SM count.
-#include "ptx.cuh"
-#include "b2s_internal.h"
+#include "ew_common.cuh"
 
 namespace b2s {
-
-constexpr int kThreads = 256;
-constexpr int kSMs = 148;
-constexpr int kEwBlocks = kSMs * 4;  // rows of every element-wise partial buffer
-
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
-  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                    pack_bf16x2(f[6], f[7]));
-}
-__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ void stg16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
 // ------------------------------------------------------------------------------------------------
 // generic deterministic row reduction: out[k] = sum_r in[r][k]
@@ -69,7 +53,7 @@ __device__ __forceinline__ void block_sum_pairs(const float* __restrict__ partia
 }
 
 // Reduce [rows][K] down to at most 128 rows (in scratch) when rows > 1024; returns pointer/rows to finalize from.
-static int reduce_to_small(const float* in, int rows, int K, float* scratch, const float** out_ptr, int* out_rows,
+int reduce_to_small(const float* in, int rows, int K, float* scratch, const float** out_ptr, int* out_rows,
                            cudaStream_t stream) {
   if (rows <= 1024) { *out_ptr = in; *out_rows = rows; return B2S_OK; }
   if (!scratch) return set_error(B2S_ERR_ARG, "scratch buffer required for rows > 1024");

@@ -1,0 +1,470 @@
+// Bandwidth kernels of the V-Net variant (reference models/vnet.py): BatchNorm -> ReLU -> Dropout (+ residual)
+// apply and its two-pass backward, squeeze-and-excitation (global pool, the two tiny FC layers, channel scale) forward
+// and backward, per-channel sums (bias gradients), zero-insertion 2x upsampling (backward of the stride-2 conv).
+// NHWC bf16 activations, 16-byte vectors (8 channels per thread), deterministic two-stage reductions.
+#include "ew_common.cuh"
+
+namespace b2s {
+
+// ---- counter-based dropout mask: depends only on (seed, logical NHWC element index) so backward re-derives it ----
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool drop_keep(unsigned long long idx, uint32_t seed, uint32_t thresh) {
+  const uint32_t h = mix32(static_cast<uint32_t>(idx) ^ mix32(static_cast<uint32_t>(idx >> 32) + seed));
+  return h >= thresh;   // P(keep) = 1 - thresh / 2^32
+}
+
+// out = dropout(relu(z * scale + shift)) + res      (models/vnet.py:51-59)
+__global__ void __launch_bounds__(kThreads)
+bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_cs,
+                    __nv_bfloat16* __restrict__ out, int out_cs, long long npix, int C, int relu, uint32_t drop_thresh,
+                    float drop_scale, uint32_t seed) {
+  const int groups = C / 8;
+  const int gshift = __ffs(groups) - 1;
+  const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  const int cg = static_cast<int>(tid & (groups - 1));
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = scale ? scale[cg * 8 + k] : 1.f; sh[k] = shift ? shift[cg * 8 + k] : 0.f; }
+  const long long total = npix * groups;
+  for (long long i = tid; i < total; i += stride) {
+    const long long pix = i >> gshift;
+    float v[8], rr[8];
+    unpack8(ldg16(z + pix * z_cs + cg * 8), v);
+    if (res) unpack8(ldg16(res + pix * res_cs + cg * 8), rr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = fmaf(v[k], sc[k], sh[k]);
+      if (relu) a = fmaxf(a, 0.f);
+      if (drop_thresh) a = drop_keep(static_cast<unsigned long long>(pix) * C + cg * 8 + k, seed, drop_thresh) ? a * drop_scale : 0.f;
+      if (res) a += rr[k];
+      v[k] = a;
+    }
+    stg16(out + pix * out_cs + cg * 8, pack8(v));
+  }
+}
+
+// Backward of a = dropout(relu(bn(z))): dy = da * keep/(1-p) * (bn(z) > 0).
+// APPLY = false: partial [grid][2][C] = sum dy, sum dy * xhat;   APPLY = true: dz = c0 (dy - c1 - xhat c2), partial
+// [grid][C] = sum dz (gradient of the conv bias). Rows beyond the grid are zero-filled (kEwBlocks rows in total).
+template <bool APPLY>
+__global__ void __launch_bounds__(kThreads)
+bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bfloat16* __restrict__ z, int z_cs,
+                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                  const float* __restrict__ invstd, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dz,
+                  int dz_cs, float* __restrict__ partial, long long npix, int C, int relu, uint32_t drop_thresh,
+                  float drop_scale, uint32_t seed) {
+  __shared__ float red[kThreads * 16];
+  const int groups = C / 8;
+  const int gshift = __ffs(groups) - 1;
+  const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  const int cg = static_cast<int>(tid & (groups - 1));
+  float sc[8], sh[8], mu[8], is[8], c0[8], c1[8], c2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = cg * 8 + k;
+    sc[k] = scale[c]; sh[k] = shift[c]; mu[k] = mean[c]; is[k] = invstd[c];
+    if (APPLY) { c0[k] = coef[c]; c1[k] = coef[C + c]; c2[k] = coef[2 * C + c]; }
+  }
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  const long long total = npix * groups;
+  for (long long i = tid; i < total; i += stride) {
+    const long long pix = i >> gshift;
+    float zv[8], g[8], outv[8];
+    unpack8(ldg16(z + pix * z_cs + cg * 8), zv);
+    unpack8(ldg16(da + pix * da_cs + cg * 8), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float d = g[k];
+      if (drop_thresh) d = drop_keep(static_cast<unsigned long long>(pix) * C + cg * 8 + k, seed, drop_thresh) ? d * drop_scale : 0.f;
+      if (relu && !(fmaf(zv[k], sc[k], sh[k]) > 0.f)) d = 0.f;
+      const float xh = (zv[k] - mu[k]) * is[k];
+      if (!APPLY) {
+        acc[k] += d;
+        acc[8 + k] = fmaf(d, xh, acc[8 + k]);
+      } else {
+        const float o = bf16_round(c0[k] * (d - c1[k] - xh * c2[k]));
+        outv[k] = o;
+        acc[k] += o;
+      }
+    }
+    if (APPLY) stg16(dz + pix * dz_cs + cg * 8, pack8(outv));
+  }
+  constexpr int NV = APPLY ? 8 : 16;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) red[threadIdx.x * NV + k] = acc[k];
+  __syncthreads();
+  const int per_group = kThreads / groups;
+  const int nout = APPLY ? C : 2 * C;
+  float* row = partial + static_cast<size_t>(blockIdx.x) * nout;
+  for (int o = threadIdx.x; o < nout; o += kThreads) {
+    const int which = o / C, ch = o - which * C;
+    const int gi = ch / 8, k = ch % 8;
+    float s = 0.f;
+    for (int t = 0; t < per_group; ++t) s += red[(t * groups + gi) * NV + which * 8 + k];
+    row[o] = s;
+  }
+  for (int rr = blockIdx.x + gridDim.x; rr < kEwBlocks; rr += gridDim.x)
+    for (int o = threadIdx.x; o < nout; o += kThreads) partial[static_cast<size_t>(rr) * nout + o] = 0.f;
+}
+
+// partial [kEwBlocks][C] = per-block sums over pixels of x (bias gradients of convs that are not followed by BN)
+__global__ void __launch_bounds__(kThreads)
+channel_sums_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, float* __restrict__ partial, long long npix, int C) {
+  __shared__ float red[kThreads * 8];
+  const int groups = C / 8;
+  const int gshift = __ffs(groups) - 1;
+  const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  const int cg = static_cast<int>(tid & (groups - 1));
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const long long total = npix * groups;
+  for (long long i = tid; i < total; i += stride) {
+    float v[8];
+    unpack8(ldg16(x + (i >> gshift) * x_cs + cg * 8), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
+  __syncthreads();
+  const int per_group = kThreads / groups;
+  float* row = partial + static_cast<size_t>(blockIdx.x) * C;
+  for (int o = threadIdx.x; o < C; o += kThreads) {
+    const int gi = o / 8, k = o % 8;
+    float s = 0.f;
+    for (int t = 0; t < per_group; ++t) s += red[(t * groups + gi) * 8 + k];
+    row[o] = s;
+  }
+}
+
+// dst [N,2Hs,2Ws,C]: dst[n,2i,2j] = src[n,i,j], zero elsewhere (zero insertion: stride-2 conv backward)
+__global__ void __launch_bounds__(kThreads)
+upsample_zero2x_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_bfloat16* __restrict__ dst, int dst_cs,
+                       int N, int Hs, int Ws, int C) {
+  const int groups = C / 8;
+  const int Hd = 2 * Hs, Wd = 2 * Ws;
+  const long long total = static_cast<long long>(N) * Hd * Wd * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int cg = static_cast<int>(i % groups);
+    const long long pix = i / groups;
+    const int w = static_cast<int>(pix % Wd);
+    const long long t = pix / Wd;
+    const int h = static_cast<int>(t % Hd);
+    const long long n = t / Hd;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(h & 1) && !(w & 1)) v = ldg16(src + ((n * Hs + (h >> 1)) * Ws + (w >> 1)) * src_cs + cg * 8);
+    stg16(dst + pix * dst_cs + cg * 8, v);
+  }
+}
+
+// ---- squeeze-and-excitation (models/vnet.py:5-26) ------------------------------------------------------------
+constexpr int kSePixPerBlock = 4096;   // pixels of one sample reduced by one block
+
+// partial[n][chunk][C] = sum over the chunk's pixels of x (DOT: of x * y)
+template <bool DOT>
+__global__ void __launch_bounds__(kThreads)
+se_pool_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat16* __restrict__ y, int y_cs,
+               float* __restrict__ partial, long long HW, int C, int chunks) {
+  __shared__ float red[kThreads * 8];
+  const int groups = C / 8;                 // power of two <= 256 (host-checked)
+  const int cg = threadIdx.x % groups;
+  const int pl = threadIdx.x / groups;
+  const int ppi = kThreads / groups;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const long long p0 = static_cast<long long>(chunk) * kSePixPerBlock;
+  const long long p1 = min(p0 + kSePixPerBlock, HW);
+  const long long base = static_cast<long long>(n) * HW;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (long long p = p0 + pl; p < p1; p += ppi) {
+    float v[8];
+    unpack8(ldg16(x + (base + p) * x_cs + cg * 8), v);
+    if (DOT) {
+      float u[8];
+      unpack8(ldg16(y + (base + p) * y_cs + cg * 8), u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(v[k], u[k], acc[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
+  __syncthreads();
+  float* row = partial + (static_cast<size_t>(n) * chunks + chunk) * C;
+  for (int o = threadIdx.x; o < C; o += kThreads) {
+    const int gi = o / 8, k = o % 8;
+    float s = 0.f;
+    for (int t = 0; t < ppi; ++t) s += red[(t * groups + gi) * 8 + k];
+    row[o] = s;
+  }
+}
+
+// one block per sample: mean = pooled / HW; hidden = relu(W1 mean + b1); gate = sigmoid(W2 hidden + b2)
+__global__ void __launch_bounds__(kThreads)
+se_fc_fwd_kernel(const float* __restrict__ partial, int chunks, float inv_hw, const float* __restrict__ w1,
+                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                 float* __restrict__ mean_out, float* __restrict__ hidden_out, float* __restrict__ gate_out, int C,
+                 int Cr) {
+  extern __shared__ float sm[];   // mean [C], hidden [Cr]
+  float* mean = sm;
+  float* hid = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += partial[(static_cast<size_t>(n) * chunks + k) * C + c];
+    s *= inv_hw;
+    mean[c] = s;
+    mean_out[static_cast<size_t>(n) * C + c] = s;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Cr; j += kThreads) {
+    float a = b1[j];
+    for (int c = 0; c < C; ++c) a = fmaf(w1[static_cast<size_t>(j) * C + c], mean[c], a);
+    a = fmaxf(a, 0.f);
+    hid[j] = a;
+    hidden_out[static_cast<size_t>(n) * Cr + j] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    float a = b2[c];
+    for (int j = 0; j < Cr; ++j) a = fmaf(w2[static_cast<size_t>(c) * Cr + j], hid[j], a);
+    gate_out[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-a));
+  }
+}
+
+// y = x * gate[n][c]
+__global__ void __launch_bounds__(kThreads)
+se_scale_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const float* __restrict__ gate,
+                const float* __restrict__ add, float add_scale, __nv_bfloat16* __restrict__ y, int y_cs, long long HW,
+                int C, long long npix) {
+  // forward: y = x * gate;  backward (add != nullptr): dx = dy * gate + add[n][c] * add_scale, with x := dy
+  const int groups = C / 8;
+  const long long total = npix * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int cg = static_cast<int>(i % groups);
+    const long long pix = i / groups;
+    const long long n = pix / HW;
+    float v[8];
+    unpack8(ldg16(x + pix * x_cs + cg * 8), v);
+    const float* gp = gate + n * C + cg * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= gp[k];
+    if (add) {
+      const float* ap = add + n * C + cg * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(ap[k], add_scale, v[k]);
+    }
+    stg16(y + pix * y_cs + cg * 8, pack8(v));
+  }
+}
+
+// one block per sample: dgate = sum partial; ds = dgate g (1-g); dh = (h>0) W2^T ds; dmean = W1^T dh
+__global__ void __launch_bounds__(kThreads)
+se_fc_bwd_kernel(const float* __restrict__ partial, int chunks, const float* __restrict__ gate,
+                 const float* __restrict__ hidden, const float* __restrict__ w1, const float* __restrict__ w2,
+                 float* __restrict__ ds_out, float* __restrict__ dh_out, float* __restrict__ dmean_out, int C, int Cr) {
+  extern __shared__ float sm[];   // ds [C], dh [Cr]
+  float* ds = sm;
+  float* dh = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += partial[(static_cast<size_t>(n) * chunks + k) * C + c];
+    const float g = gate[static_cast<size_t>(n) * C + c];
+    s *= g * (1.f - g);
+    ds[c] = s;
+    ds_out[static_cast<size_t>(n) * C + c] = s;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Cr; j += kThreads) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(w2[static_cast<size_t>(c) * Cr + j], ds[c], a);
+    a = hidden[static_cast<size_t>(n) * Cr + j] > 0.f ? a : 0.f;
+    dh[j] = a;
+    dh_out[static_cast<size_t>(n) * Cr + j] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    float a = 0.f;
+    for (int j = 0; j < Cr; ++j) a = fmaf(w1[static_cast<size_t>(j) * C + c], dh[j], a);
+    dmean_out[static_cast<size_t>(n) * C + c] = a;
+  }
+}
+
+// out[r][k] = sum_n a[n][r] * b[n][k]  (batch-summed outer products: the SE weight gradients), out [R][K];
+// bias gradients: out_bias[r] = sum_n a[n][r]
+__global__ void __launch_bounds__(kThreads)
+outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                 float* __restrict__ out_bias, int N, int R, int K) {
+  const long long total = static_cast<long long>(R) * K;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int r = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(r) * K);
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(a[static_cast<size_t>(n) * R + r], b[static_cast<size_t>(n) * K + k], s);
+    out[i] = s;
+    if (k == 0 && out_bias) {
+      float sb = 0.f;
+      for (int n = 0; n < N; ++n) sb += a[static_cast<size_t>(n) * R + r];
+      out_bias[r] = sb;
+    }
+  }
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+#define STREAM(s) static_cast<cudaStream_t>(s)
+
+static uint32_t drop_threshold(float p) {
+  if (p <= 0.f) return 0u;
+  double t = static_cast<double>(p) * 4294967296.0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return static_cast<uint32_t>(t);
+}
+
+extern "C" int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale, const float* shift, const void* res,
+                                int res_cstride, void* out, int out_cstride, long long npix, int C, int relu,
+                                float dropout_p, unsigned seed, void* stream) {
+  if (!z || !out) return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: null pointer");
+  if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: C/8 must be a power of two <= 256");
+  if (z_cstride % 8 || out_cstride % 8 || (res && res_cstride % 8))
+    return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: strides must be multiples of 8");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: dropout_p in [0,1)");
+  count_launch();
+  bn_act_apply_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, static_cast<const __nv_bfloat16*>(res), res_cstride,
+      static_cast<__nv_bfloat16*>(out), out_cstride, npix, C, relu, drop_threshold(dropout_p), 1.f / (1.f - dropout_p),
+      seed);
+  return check_launch("bn_act_apply_kernel");
+}
+
+extern "C" int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void* z, int z_cstride, const float* scale,
+                                     const float* shift, const float* mean, const float* invstd, float* partial,
+                                     long long npix, int C, int relu, float dropout_p, unsigned seed, void* stream) {
+  if (!da || !z || !scale || !shift || !mean || !invstd || !partial)
+    return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: null pointer");
+  if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: unsupported C");
+  count_launch();
+  bn_act_bwd_kernel<false><<<kSMs * 2, kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
+      mean, invstd, nullptr, nullptr, 0, partial, npix, C, relu, drop_threshold(dropout_p), 1.f / (1.f - dropout_p), seed);
+  return check_launch("bn_act_bwd_kernel<reduce>");
+}
+
+extern "C" int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* z, int z_cstride, const float* scale,
+                                    const float* shift, const float* mean, const float* invstd, const float* coef,
+                                    void* dz, int dz_cstride, float* dbias_partial, long long npix, int C, int relu,
+                                    float dropout_p, unsigned seed, void* stream) {
+  if (!da || !z || !scale || !shift || !mean || !invstd || !coef || !dz || !dbias_partial)
+    return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: null pointer");
+  if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: unsupported C");
+  count_launch();
+  bn_act_bwd_kernel<true><<<kSMs * 2, kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
+      mean, invstd, coef, static_cast<__nv_bfloat16*>(dz), dz_cstride, dbias_partial, npix, C, relu,
+      drop_threshold(dropout_p), 1.f / (1.f - dropout_p), seed);
+  return check_launch("bn_act_bwd_kernel<apply>");
+}
+
+extern "C" int b2s_channel_sums(const void* x, int x_cstride, float* partial, long long npix, int C, void* stream) {
+  if (!x || !partial) return set_error(B2S_ERR_ARG, "b2s_channel_sums: null pointer");
+  if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_channel_sums: unsupported C");
+  count_launch();
+  channel_sums_kernel<<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_cstride,
+                                                                 partial, npix, C);
+  return check_launch("channel_sums_kernel");
+}
+
+extern "C" int b2s_upsample_zero2x(const void* src, int src_cstride, void* dst, int dst_cstride, int N, int Hs, int Ws,
+                                   int C, void* stream) {
+  if (!src || !dst) return set_error(B2S_ERR_ARG, "b2s_upsample_zero2x: null pointer");
+  if (C % 8 || src_cstride % 8 || dst_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_upsample_zero2x: need multiples of 8");
+  const long long items = static_cast<long long>(N) * 4 * Hs * Ws * (C / 8);
+  count_launch();
+  upsample_zero2x_kernel<<<ew_grid_for(items, kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), src_cstride, static_cast<__nv_bfloat16*>(dst), dst_cstride, N, Hs, Ws, C);
+  return check_launch("upsample_zero2x_kernel");
+}
+
+extern "C" int b2s_se_chunks(long long HW) { return static_cast<int>((HW + kSePixPerBlock - 1) / kSePixPerBlock); }
+
+// partial [N][b2s_se_chunks(HW)][C]: sums of x over H*W (y == NULL) or of x*y (the gate gradient) per sample, channel
+extern "C" int b2s_se_pool(const void* x, int x_cstride, const void* y, int y_cstride, float* partial, int N,
+                           long long HW, int C, void* stream) {
+  if (!x || !partial) return set_error(B2S_ERR_ARG, "b2s_se_pool: null pointer");
+  if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_se_pool: unsupported C");
+  if (N <= 0 || N > 65535) return set_error(B2S_ERR_ARG, "b2s_se_pool: bad batch");
+  const int chunks = b2s_se_chunks(HW);
+  dim3 grid(chunks, N);
+  count_launch();
+  if (y)
+    se_pool_kernel<true><<<grid, kThreads, 0, STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_cstride,
+                                                                static_cast<const __nv_bfloat16*>(y), y_cstride, partial,
+                                                                HW, C, chunks);
+  else
+    se_pool_kernel<false><<<grid, kThreads, 0, STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_cstride, nullptr,
+                                                                 0, partial, HW, C, chunks);
+  return check_launch("se_pool_kernel");
+}
+
+extern "C" int b2s_se_fc_fwd(const float* partial, int chunks, long long HW, const float* w1, const float* b1,
+                             const float* w2, const float* b2, float* mean, float* hidden, float* gate, int N, int C,
+                             int Cr, void* stream) {
+  if (!partial || !w1 || !b1 || !w2 || !b2 || !mean || !hidden || !gate)
+    return set_error(B2S_ERR_ARG, "b2s_se_fc_fwd: null pointer");
+  if (C > 4096 || Cr < 1 || Cr > C) return set_error(B2S_ERR_ARG, "b2s_se_fc_fwd: unsupported channel counts");
+  count_launch();
+  se_fc_fwd_kernel<<<N, kThreads, (C + Cr) * sizeof(float), STREAM(stream)>>>(partial, chunks, 1.f / static_cast<float>(HW),
+                                                                             w1, b1, w2, b2, mean, hidden, gate, C, Cr);
+  return check_launch("se_fc_fwd_kernel");
+}
+
+extern "C" int b2s_se_scale(const void* x, int x_cstride, const float* gate, const float* add, float add_scale, void* y,
+                            int y_cstride, int N, long long HW, int C, void* stream) {
+  if (!x || !gate || !y) return set_error(B2S_ERR_ARG, "b2s_se_scale: null pointer");
+  if (C % 8 || x_cstride % 8 || y_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_se_scale: need multiples of 8");
+  const long long npix = static_cast<long long>(N) * HW;
+  count_launch();
+  se_scale_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_cstride, gate, add, add_scale, static_cast<__nv_bfloat16*>(y),
+      y_cstride, HW, C, npix);
+  return check_launch("se_scale_kernel");
+}
+
+extern "C" int b2s_se_fc_bwd(const float* partial, int chunks, const float* gate, const float* hidden, const float* mean,
+                             const float* w1, const float* w2, float* ds, float* dh, float* dmean, float* dw1, float* db1,
+                             float* dw2, float* db2, int N, int C, int Cr, void* stream) {
+  if (!partial || !gate || !hidden || !mean || !w1 || !w2 || !ds || !dh || !dmean || !dw1 || !db1 || !dw2 || !db2)
+    return set_error(B2S_ERR_ARG, "b2s_se_fc_bwd: null pointer");
+  if (C > 4096 || Cr < 1 || Cr > C) return set_error(B2S_ERR_ARG, "b2s_se_fc_bwd: unsupported channel counts");
+  count_launch();
+  se_fc_bwd_kernel<<<N, kThreads, (C + Cr) * sizeof(float), STREAM(stream)>>>(partial, chunks, gate, hidden, w1, w2, ds, dh,
+                                                                             dmean, C, Cr);
+  int rc = check_launch("se_fc_bwd_kernel");
+  if (rc) return rc;
+  // dW2 [C][Cr] = sum_n ds (x) hidden, db2 = sum_n ds;  dW1 [Cr][C] = sum_n dh (x) mean, db1 = sum_n dh
+  count_launch();
+  outer_sum_kernel<<<ew_grid_for(static_cast<long long>(C) * Cr, kThreads), kThreads, 0, STREAM(stream)>>>(ds, hidden, dw2, db2, N,
+                                                                                                         C, Cr);
+  count_launch();
+  outer_sum_kernel<<<ew_grid_for(static_cast<long long>(C) * Cr, kThreads), kThreads, 0, STREAM(stream)>>>(dh, mean, dw1, db1, N,
+                                                                                                         Cr, C);
+  return check_launch("outer_sum_kernel");
+}

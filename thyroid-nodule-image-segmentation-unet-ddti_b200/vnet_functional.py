@@ -1,0 +1,330 @@
+"""Autograd nodes of the V-Net variant (reference models/vnet.py) over libb2s kernels.
+
+Activations flow between the nodes as NHWC bf16 tensors ``[N,H,W,C]`` (contiguous, or a channel slice of a
+contiguous concat buffer). Every node's forward AND backward is a sequence of libb2s kernel launches (ops.py);
+torch.autograd only walks the graph (fan-out gradient sums at the residual / skip branches are its one arithmetic
+contribution). The UNet path (engine.py) does not use autograd internally; this composition trades some fusion
+for covering the V-Net's larger op set (stride-2 conv, 1x1 projections, SE blocks, Conv->BN->ReLU->Dropout order).
+"""
+import torch
+
+from . import ops
+from .ops import Act, BF16
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def as_act(t):
+    """NHWC bf16 tensor (contiguous or a channel slice of a contiguous buffer) -> ops.Act"""
+    if t.dtype != BF16 or t.dim() != 4:
+        raise ValueError(f"expected a 4-D bf16 NHWC tensor, got {t.dtype} {tuple(t.shape)}")
+    if not t.is_cuda:
+        raise ops._lib.B2SError("libb2s kernels need CUDA tensors; there is no CPU fallback")
+    N, H, W, C = t.shape
+    if t.is_contiguous() and t.storage_offset() % 8 == 0:
+        return Act(t)
+    s = t.stride()
+    Ct = s[2]
+    if s[3] != 1 or s[1] != W * Ct or s[0] != H * W * Ct or Ct < C:
+        return Act(t.contiguous())
+    c0 = t.storage_offset() % Ct
+    base = torch.as_strided(t, (N, H, W, Ct), (H * W * Ct, W * Ct, Ct, 1), t.storage_offset() - c0)
+    return Act(base, c0, C)
+
+
+def new_act(N, H, W, C, device):
+    return torch.empty((N, H, W, C), dtype=BF16, device=device)
+
+
+def _bn_affine(training, stats, rows, count, gamma, beta, rm, rv, nbt, C, device):
+    f32 = dict(dtype=torch.float32, device=device)
+    scale, shift, mean, invstd = (torch.empty(C, **f32) for _ in range(4))
+    if training:
+        scratch = torch.empty(128 * 2 * C, **f32)
+        ops.bn_finalize(stats, rows, C, count, gamma, beta, rm, rv, nbt, BN_MOMENTUM, BN_EPS, scale, shift, mean, invstd,
+                        scratch)
+    else:
+        ops.bn_eval_affine(gamma, beta, rm, rv, BN_EPS, scale, shift)
+        mean, invstd = None, None
+    return scale, shift, mean, invstd
+
+
+class ConvBnAct(torch.autograd.Function):
+    """out = dropout(relu(BN(conv3x3(x) + b))) (+ res)      models/vnet.py:51-59 (one loop trip, + the residual add)
+
+    x: NHWC bf16 activation, or the fp32 image [N,1,H,W] for the first conv of a branch (Cin = 1 kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, res, w, b, gamma, beta, rm, rv, nbt, training, p_drop, seed):
+        dev = w.device
+        Cout = w.shape[0]
+        first = x.dtype == torch.float32
+        if first:
+            N, _, H, W = x.shape
+            x = x.contiguous()
+        else:
+            xa = as_act(x)
+            N, H, W = xa.N, xa.H, xa.W
+        z = new_act(N, H, W, Cout, dev)
+        za = Act(z)
+        if first:
+            rows = ops.c1_rows(N, H, W)
+            stats = torch.empty(rows * 2 * Cout, dtype=torch.float32, device=dev) if training else None
+            ops.conv3x3_c1_fwd(x, w.detach(), b.detach(), za, relu=False, stats=stats)
+        else:
+            wf, _ = ops.pack_conv_weight(w, want_dgrad=False)
+            rows = ops.conv_stats_rows(N, H, W, Cout)
+            stats = torch.empty(rows * 2 * Cout, dtype=torch.float32, device=dev) if training else None
+            ops.conv_fwd(xa, wf, b.detach(), za, ksize=3, relu=False, stats=stats)
+        scale, shift, mean, invstd = _bn_affine(training, stats, rows, float(N * H * W), gamma.detach(), beta.detach(),
+                                                rm, rv, nbt, Cout, dev)
+        out = new_act(N, H, W, Cout, dev)
+        ops.bn_act_apply(za, scale, shift, as_act(res) if res is not None else None, Act(out), relu=True,
+                         dropout_p=p_drop if training else 0.0, seed=seed)
+        ctx.save_for_backward(x, z, w, gamma, scale, shift, mean if mean is not None else scale,
+                              invstd if invstd is not None else scale)
+        ctx.cfg = (first, training, p_drop, seed, res is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, z, w, gamma, scale, shift, mean, invstd = ctx.saved_tensors
+        first, training, p_drop, seed, has_res = ctx.cfg
+        if not training:
+            raise RuntimeError("b200seg V-Net: backward through eval-mode BatchNorm is not implemented")
+        dev = w.device
+        Cout, Cin = w.shape[0], w.shape[1]
+        za = Act(z)
+        N, H, W = za.N, za.H, za.W
+        da = as_act(dout)
+        f32 = dict(dtype=torch.float32, device=dev)
+        dz = new_act(N, H, W, Cout, dev)
+        dgamma, dbeta, dbias = torch.empty(Cout, **f32), torch.empty(Cout, **f32), torch.empty(Cout, **f32)
+        ops.bn_act_bwd(da, za, scale, shift, mean, invstd, gamma.detach(), float(N * H * W), Act(dz), dgamma, dbeta,
+                       dbias, relu=True, dropout_p=p_drop, seed=seed)
+        dw = torch.empty((Cout, Cin, 3, 3), **f32)
+        dx = None
+        if first:
+            rows = ops.c1_rows(N, H, W)
+            partial = torch.empty(rows * Cout * 9, **f32)
+            scratch = torch.empty(128 * Cout * 9, **f32)
+            ops.conv3x3_c1_wgrad(x, Act(dz), partial, scratch, dw)
+        else:
+            xa = as_act(x)
+            nbytes, _ = ops.wgrad_workspace(N, H, W, Cin, Cout, 9)
+            ws = torch.empty(nbytes // 4, **f32)
+            ops.conv3x3_wgrad(xa, Act(dz), ws, dw)
+            if ctx.needs_input_grad[0]:
+                _, wd = ops.pack_conv_weight(w, want_dgrad=True)
+                dx = new_act(N, H, W, Cin, dev)
+                ops.conv_fwd(Act(dz), wd, None, Act(dx), ksize=3)
+        dres = dout if has_res else None
+        return dx, dres, dw, dbias, dgamma, dbeta, None, None, None, None, None, None
+
+
+class Conv1x1(torch.autograd.Function):
+    """nn.Conv2d(Cin, Cout, 1) on NHWC bf16 (residual projections, models/vnet.py:46,58). For the fp32 image
+    (Cin = 1) the 1x1 conv is the centre tap of the Cin = 1 3x3 kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        dev = w.device
+        Cout = w.shape[0]
+        first = x.dtype == torch.float32
+        if first:
+            N, _, H, W = x.shape
+            x = x.contiguous()
+            w3 = torch.zeros((Cout, 1, 3, 3), dtype=torch.float32, device=dev)
+            w3[:, :, 1, 1] = w.detach()[:, :, 0, 0]
+            out = new_act(N, H, W, Cout, dev)
+            ops.conv3x3_c1_fwd(x, w3, b.detach(), Act(out), relu=False, stats=None)
+        else:
+            xa = as_act(x)
+            N, H, W = xa.N, xa.H, xa.W
+            wf, _ = ops.pack_conv_weight(w, want_dgrad=False)
+            out = new_act(N, H, W, Cout, dev)
+            ops.conv_fwd(xa, wf, b.detach(), Act(out), ksize=1)
+        ctx.save_for_backward(x, w)
+        ctx.first = first
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        dev = w.device
+        Cout, Cin = w.shape[0], w.shape[1]
+        dy = as_act(dout)
+        N, H, W = dy.N, dy.H, dy.W
+        f32 = dict(dtype=torch.float32, device=dev)
+        db = torch.empty(Cout, **f32)
+        ops.channel_sums(dy, db)
+        dx = None
+        if ctx.first:
+            dyc = Act(dout.contiguous()) if dy.c0 or dy.cstride != dy.C else dy
+            rows = ops.c1_rows(N, H, W)
+            partial = torch.empty(rows * Cout * 9, **f32)
+            scratch = torch.empty(128 * Cout * 9, **f32)
+            dw3 = torch.empty((Cout, 1, 3, 3), **f32)
+            ops.conv3x3_c1_wgrad(x, dyc, partial, scratch, dw3)
+            dw = dw3[:, :, 1:2, 1:2].contiguous()
+        else:
+            xa = as_act(x)
+            dw = torch.empty((Cout, Cin, 1, 1), **f32)
+            ops.conv1x1_wgrad(xa, dy, dw)
+            if ctx.needs_input_grad[0]:
+                _, wd = ops.pack_conv_weight(w, want_dgrad=True)
+                dx = new_act(N, H, W, Cin, dev)
+                ops.conv_fwd(dy, wd, None, Act(dx), ksize=1)
+        return dx, dw, db
+
+
+class ConvS2(torch.autograd.Function):
+    """nn.Conv2d(C, 2C, 3, stride=2, padding=1) (models/vnet.py:97). Backward = stride-1 kernels on the zero-inserted
+    output gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xa = as_act(x)
+        Cout = w.shape[0]
+        wf, _ = ops.pack_conv_weight(w, want_dgrad=False)
+        out = new_act(xa.N, xa.H // 2, xa.W // 2, Cout, w.device)
+        ops.conv3x3_s2_fwd(xa, wf, b.detach(), Act(out))
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        dev = w.device
+        xa = as_act(x)
+        dy = as_act(dout)
+        Cout, Cin = w.shape[0], w.shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        db = torch.empty(Cout, **f32)
+        ops.channel_sums(dy, db)
+        up = new_act(xa.N, xa.H, xa.W, Cout, dev)
+        ops.upsample_zero2x(dy, Act(up))
+        dw = torch.empty((Cout, Cin, 3, 3), **f32)
+        nbytes, _ = ops.wgrad_workspace(xa.N, xa.H, xa.W, Cin, Cout, 9)
+        ws = torch.empty(nbytes // 4, **f32)
+        ops.conv3x3_wgrad(xa, Act(up), ws, dw)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wd = ops.pack_conv_weight(w, want_dgrad=True)
+            dx = new_act(xa.N, xa.H, xa.W, Cin, dev)
+            ops.conv_fwd(Act(up), wd, None, Act(dx), ksize=3)
+        return dx, dw, db
+
+
+class ConvT2x2(torch.autograd.Function):
+    """nn.ConvTranspose2d(Cin, Cout, 2, stride=2) (models/vnet.py:101-104)"""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xa = as_act(x)
+        Cout = w.shape[1]
+        wf, _ = ops.pack_convt_weight(w)
+        out = new_act(xa.N, 2 * xa.H, 2 * xa.W, Cout, w.device)
+        ops.convt_fwd(xa, wf, b.detach(), Act(out))
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        dev = w.device
+        xa = as_act(x)
+        dy = as_act(dout)
+        Cin, Cout = w.shape[0], w.shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        db = torch.empty(Cout, **f32)
+        ops.channel_sums(dy, db)
+        dw = torch.empty((Cin, Cout, 2, 2), **f32)
+        nbytes, _ = ops.wgrad_workspace(xa.N, xa.H, xa.W, Cin, Cout, 4)
+        ws = torch.empty(nbytes // 4, **f32)
+        ops.convt_wgrad(xa, dy, ws, dw)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wd = ops.pack_convt_weight(w)
+            dx = new_act(xa.N, xa.H, xa.W, Cin, dev)
+            ops.convt_dgrad(dy, wd, Act(dx))
+        return dx, dw, db
+
+
+class SE(torch.autograd.Function):
+    """SEBlock (models/vnet.py:18-26): x * sigmoid(W2 relu(W1 avgpool(x) + b1) + b2)"""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        xa = as_act(x)
+        C, Cr = w1.shape[1], w1.shape[0]
+        out = new_act(xa.N, xa.H, xa.W, C, w1.device)
+        w1m, w2m = w1.detach().reshape(Cr, C).contiguous(), w2.detach().reshape(C, Cr).contiguous()
+        mean, hidden, gate = ops.se_forward(xa, w1m, b1.detach(), w2m, b2.detach(), Act(out))
+        ctx.save_for_backward(x, mean, hidden, gate, w1m, w2m)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mean, hidden, gate, w1m, w2m = ctx.saved_tensors
+        xa = as_act(x)
+        dy = as_act(dout)
+        dx = new_act(xa.N, xa.H, xa.W, xa.C, x.device)
+        dw1, db1, dw2, db2 = ops.se_backward(dy, xa, mean, hidden, gate, w1m, w2m, Act(dx))
+        Cr, C = dw1.shape
+        return dx, dw1.view(Cr, C, 1, 1), db1, dw2.view(C, Cr, 1, 1), db2
+
+
+class Cat(torch.autograd.Function):
+    """torch.cat along channels (models/vnet.py:127-150) with the strided channel-slice copy kernel; backward hands
+    out channel-slice views of the incoming gradient (no copy)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        acts = [as_act(t) for t in xs]
+        a0 = acts[0]
+        Ct = sum(a.C for a in acts)
+        out = new_act(a0.N, a0.H, a0.W, Ct, xs[0].device)
+        o = 0
+        for a in acts:
+            ops.copy_channels(a, Act(out, o, a.C))
+            o += a.C
+        ctx.sizes = [a.C for a in acts]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads, o = [], 0
+        for c in ctx.sizes:
+            grads.append(dout[..., o:o + c])
+            o += c
+        return tuple(grads)
+
+
+class Head(torch.autograd.Function):
+    """final nn.Conv2d(C, num_classes, 1) (models/vnet.py:115): NHWC bf16 -> fp32 logits [N,O,H,W]"""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xa = as_act(x)
+        O = w.shape[0]
+        logits = torch.empty((xa.N, O, xa.H, xa.W), dtype=torch.float32, device=w.device)
+        ops.head_fwd(xa, None, None, w.detach().reshape(O, -1).contiguous(), b.detach(), logits, None)
+        ctx.save_for_backward(x, w)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, w = ctx.saved_tensors
+        xa = as_act(x)
+        O, C = w.shape[0], w.shape[1]
+        dev = w.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dx = new_act(xa.N, xa.H, xa.W, C, dev)
+        partial = torch.empty(ops.ew_rows() * (O * C + O), **f32)
+        scratch = torch.empty(128 * (O * C + O), **f32)
+        dwdb = torch.empty(O * C + O, **f32)
+        ops.head_bwd(dlogits.contiguous().float(), xa, None, None, w.detach().reshape(O, C).contiguous(), Act(dx),
+                     partial, scratch, dwdb)
+        return dx, dwdb[:O * C].view(O, C, 1, 1).clone(), dwdb[O * C:].clone()
