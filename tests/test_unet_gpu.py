@@ -259,3 +259,35 @@ def test_full_size_properties(net, ref_params):
         full = net(x)
         half = net(x[:2].contiguous())
     assert float((full[:2] - half).abs().max()) < 1e-5, "eval-mode samples must be independent of the batch"
+
+
+def test_inference_512_masks_match_torch_fp32(net, ref_params):
+    """BASELINE configs[3] shape (1x512x512 frames, eval mode, thresholded masks) at batch 4: logits against the
+    functional torch port in fp32 on the GPU (TF32 off), masks bit-exact outside the bf16 guard band and equal to the
+    threshold of this run's own logits everywhere."""
+    from oracle import unet_torch_ref as T
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = {k: v.clone() for k, v in ref_params.items()}
+    g = torch.Generator().manual_seed(5)
+    for k in sd:   # non-degenerate running statistics (a freshly initialised net has mean 0 / var 1)
+        if k.endswith("running_mean"):
+            sd[k] = torch.rand(sd[k].shape, generator=g) * 0.2
+        elif k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=g)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    x, _ = O.synth_batch(4, 512, 512, seed=99)
+    x = x.to(DEV)
+    with torch.no_grad():
+        logits, mask = net.predict_mask(x)
+        ref = T.unet_forward({k: v.to(DEV) for k, v in sd.items()}, x, train=False)
+    torch.cuda.synchronize()
+    d = (logits - ref).abs()
+    scale = float(ref.abs().mean())
+    assert float(d.mean()) < 0.02 * max(scale, 1e-3) + 2e-3, f"mean |dlogit| {float(d.mean())} (mean |logit| {scale})"
+    band = ref.abs() > 8 * float(d.mean()) + 1e-3
+    assert bool((mask.bool()[band] == (torch.sigmoid(ref) > 0.5)[band]).all())
+    assert float((~band).float().mean()) < 0.2, "guard band covers too many pixels to be a meaningful check"
+    assert torch.equal(mask.bool(), torch.sigmoid(logits) > 0.5)
+    net.train()
