@@ -140,6 +140,10 @@ int b2s_seg_loss_bwd(const float* logits, const float* targets, const float* sum
 int b2s_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* same update with hyper = {lr, beta1, beta2, eps, weight_decay, 1-beta1^step, sqrt(1-beta2^step), grad_scale} read
+ * from DEVICE memory: lets a captured CUDA graph of the whole step be replayed while lr / step change. */
+int b2s_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper, void* stream);
+
 /* torch.cat along channels for API-visible concat (models/model.py:64-70): strided channel-slice copy. */
 int b2s_copy_channels(const void* src, int src_cstride, void* dst, int dst_cstride, long long npix, int C,
                       void* stream);

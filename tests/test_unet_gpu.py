@@ -291,3 +291,32 @@ def test_inference_512_masks_match_torch_fp32(net, ref_params):
     assert float((~band).float().mean()) < 0.2, "guard band covers too many pixels to be a meaningful check"
     assert torch.equal(mask.bool(), torch.sigmoid(logits) > 0.5)
     net.train()
+
+
+def test_cuda_graph_step_equals_eager_step(ref_params):
+    """TrainStep.capture/step_graphed (one CUDA graph per optimisation step) against the host-launched step: same
+    parameters, BatchNorm buffers and losses after several steps with a changing learning rate."""
+    from b200seg.train import TrainStep
+    x, t = O.synth_batch(2, 32, 32, seed=7)
+    x2, t2 = O.synth_batch(2, 32, 32, seed=8)
+    x, t, x2, t2 = (v.to(DEV) for v in (x, t, x2, t2))
+    lrs = [1e-3, 5e-4, 2e-3]
+    eager = TrainStep({k: v.clone() for k, v in ref_params.items()}, DEV, lr=1e-3)
+    graph = TrainStep({k: v.clone() for k, v in ref_params.items()}, DEV, lr=1e-3)
+    assert graph.capture(x, t), getattr(graph, "capture_error", "")
+    for _ in range(2):                      # capture() ran two real eager steps on (x, t) at the default lr
+        eager.step(x, t)
+    losses = []
+    for i, lr in enumerate(lrs):
+        xb, tb = (x, t) if i % 2 == 0 else (x2, t2)
+        le = eager.step(xb, tb, lr=lr).clone()
+        lg = graph.step_graphed(xb, tb, lr=lr).clone()
+        losses.append((float(le[0]), float(lg[0])))
+    torch.cuda.synchronize()
+    for a, b in losses:
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), losses
+    assert eager.step_count == graph.step_count == 5
+    se, sg = eager.state_dict(), graph.state_dict()
+    for k in se:
+        assert torch.allclose(se[k].float(), sg[k].float(), rtol=1e-6, atol=1e-7), k
+    assert graph.graph_launches > 150

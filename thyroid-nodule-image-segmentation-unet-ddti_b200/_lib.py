@@ -48,6 +48,7 @@ SIGNATURES = {
     "b2s_seg_loss_fwd": (I, [P, P, I, LL, P, P, P, F, F, F, F, F, F, F, F, P]),
     "b2s_seg_loss_bwd": (I, [P, P, P, P, I, LL, LL, I, P, P, F, F, F, F, F, F, F, F, P]),
     "b2s_adamw_step": (I, [P, P, P, P, LL, F, F, F, F, F, I, F, P]),
+    "b2s_adamw_step_dev": (I, [P, P, P, P, LL, P, P]),
     "b2s_copy_channels": (I, [P, I, P, I, LL, I, P]),
     "b2s_conv3x3_s2_fwd": (I, [P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "b2s_upsample_zero2x": (I, [P, I, P, I, I, I, I, I, P]),

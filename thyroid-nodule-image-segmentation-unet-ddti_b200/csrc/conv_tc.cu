@@ -285,15 +285,16 @@ struct WgradParams {
   int total_rb;                   // num_taps * ci_blocks
   int cin, cout;
   int tiles_nn;                   // cout / BLOCK_N
-  int m_tiles;                    // ceil(total_rb / 2)
+  int mt;                         // M tiles (pairs of row blocks) per CTA: 1 or 2
+  int m_tiles;                    // ceil(total_rb / (2 * mt))
   int splits, chunks_total, chunks_per_split;
   int mode;
   float* ws;                      // [splits][num_taps*cin][cout] fp32
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MT>
 struct WgSmem {
-  static constexpr int kABytes = 2 * 64 * 128;            // two (64 px x 64 ch) boxes
+  static constexpr int kABytes = MT * 2 * 64 * 128;       // MT M tiles x two (64 px x 64 ch) boxes
   static constexpr int kBBytes = (BLOCK_N / 64) * 64 * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kPipeBytes = STAGES * kStageBytes;
@@ -301,13 +302,18 @@ struct WgSmem {
   static constexpr int kTmemPtrOffset = kBarOffset + (2 * STAGES + 1) * 8;
   static constexpr int kTotal = kTmemPtrOffset + 16;
   static constexpr int kDynBytes = kTotal + 1024;
+  static constexpr int kTmemCols = MT * BLOCK_N;
+  static_assert(kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns");
+  static_assert(kDynBytes <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
-template <int BLOCK_N, int STAGES>
+// MT = 2: two M tiles (four (tap, ci) row blocks) share every dz (B) stage: 131 FLOP per L2 byte at BLOCK_N = 256.
+template <int BLOCK_N, int STAGES, int MT>
 __global__ void __launch_bounds__(kNumThreads)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const WgradParams p) {
-  using L = WgSmem<BLOCK_N, STAGES>;
+  using L = WgSmem<BLOCK_N, STAGES, MT>;
+  constexpr int NRB = 2 * MT;   // row blocks (64 rows of the (tap, ci) space) per CTA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -332,7 +338,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
     }
-    tmem_alloc(tmem_ptr_smem, BLOCK_N);
+    tmem_alloc(tmem_ptr_smem, L::kTmemCols);
     tmem_relinquish();
   } else if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -349,11 +355,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      // row blocks (tap, ci block of 64) of this tile; a padding block re-loads the last valid one
-      int tap_j[2], cib_j[2];
+      // row blocks (tap, ci block of 64) of this CTA; a padding block re-loads the last valid one
+      int tap_j[NRB], cib_j[NRB];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        int rb = min(m_tile * 2 + j, p.total_rb - 1);
+      for (int j = 0; j < NRB; ++j) {
+        int rb = min(m_tile * NRB + j, p.total_rb - 1);
         tap_j[j] = rb / p.ci_blocks;
         cib_j[j] = rb - tap_j[j] * p.ci_blocks;
       }
@@ -370,7 +376,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint8_t* a_dst = smem_a + stage * L::kABytes;
         uint8_t* b_dst = smem_b + stage * L::kBBytes;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < NRB; ++j) {
           int dh = 0, dw = 0;
           if (p.mode == WG_CONV3) { dh = tap_j[j] / 3 - 1; dw = tap_j[j] % 3 - 1; }
           tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 8192, cib_j[j] * 64, w0 + dw, h0 + dh, n0);
@@ -380,7 +386,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_4d(&tmB, &full_bar[stage], b_dst + j * 8192, n_tile * BLOCK_N + j * 64, w0, h0, n0);
         } else {
-          // convT: both row blocks of a tile share one tap only if ci_blocks is even (host guarantees it)
+          // convT: all row blocks of a CTA share one tap (host guarantees ci_blocks % NRB == 0)
           const int a = tap_j[0] >> 1, b = tap_j[0] & 1;
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
@@ -391,49 +397,66 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && k_iters > 0) {
+    // whole warp walks the ring (addresses stay in uniform registers); one elected lane issues
+    if (k_iters > 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 1, 1);
+      const uint32_t tbase = __reduce_or_sync(0xffffffffu, tmem_acc);
+      const bool leader = elect_one();
+      const uint64_t proto = umma_smem_desc_sw128(0, 8192, 1024);   // 64-wide panels 8 KB apart, 8-pixel groups 1 KB
+      const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(proto) + (smem_u32(smem_a) >> 4);
+      const uint32_t b_lo0 = static_cast<uint32_t>(proto) + (smem_u32(smem_b) >> 4);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a + stage * L::kABytes);
-        const uint32_t b_addr = smem_u32(smem_b + stage * L::kBBytes);
+        const uint32_t a_lo = a_lo0 + stage * (L::kABytes >> 4);
+        const uint32_t b_lo = b_lo0 + stage * (L::kBBytes >> 4);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 16 pixels (K rows of 128 B) per MMA
-          const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, 8192, 1024);
-          const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, 8192, 1024);
-          umma_bf16(tmem_acc, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // 16 pixels (K rows of 128 B) per MMA
+              umma_bf16_lohi(tbase + mt * BLOCK_N, a_lo + mt * (16384 >> 4) + k * (2048 >> 4), desc_hi,
+                             b_lo + k * (2048 >> 4), desc_hi, idesc, k != 0 ? 1u : static_cast<uint32_t>(it != 0));
+          }
+          umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);
+      if (leader) umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int rb = m_tile * 2 + (row >> 6);
-    const bool valid = rb < p.total_rb;
-    const size_t grow = static_cast<size_t>(rb) * 64 + (row & 63);  // row in (tap, ci) space
-    float* dst = p.ws + (static_cast<size_t>(split) * p.num_taps * p.cin + grow) * p.cout + n_tile * BLOCK_N;
     if (k_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
+    }
 #pragma unroll 1
-      for (int s = 0; s < BLOCK_N / 32; ++s) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + s * 32, v);
-        tmem_ld_wait();
-        if (valid) {
+    for (int mt = 0; mt < MT; ++mt) {
+      const int rb = (m_tile * MT + mt) * 2 + (row >> 6);
+      const bool valid = rb < p.total_rb;
+      const size_t grow = static_cast<size_t>(rb) * 64 + (row & 63);  // row in (tap, ci) space
+      float* dst = p.ws + (static_cast<size_t>(split) * p.num_taps * p.cin + grow) * p.cout + n_tile * BLOCK_N;
+      if (k_iters > 0) {
+#pragma unroll 1
+        for (int s = 0; s < BLOCK_N / 32; ++s) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + mt * BLOCK_N + s * 32, v);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(dst + s * 32 + c * 4) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(dst + s * 32 + c * 4) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
         }
+      } else if (valid) {
+        for (int c = 0; c < BLOCK_N / 4; ++c) *reinterpret_cast<uint4*>(dst + c * 4) = make_uint4(0, 0, 0, 0);
       }
-    } else if (valid) {
-      for (int c = 0; c < BLOCK_N / 4; ++c) *reinterpret_cast<uint4*>(dst + c * 4) = make_uint4(0, 0, 0, 0);
     }
   }
 
@@ -441,7 +464,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, BLOCK_N);
+    tmem_dealloc(tmem_acc, L::kTmemCols);
   }
 }
 
@@ -603,11 +626,11 @@ extern "C" int b2s_convt2x2_dgrad(const void* dy, int dy_cstride, const void* w_
 
 // ---- wgrad -----------------------------------------------------------------------------------
 namespace b2s {
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MT>
 static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, int grid,
                         cudaStream_t stream) {
-  using L = WgSmem<BLOCK_N, STAGES>;
-  auto kfn = wgrad_tc_kernel<BLOCK_N, STAGES>;
+  using L = WgSmem<BLOCK_N, STAGES, MT>;
+  auto kfn = wgrad_tc_kernel<BLOCK_N, STAGES, MT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes);
@@ -616,6 +639,25 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Wg
   }
   kfn<<<grid, kNumThreads, L::kDynBytes, stream>>>(tmA, tmB, p);
   return check_launch("wgrad_tc_kernel");
+}
+
+static int dispatch_wgrad(int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p,
+                          cudaStream_t stream) {
+  const int grid = p.m_tiles * p.tiles_nn * p.splits;
+  count_launch();
+  if (p.mt == 2) {
+    switch (block_n) {
+      case 128: return launch_wgrad<128, 4, 2>(tmA, tmB, p, grid, stream);   // 4 x 48 KB
+      case 256: return launch_wgrad<256, 3, 2>(tmA, tmB, p, grid, stream);   // 3 x 64 KB, all 512 TMEM columns
+    }
+  } else {
+    switch (block_n) {
+      case 64:  return launch_wgrad<64, 6, 1>(tmA, tmB, p, grid, stream);    // 6 x 24 KB
+      case 128: return launch_wgrad<128, 3, 1>(tmA, tmB, p, grid, stream);   // 3 x 32 KB
+      case 256: return launch_wgrad<256, 4, 1>(tmA, tmB, p, grid, stream);   // 4 x 48 KB
+    }
+  }
+  return set_error(B2S_ERR_ARG, "wgrad: unsupported tile_n");
 }
 
 static int wgrad_plan(int N, int H, int W, int Cin, int Cout, int num_taps, int tile_n, int splits_req,
@@ -627,15 +669,18 @@ static int wgrad_plan(int N, int H, int W, int Cin, int Cout, int num_taps, int 
   p->chunks_w = (W + p->pw - 1) / p->pw; p->chunks_h = (H + p->ph - 1) / p->ph; p->chunks_n = (N + p->pn - 1) / p->pn;
   p->H = H;
   p->num_taps = num_taps; p->ci_blocks = Cin / 64; p->total_rb = num_taps * p->ci_blocks;
-  p->cin = Cin; p->cout = Cout; p->tiles_nn = Cout / block_n; p->m_tiles = (p->total_rb + 1) / 2;
+  // two M tiles per dz stage when the row-block count allows it (transposed conv: every row block of a CTA must
+  // belong to one tap, i.e. Cin % 256 == 0)
+  p->mt = (block_n >= 128 && p->total_rb >= 4 && (num_taps != 4 || p->ci_blocks % 4 == 0)) ? 2 : 1;
+  p->cin = Cin; p->cout = Cout; p->tiles_nn = Cout / block_n; p->m_tiles = (p->total_rb + 2 * p->mt - 1) / (2 * p->mt);
   p->chunks_total = p->chunks_w * p->chunks_h * p->chunks_n;
   int splits = splits_req;
   if (splits <= 0) {
     // keep >= 16 K-chunks per CTA (every split costs a K-sized fp32 partial) and
     // the grid must fit in ONE wave: CTAs resident per SM follow from the shared memory of the instantiation
-    // (block_n 64: 6 x 24 KB, 128: 3 x 32 KB, 256: 4 x 48 KB -> 1, 2, 1 CTAs per SM)
+    // (one tile per stage: block_n 64: 6 x 24 KB, 128: 3 x 32 KB, 256: 4 x 48 KB -> 1, 2, 1 CTAs per SM; tile pairs: 1)
     const int base = p->m_tiles * p->tiles_nn;
-    const int resident = num_sms() * (block_n == 128 ? 2 : 1);
+    const int resident = num_sms() * ((block_n == 128 && p->mt == 1) ? 2 : 1);
     splits = resident / base;
     const int max_by_work = p->chunks_total / 16 > 0 ? p->chunks_total / 16 : 1;
     if (splits > max_by_work) splits = max_by_work;
@@ -687,14 +732,7 @@ extern "C" int b2s_conv3x3_wgrad(const void* x, int x_cstride, const void* dz, i
   int rc;
   if ((rc = make_act_map4(&tmA, x, Cin, W, H, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
   if ((rc = make_act_map4(&tmB, dz, Cout, W, H, N, dz_cstride, p.pw, p.ph, p.pn))) return rc;
-  const int grid = p.m_tiles * p.tiles_nn * p.splits;
-  count_launch();
-  switch (block_n) {
-    case 64:  return launch_wgrad<64, 6>(tmA, tmB, p, grid, stream);    // 6 x 24 KB
-    case 128: return launch_wgrad<128, 3>(tmA, tmB, p, grid, stream);   // 3 x 32 KB
-    case 256: return launch_wgrad<256, 4>(tmA, tmB, p, grid, stream);   // 4 x 48 KB
-  }
-  return set_error(B2S_ERR_ARG, "b2s_conv3x3_wgrad: unsupported tile_n");
+  return dispatch_wgrad(block_n, tmA, tmB, p, stream);
 }
 
 // 1x1 conv weight gradient partials (residual projections of models/vnet.py:46): ws[split][ci][co].
@@ -713,14 +751,7 @@ extern "C" int b2s_conv1x1_wgrad(const void* x, int x_cstride, const void* dz, i
   int rc;
   if ((rc = make_act_map4(&tmA, x, Cin, W, H, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
   if ((rc = make_act_map4(&tmB, dz, Cout, W, H, N, dz_cstride, p.pw, p.ph, p.pn))) return rc;
-  const int grid = p.m_tiles * p.tiles_nn * p.splits;
-  count_launch();
-  switch (block_n) {
-    case 64:  return launch_wgrad<64, 6>(tmA, tmB, p, grid, stream);
-    case 128: return launch_wgrad<128, 3>(tmA, tmB, p, grid, stream);
-    case 256: return launch_wgrad<256, 4>(tmA, tmB, p, grid, stream);
-  }
-  return set_error(B2S_ERR_ARG, "b2s_conv1x1_wgrad: unsupported tile_n");
+  return dispatch_wgrad(block_n, tmA, tmB, p, stream);
 }
 
 // ConvTranspose2d(k2,s2) weight gradient partials: ws[split][(a*2+b)*Cin+ci][co]; x [N,Hi,Wi,Cin], dy [N,2Hi,2Wi,Cout].
@@ -739,12 +770,5 @@ extern "C" int b2s_convt2x2_wgrad(const void* x, int x_cstride, const void* dy, 
   int rc;
   if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hi, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
   if ((rc = make_up_map5(&tmB, dy, Cout, Wi, Hi, N, dy_cstride, p.pw, p.ph * p.pn))) return rc;
-  const int grid = p.m_tiles * p.tiles_nn * p.splits;
-  count_launch();
-  switch (block_n) {
-    case 64:  return launch_wgrad<64, 6>(tmA, tmB, p, grid, stream);
-    case 128: return launch_wgrad<128, 3>(tmA, tmB, p, grid, stream);
-    case 256: return launch_wgrad<256, 4>(tmA, tmB, p, grid, stream);
-  }
-  return set_error(B2S_ERR_ARG, "b2s_convt2x2_wgrad: unsupported tile_n");
+  return dispatch_wgrad(block_n, tmA, tmB, p, stream);
 }

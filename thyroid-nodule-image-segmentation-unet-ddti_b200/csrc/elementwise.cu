@@ -945,6 +945,27 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// Same update with the hyper-parameters read from device memory, so that a CUDA graph of the whole training step can
+// be replayed while lr and the bias corrections change per step. hyper = {lr, beta1, beta2, eps, wd, bc1, sqrt(bc2),
+// grad_scale}.
+__global__ void __launch_bounds__(kThreads)
+adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 long long n, const float* __restrict__ hyper) {
+  const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5],
+              bc2_sqrt = hyper[6], grad_scale = hyper[7];
+  const float step_size = lr / bc1;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_bfloat16* __restrict__ dst, int dst_cs,
                      long long npix, int C) {
@@ -1250,6 +1271,14 @@ extern "C" int b2s_adamw_step(float* p, const float* g, float* m, float* v, long
       p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
       grad_scale);
   return check_launch("adamw_kernel");
+}
+
+extern "C" int b2s_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper,
+                                  void* stream) {
+  if (!p || !g || !m || !v || !hyper) return set_error(B2S_ERR_ARG, "b2s_adamw_step_dev: null pointer");
+  count_launch();
+  adamw_dev_kernel<<<grid_for(n, kThreads * 8), kThreads, 0, STREAM(stream)>>>(p, g, m, v, n, hyper);
+  return check_launch("adamw_dev_kernel");
 }
 
 extern "C" int b2s_copy_channels(const void* src, int src_cstride, void* dst, int dst_cstride, long long npix, int C,

@@ -315,6 +315,12 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale
                                   grad_scale, _stream()), "b2s_adamw_step"))
 
 
+def adamw_step_dev(p, g, m, v, hyper):
+    """hyper: device fp32 [8] = lr, beta1, beta2, eps, wd, 1-beta1^t, sqrt(1-beta2^t), grad_scale"""
+    _timed("adamw", "hbm", 28.0 * p.numel(), lambda: check(
+        _lib.lib().b2s_adamw_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), _stream()), "b2s_adamw_step_dev"))
+
+
 def copy_channels(src, dst):
     npix = src.N * src.H * src.W
     check(_lib.lib().b2s_copy_channels(src.ptr, src.cstride, dst.ptr, dst.cstride, npix, src.C, _stream()),

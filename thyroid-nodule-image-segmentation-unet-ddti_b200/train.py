@@ -125,3 +125,65 @@ class TrainStep:
         out = self.forward_backward(x, t)
         self.optimizer_step(lr)
         return out
+
+    # ---- the same step as ONE CUDA graph -----------------------------------------------------------------------
+    # ~230 kernel launches per step cost more host time than the GPU needs to run them at batch 64; the graph removes
+    # the host from the loop. Everything that changes between steps lives in device memory: the batch (copied into
+    # static input buffers), BatchNorm counters (updated in-kernel), and the AdamW scalars (lr, bias corrections),
+    # an 8-float device vector refreshed by a stream-ordered copy from pageable host memory before each replay
+    # (staged by the driver at call time, so the host may run ahead safely).
+    def _write_hyper(self, lr):
+        self.step_count += 1
+        # betas rounded to fp32 first: the same double-precision bias corrections b2s_adamw_step derives from its
+        # float arguments, so the graphed and the host-launched step stay bit-identical
+        b1, b2 = (torch.tensor(b, dtype=torch.float32).item() for b in self.betas)
+        h = torch.tensor([lr if lr is not None else self.lr, b1, b2, self.eps, self.wd, 1.0 - b1 ** self.step_count,
+                          math.sqrt(1.0 - b2 ** self.step_count), 1.0 / self.world], dtype=torch.float32)
+        self._hyper_dev.copy_(h)
+
+    def _graph_body(self):
+        self.forward_backward(self._gx, self._gt)
+        ops.adamw_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self._hyper_dev)
+        self.engine.invalidate_packed()
+
+    def capture(self, x, t):
+        """Captures forward + loss + backward (+ bucketed all-reduce) + AdamW for inputs shaped like x, t.
+        Runs two eager steps first (lazy initialisation inside the library, NCCL warm-up); they are real optimisation
+        steps. Returns True when the graph is in use, False when capture failed (eager path stays in effect)."""
+        from . import _lib
+        self._gx, self._gt = torch.empty_like(x), torch.empty_like(t)
+        self._hyper_dev = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._graph = None
+        for _ in range(2):
+            self.step(x, t)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        step_before = self.step_count
+        try:
+            self._gx.copy_(x); self._gt.copy_(t)
+            self._write_hyper(None)
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                self._graph_body()
+            self.graph_launches = _lib.launch_count() - l0
+            self._graph = g
+        except Exception as e:   # capture is an optimisation: report and keep the eager path
+            self.capture_error = f"{type(e).__name__}: {e}"
+            self.step_count = step_before
+            self._graph = None
+            torch.cuda.synchronize()
+            return False
+        # the capture itself did not execute the step (and step_count was advanced for it): undo the count
+        self.step_count = step_before
+        return True
+
+    def step_graphed(self, x, t, lr=None):
+        """Replays the captured step on a new batch; returns the 8-float loss vector (device tensor, static buffer)."""
+        if getattr(self, "_graph", None) is None:
+            return self.step(x, t, lr)
+        self._gx.copy_(x, non_blocking=True)
+        self._gt.copy_(t, non_blocking=True)
+        self._write_hyper(lr)
+        self._graph.replay()
+        key = (x.shape[0], x.shape[2], x.shape[3], str(x.device))
+        return self.engine.plans[key].loss_out
