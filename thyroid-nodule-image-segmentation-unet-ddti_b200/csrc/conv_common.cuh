@@ -175,14 +175,18 @@ static inline int conv_plan(int N, int H, int W, int n_total, int cout_sub, int 
     pl->tiles_w = W / 128; pl->tiles_h = H; pl->tiles_n = N; pl->tiles_m = pl->tiles_w * H * N;
     pl->items_m = N * (H / 2) * (W / 128);
   } else if (kind == CONV_PAIR) {
-    if (tile_n == 0) tile_n = cout_sub >= 256 ? 256 : cout_sub >= 128 ? 128 : 64;
+    if (tile_n == 0) tile_n = cout_sub >= 256 ? 256 : cout_sub >= 128 ? 128 : 64;   // (convT tiles spanning sub-positions: no gain measured)
     pl->items_m = (pl->tiles_m + 1) / 2;
   } else {
     tile_n = auto_block_n(n_total, cout_sub, tile_n);
     pl->items_m = pl->tiles_m;
   }
-  if (tile_n > cout_sub) tile_n = cout_sub;
-  if ((tile_n != 64 && tile_n != 128 && tile_n != 256) || cout_sub % tile_n) return -1;
+  // A tile wider than cout_sub is allowed when it covers whole (a,b) sub-blocks of a transposed-conv forward
+  // (n_total = 4 * cout_sub): the epilogue maps every 64-column chunk to its sub-position and bias on its own.
+  const bool multi_sub = out_mode == OUT_CONVT_5D && kind == CONV_PAIR && tile_n > cout_sub && tile_n % cout_sub == 0 &&
+                         n_total % tile_n == 0;
+  if (tile_n > cout_sub && !multi_sub) tile_n = cout_sub;
+  if ((tile_n != 64 && tile_n != 128 && tile_n != 256) || (!multi_sub && cout_sub % tile_n)) return -1;
   pl->kind = kind;
   pl->block_n = tile_n;
   pl->tiles_nn = n_total / tile_n;

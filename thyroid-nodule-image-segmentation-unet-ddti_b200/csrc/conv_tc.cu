@@ -671,7 +671,7 @@ static int wgrad_plan(int N, int H, int W, int Cin, int Cout, int num_taps, int 
   p->num_taps = num_taps; p->ci_blocks = Cin / 64; p->total_rb = num_taps * p->ci_blocks;
   // two M tiles per dz stage when the row-block count allows it (transposed conv: every row block of a CTA must
   // belong to one tap, i.e. Cin % 256 == 0)
-  p->mt = (block_n >= 128 && p->total_rb >= 4 && (num_taps != 4 || p->ci_blocks % 4 == 0)) ? 2 : 1;
+  p->mt = (block_n == 256 && p->total_rb >= 4 && (num_taps != 4 || p->ci_blocks % 4 == 0)) ? 2 : 1;   // 128: two CTAs/SM measured faster
   p->cin = Cin; p->cout = Cout; p->tiles_nn = Cout / block_n; p->m_tiles = (p->total_rb + 2 * p->mt - 1) / (2 * p->mt);
   p->chunks_total = p->chunks_w * p->chunks_h * p->chunks_n;
   int splits = splits_req;

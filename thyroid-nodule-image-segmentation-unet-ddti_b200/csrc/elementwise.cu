@@ -585,25 +585,32 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __re
   const int cg = threadIdx.x % groups;
   const long long npix = static_cast<long long>(N) * HW;
   const long long ppi = kThreads / groups;
-  for (long long p0 = static_cast<long long>(blockIdx.x) * ppi; p0 < npix; p0 += static_cast<long long>(gridDim.x) * ppi) {
-    const long long p = p0 + threadIdx.x / groups;
-    float v[8];
-    if (p < npix) unpack8(ldg16(r + p * r_cs + cg * 8), v);
-    else {
+  constexpr int U = 4;       // pixels per lane group and loop trip: four independent 16-byte loads in flight
+  for (long long p0 = static_cast<long long>(blockIdx.x) * ppi * U; p0 < npix;
+       p0 += static_cast<long long>(gridDim.x) * ppi * U) {
+    uint4 raw[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * ppi + threadIdx.x / groups;
+      raw[u] = p < npix ? ldg16(r + p * r_cs + cg * 8) : make_uint4(0, 0, 0, 0);
     }
-    for (int o = 0; o < O; ++o) {
-      float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc = fmaf(v[k], wf[o * C + cg * 8 + k], acc);
-      for (int off = groups >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      if (cg == 0 && p < npix) {
-        const float logit = acc + wf[O * C + o];
-        const long long n = static_cast<unsigned>(p) / static_cast<unsigned>(HW), hw = p - n * HW;
-        const long long oi = (n * O + o) * HW + hw;
-        logits[oi] = logit;
-        if (mask) mask[oi] = (1.f / (1.f + expf(-logit))) > 0.5f ? 1 : 0;
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * ppi + threadIdx.x / groups;
+      float v[8];
+      unpack8(raw[u], v);
+      for (int o = 0; o < O; ++o) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(v[k], wf[o * C + cg * 8 + k], acc);
+        for (int off = groups >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (cg == 0 && p < npix) {
+          const float logit = acc + wf[O * C + o];
+          const long long n = static_cast<unsigned>(p) / static_cast<unsigned>(HW), hw = p - n * HW;
+          const long long oi = (n * O + o) * HW + hw;
+          logits[oi] = logit;
+          if (mask) mask[oi] = (1.f / (1.f + expf(-logit))) > 0.5f ? 1 : 0;
+        }
       }
     }
   }
@@ -1168,7 +1175,7 @@ extern "C" int b2s_head_fwd(const void* r, int r_cstride, const float* scale, co
   const long long npix = static_cast<long long>(N) * HW;
   const int ppi = kThreads / (C / 8);
   count_launch();
-  head_fwd_kernel<<<grid_for(npix, ppi * 8), kThreads, (O * C + O) * sizeof(float), STREAM(stream)>>>(
+  head_fwd_kernel<<<grid_for(npix, ppi * 16), kThreads, (O * C + O) * sizeof(float), STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(r), r_cstride, scale, shift, w, b, logits, mask, N, HW, C, O);
   return check_launch("head_fwd_kernel");
 }
