@@ -135,6 +135,14 @@ int b2s_seg_loss_bwd(const float* logits, const float* targets, const float* sum
                      float dice_smooth, float w_bce, float w_dice, float w_ft, float ft_alpha, float ft_beta,
                      float ft_gamma, float ft_smooth, void* stream);
 
+/* Segmentation metric counters without a per-step device->host copy (utils/trainer.py:101-107,236-250 with
+ * utils/utils.py:225-251): pred = sigmoid(logit) > 0.5 (fp32). ADDS to counters (int64 [7], device) =
+ * {TP, FP, FN, TN against target.astype(int), intersection, union against target.astype(bool), elements}.
+ * partial: uint32 [b2s_metrics_blocks(n)][6] scratch. */
+int b2s_metrics_blocks(long long n);
+int b2s_seg_metrics(const float* logits, const float* targets, long long n, unsigned int* partial, long long* counters,
+                    void* stream);
+
 /* torch.optim.AdamW step (utils/trainer.py:41,92) over a flat fp32 parameter/gradient bucket;
  * grad_scale multiplies g first (1/world_size after a sum all-reduce). step is 1-based. */
 int b2s_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

@@ -156,3 +156,14 @@ def test_functional_torch_port_matches_reference(unet_golden, ref_params):
     for k, g in zip(names, grads):
         ref = A["grads"][k]
         assert abs(float(g.double().norm()) - ref["norm"]) <= 1e-4 * ref["norm"] + 1e-9, k
+
+
+def test_metrics_oracle_matches_reference_functions():
+    """oracle/metrics_oracle.py against goldens computed with the reference's own utils/utils.py:225-251"""
+    import os
+    from oracle import metrics_oracle as MO
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_golden.pt"), weights_only=False)
+    for name, c in gold.items():
+        got = MO.metrics((torch.sigmoid(c["logits"]) > 0.5).numpy(), c["targets"].numpy())
+        for k in ("acc", "precision", "recall", "f1", "iou"):
+            assert abs(got[k] - c[k]) < 1e-12, (name, k)

@@ -320,3 +320,53 @@ def test_cuda_graph_step_equals_eager_step(ref_params):
     for k in se:
         assert torch.allclose(se[k].float(), sg[k].float(), rtol=1e-6, atol=1e-7), k
     assert graph.graph_launches > 150
+
+
+def test_on_device_metrics_match_reference():
+    """SegMetrics (int64 counters on the GPU, no per-step D2H) against the reference's utils/utils.py functions
+    (goldens from oracle/make_golden_metrics.py) and the numpy oracle, binary and soft targets, accumulated over steps."""
+    import numpy as np
+    from b200seg.models.metrics import SegMetrics
+    from oracle import metrics_oracle as MO
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_golden.pt"), weights_only=False)
+    for name, c in gold.items():
+        m = SegMetrics(DEV)
+        for i in range(3):     # one sample per update: the counters accumulate like the reference's epoch-level concat
+            m.update(c["logits"][i:i + 1].to(DEV), c["targets"][i:i + 1].to(DEV))
+        got = m.compute()
+        ref = MO.metrics((torch.sigmoid(c["logits"]) > 0.5).numpy(), c["targets"].numpy())
+        for k in ("acc", "precision", "recall", "f1", "iou"):
+            assert abs(got[k] - c[k]) < 1e-12, (name, k, got[k], c[k])
+            assert abs(ref[k] - c[k]) < 1e-12, (name, k, "oracle")
+        assert got["n"] == c["logits"].numel()
+        m.reset()
+        assert int(m.counters.sum()) == 0
+
+
+def test_focal_tversky_gradient_with_global_sums():
+    """Data-parallel FocalTversky: two half batches, each with the batch-global {TP, sum p, sum t} (what TrainStep
+    all-reduces), reproduce the full-batch gradient."""
+    from b200seg import ops
+    g = torch.Generator().manual_seed(21)
+    logits = (torch.randn((4, 1, 32, 32), generator=g) * 2).to(DEV)
+    targets = (torch.rand((4, 1, 32, 32), generator=g) > 0.6).float().to(DEV)
+    cfg = dict(w_bce=0.0, w_dice=0.0, w_ft=1.0)
+
+    def run(lg, tg, ft_tot=None):
+        B, per = lg.shape[0], lg[0].numel()
+        partial = torch.empty(B * ops.loss_chunks(per) * 4, dtype=torch.float32, device=DEV)
+        sums, out, dl = torch.empty(B * 4, device=DEV), torch.empty(8, device=DEV), torch.empty_like(lg)
+        ops.seg_loss_fwd(lg, tg, partial, sums, out, **cfg)
+        ops.seg_loss_bwd(lg, tg, sums, out[4:7] if ft_tot is None else ft_tot, None, dl, **cfg)
+        return out.clone(), dl
+
+    out_full, dl_full = run(logits, targets)
+    o0, _ = run(logits[:2].contiguous(), targets[:2].contiguous())
+    o1, _ = run(logits[2:].contiguous(), targets[2:].contiguous())
+    tot = o0[4:7] + o1[4:7]
+    assert torch.allclose(tot, out_full[4:7], rtol=1e-6)
+    _, d0 = run(logits[:2].contiguous(), targets[:2].contiguous(), tot)
+    _, d1 = run(logits[2:].contiguous(), targets[2:].contiguous(), tot)
+    assert torch.allclose(torch.cat([d0, d1]), dl_full, rtol=1e-5, atol=1e-9)
+    r = O.seg_loss(logits.double().cpu(), targets.double().cpu(), w_bce=0, w_dice=0, w_ft=1)
+    assert float((dl_full.double().cpu() - r["dlogits"]).abs().max()) < 1e-6 * float(r["dlogits"].abs().max()) + 1e-9

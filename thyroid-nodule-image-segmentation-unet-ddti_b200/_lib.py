@@ -47,6 +47,8 @@ SIGNATURES = {
     "b2s_loss_chunks": (I, [LL]),
     "b2s_seg_loss_fwd": (I, [P, P, I, LL, P, P, P, F, F, F, F, F, F, F, F, P]),
     "b2s_seg_loss_bwd": (I, [P, P, P, P, I, LL, LL, I, P, P, F, F, F, F, F, F, F, F, P]),
+    "b2s_metrics_blocks": (I, [LL]),
+    "b2s_seg_metrics": (I, [P, P, LL, P, P, P]),
     "b2s_adamw_step": (I, [P, P, P, P, LL, F, F, F, F, F, I, F, P]),
     "b2s_adamw_step_dev": (I, [P, P, P, P, LL, P, P]),
     "b2s_copy_channels": (I, [P, I, P, I, LL, I, P]),

@@ -831,6 +831,59 @@ seg_loss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ 
   }
 }
 
+// Segmentation metrics counters (utils/utils.py:225-251, utils/trainer.py:101-107,236-250): pred = sigmoid(x) > 0.5 in
+// fp32; the reference compares it with target.astype(int) (truncation) for accuracy / precision / recall and with
+// target.astype(bool) (non-zero) for IoU. partial [blocks][6] = {TP, FP, FN, TN (int targets), intersection, union
+// (bool targets)} per block; metrics_accumulate adds them to the running int64 counters [6] (+ element count in [6]).
+__global__ void __launch_bounds__(kThreads)
+seg_metrics_partial_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long long n,
+                           unsigned int* __restrict__ partial) {
+  __shared__ unsigned int red[6][kThreads / 32];
+  unsigned int c[6] = {0, 0, 0, 0, 0, 0};
+  const long long i0 = static_cast<long long>(blockIdx.x) * kLossChunk;
+  const long long i1 = min(i0 + kLossChunk, n);
+  for (long long i = i0 + threadIdx.x; i < i1; i += kThreads) {
+    const float x = logits[i], t = targets[i];
+    const bool pred = (1.f / (1.f + expf(-x))) > 0.5f;
+    const int ti = static_cast<int>(t);          // numpy astype(int): truncation toward zero
+    const bool tb = t != 0.f;                    // numpy astype(bool)
+    c[0] += (pred && ti == 1); c[1] += (pred && ti == 0); c[2] += (!pred && ti == 1); c[3] += (!pred && ti == 0);
+    c[4] += (pred && tb); c[5] += (pred || tb);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    unsigned int v = c[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    unsigned int s = 0;
+#pragma unroll
+    for (int j = 0; j < kThreads / 32; ++j) s += red[threadIdx.x][j];
+    partial[static_cast<size_t>(blockIdx.x) * 6 + threadIdx.x] = s;
+  }
+}
+
+__global__ void seg_metrics_accumulate_kernel(const unsigned int* __restrict__ partial, int blocks, long long n,
+                                              long long* __restrict__ counters) {
+  __shared__ long long red[6][kThreads];
+  long long c[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < blocks; b += kThreads)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c[k] += partial[static_cast<size_t>(b) * 6 + k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) red[k][threadIdx.x] = c[k];
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    long long s = 0;
+    for (int j = 0; j < kThreads; ++j) s += red[threadIdx.x][j];
+    counters[threadIdx.x] += s;
+  }
+  if (threadIdx.x == 6) counters[6] += n;
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight packing / wgrad reduce / AdamW / copy
 // ------------------------------------------------------------------------------------------------
@@ -1231,6 +1284,22 @@ extern "C" int b2s_seg_loss_bwd(const float* logits, const float* targets, const
                                                                    dice_smooth, w_bce, w_dice, w_ft, ft_alpha, ft_beta,
                                                                    ft_gamma, ft_smooth);
   return check_launch("seg_loss_bwd_kernel");
+}
+
+extern "C" int b2s_metrics_blocks(long long n) { return static_cast<int>((n + kLossChunk - 1) / kLossChunk); }
+
+extern "C" int b2s_seg_metrics(const float* logits, const float* targets, long long n, unsigned int* partial,
+                               long long* counters, void* stream) {
+  if (!logits || !targets || !partial || !counters) return set_error(B2S_ERR_ARG, "b2s_seg_metrics: null pointer");
+  if (n <= 0) return set_error(B2S_ERR_ARG, "b2s_seg_metrics: empty input");
+  const int blocks = b2s_metrics_blocks(n);
+  count_launch();
+  seg_metrics_partial_kernel<<<blocks, kThreads, 0, STREAM(stream)>>>(logits, targets, n, partial);
+  int rc = check_launch("seg_metrics_partial_kernel");
+  if (rc) return rc;
+  count_launch();
+  seg_metrics_accumulate_kernel<<<1, kThreads, 0, STREAM(stream)>>>(partial, blocks, n, counters);
+  return check_launch("seg_metrics_accumulate_kernel");
 }
 
 extern "C" int b2s_pack_conv_weight(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int ksize,

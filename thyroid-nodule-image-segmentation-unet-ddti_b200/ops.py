@@ -309,6 +309,15 @@ def seg_loss_bwd(logits, targets, sums, ft_tot, grad_out, dlogits, dice_smooth=1
                                     ft_gamma, ft_smooth, _stream()), "b2s_seg_loss_bwd"))
 
 
+def seg_metrics(logits, targets, counters):
+    """adds the confusion counts of sigmoid(logits) > 0.5 against targets to counters (int64 [7], device)"""
+    lg, tg = logits.detach().float().contiguous(), targets.detach().float().contiguous()
+    n = lg.numel()
+    partial = torch.empty(_lib.lib().b2s_metrics_blocks(n) * 6, dtype=torch.int32, device=lg.device)
+    _timed("seg_metrics", "hbm", 8.0 * n, lambda: check(
+        _lib.lib().b2s_seg_metrics(_p(lg), _p(tg), n, _p(partial), _p(counters), _stream()), "b2s_seg_metrics"))
+
+
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     _timed("adamw", "hbm", 28.0 * p.numel(), lambda: check(
         _lib.lib().b2s_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,

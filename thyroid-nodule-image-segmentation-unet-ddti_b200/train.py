@@ -44,11 +44,11 @@ class TrainStep:
     """Owns flat fp32 parameter / gradient / Adam-moment buckets laid out in gradient-ready order."""
 
     def __init__(self, state_dict, device, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 bucket_mb=16.0, w_bce=1.0, w_dice=1.0, process_group=None, use_dist=None, engine=None):
+                 bucket_mb=16.0, w_bce=1.0, w_dice=1.0, w_ft=0.0, process_group=None, use_dist=None, engine=None):
         self.device = torch.device(device)
         self.engine = engine if engine is not None else UNetEngine(out_channels=state_dict["final.1.bias"].numel())
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
-        self.w_bce, self.w_dice = w_bce, w_dice
+        self.w_bce, self.w_dice, self.w_ft = w_bce, w_dice, w_ft
         self.step_count = 0
         self.pg = process_group
         self.use_dist = dist.is_available() and dist.is_initialized() if use_dist is None else use_dist
@@ -108,8 +108,16 @@ class TrainStep:
         reduce=False leaves the gradients un-reduced (the caller all-reduces flat_g itself)."""
         eng = self.engine
         _, pl = eng.forward(self.P, x, train=True)
-        out = eng.loss(pl, t, w_bce=self.w_bce, w_dice=self.w_dice)
-        dl = eng.loss_backward(pl, t, w_bce=self.w_bce, w_dice=self.w_dice)
+        out = eng.loss(pl, t, w_bce=self.w_bce, w_dice=self.w_dice, w_ft=self.w_ft)
+        ft_tot, w_ft = None, self.w_ft
+        if self.w_ft != 0.0 and self.world > 1:
+            # FocalTversky (models/loss.py:34-46) is a function of BATCH-GLOBAL sums: all-reduce {TP, sum p, sum t}
+            # before the gradient. Its gradient is a sum over ranks, not a mean, so it is pre-multiplied by the world
+            # size that the optimiser's 1/world gradient scale divides out again. out[3] stays the rank-local value.
+            ft_tot = out[4:7].clone()
+            dist.all_reduce(ft_tot, op=dist.ReduceOp.SUM, group=self.pg)
+            w_ft = self.w_ft * self.world
+        dl = eng.loss_backward(pl, t, ft_tot=ft_tot, w_bce=self.w_bce, w_dice=self.w_dice, w_ft=w_ft)
         self._works = []
         eng.backward(self.P, pl, dl, self.G, on_grad_ready=self._on_grad_ready if reduce else None)
         for w in self._works:
