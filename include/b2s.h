@@ -45,6 +45,11 @@ int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, const float
                  float* stats_partial, int N, int H, int W, int Cin, int Cout, int ksize, int flags, int tile_n,
                  void* stream);
 int b2s_conv_stats_rows(int N, int H, int W, int Cout, int tile_n);
+/* inference variant: y = act(conv(x) + bias) * post_scale + post_shift, i.e. the eval-mode BatchNorm2d
+ * (models/model.py:38,41 with running statistics, b2s_bn_eval_affine) applied in the conv epilogue. */
+int b2s_conv_fwd_affine(const void* x, int x_cstride, const void* w_packed, const float* bias, const float* post_scale,
+                        const float* post_shift, void* y, int y_cstride, int N, int H, int W, int Cin, int Cout,
+                        int ksize, int flags, int tile_n, void* stream);
 
 /* nn.ConvTranspose2d(Cin,Cout,2,stride=2) forward (models/model.py:19,49): x [N,Hi,Wi,Cin] -> y [N,2Hi,2Wi,Cout];
  * w_packed [(a*2+b)*Cout+co][Cin] bf16 (b2s_pack_convt_weight). */
@@ -98,6 +103,8 @@ int b2s_bn_eval_affine(const float* gamma, const float* beta, const float* runni
  * (models/model.py:17,56-58) into the dense tensor pooled [N,H/2,W/2,C]. */
 int b2s_bn_apply(const void* r, int r_cstride, const float* scale, const float* shift, void* y, int y_cstride,
                  void* pooled, int N, int H, int W, int C, void* stream);
+/* F.max_pool2d(x, 2) on its own (inference path): x [N,H,W,C] -> pooled [N,H/2,W/2,C] dense. */
+int b2s_maxpool2x2(const void* x, int x_cstride, void* pooled, int N, int H, int W, int C, void* stream);
 int b2s_ew_rows(void); /* partial rows written by the element-wise reduction kernels below */
 /* BatchNorm+ReLU backward, pass 1: partial [b2s_ew_rows][2][C] = sum dy, sum dy*xhat, where
  * dy = dy_in (+ max-pool routed dpool when dpool != NULL; first maximum in row-major window order). */

@@ -23,6 +23,8 @@ SIGNATURES = {
     "b2s_version": (I, []),
     "b2s_conv_fwd": (I, [P, I, P, P, P, I, P, I, I, I, I, I, I, I, I, P]),
     "b2s_conv_stats_rows": (I, [I, I, I, I, I]),
+    "b2s_conv_fwd_affine": (I, [P, I, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
+    "b2s_maxpool2x2": (I, [P, I, P, I, I, I, I, P]),
     "b2s_convt2x2_fwd": (I, [P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "b2s_convt2x2_dgrad": (I, [P, I, P, P, I, I, I, I, I, I, I, P]),
     "b2s_conv_wgrad_workspace": (LL, [I, I, I, I, I, I, I, I, POINTER(c_int)]),

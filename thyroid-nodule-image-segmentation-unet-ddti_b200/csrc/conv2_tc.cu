@@ -309,6 +309,12 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             b += bb.y;
           }
           if (do_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          if (p.post_scale != nullptr) {
+            const float2 ps = __ldg(reinterpret_cast<const float2*>(p.post_scale + bias_base) + j);
+            const float2 pt = __ldg(reinterpret_cast<const float2*>(p.post_shift + bias_base) + j);
+            a = fmaf(a, ps.x, pt.x);
+            b = fmaf(b, ps.y, pt.y);
+          }
           if (!valid) { a = 0.f; b = 0.f; }
           packed[j] = pack_bf16x2(a, b);
         }

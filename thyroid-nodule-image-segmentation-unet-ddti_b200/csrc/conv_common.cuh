@@ -25,6 +25,8 @@ struct ConvTcParams {
   int tiles_nn;                    // n_total / BLOCK_N
   int flags;                       // B2S_FLAG_*
   const float* bias;               // [cout_sub] or nullptr
+  const float* post_scale;         // eval-mode BatchNorm folded into the epilogue: y = act(acc + bias) * post_scale +
+  const float* post_shift;         // post_shift per output channel (both nullptr in training)
   int items_m;                     // work items of the tile-pair / halo kernels (see conv_plan)
   float* stats;                    // [2 * gridDim.x / tiles_nn][2][n_total] partial column sums, or nullptr
 };

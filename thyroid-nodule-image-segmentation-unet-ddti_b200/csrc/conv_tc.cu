@@ -203,6 +203,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             b += __ldg(p.bias + bias_base + 2 * j + 1);
           }
           if (do_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          if (p.post_scale != nullptr) {
+            a = fmaf(a, __ldg(p.post_scale + bias_base + 2 * j), __ldg(p.post_shift + bias_base + 2 * j));
+            b = fmaf(b, __ldg(p.post_scale + bias_base + 2 * j + 1), __ldg(p.post_shift + bias_base + 2 * j + 1));
+          }
           if (!valid) { a = 0.f; b = 0.f; }
           packed[j] = pack_bf16x2(a, b);
         }
@@ -511,10 +515,12 @@ static int make_weight_map(CUtensorMap* m, const void* w_packed, int K, int rows
 using namespace b2s;
 
 // Generic tap-GEMM conv. ksize 3 (pad 1) or 1. See include/b2s.h.
-extern "C" int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y,
-                            int y_cstride, float* stats_partial, int N, int H, int W, int Cin, int Cout, int ksize,
-                            int flags, int tile_n, void* stream_) {
+static int conv_fwd_impl(const void* x, int x_cstride, const void* w_packed, const float* bias, const float* post_scale,
+                         const float* post_shift, void* y, int y_cstride, float* stats_partial, int N, int H, int W,
+                         int Cin, int Cout, int ksize, int flags, int tile_n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if ((post_scale == nullptr) != (post_shift == nullptr))
+    return set_error(B2S_ERR_ARG, "b2s_conv_fwd: post_scale and post_shift must both be given");
   if (!x || !w_packed || !y) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: null pointer");
   if (ksize != 3 && ksize != 1) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: ksize must be 1 or 3");
   if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_conv_fwd: Cin and Cout must be multiples of 64");
@@ -529,6 +535,7 @@ extern "C" int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, 
   p.num_taps = ksize * ksize; p.k_chunks = Cin / 64;
   p.n_total = Cout; p.cout_sub = Cout;
   p.flags = flags; p.bias = bias; p.stats = stats_partial;
+  p.post_scale = post_scale; p.post_shift = post_shift;
 
   CUtensorMap tmA, tmB, tmOut;
   int rc;
@@ -541,6 +548,22 @@ extern "C" int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, 
   if ((rc = make_weight_map(&tmB, w_packed, Cin, p.num_taps * Cout, pl.block_n))) return rc;
   if ((rc = make_act_map4(&tmOut, y, Cout, W, H, N, y_cstride, pl.bw, pl.bh, pl.bn))) return rc;
   return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
+}
+
+extern "C" int b2s_conv_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y,
+                            int y_cstride, float* stats_partial, int N, int H, int W, int Cin, int Cout, int ksize,
+                            int flags, int tile_n, void* stream) {
+  return conv_fwd_impl(x, x_cstride, w_packed, bias, nullptr, nullptr, y, y_cstride, stats_partial, N, H, W, Cin, Cout,
+                       ksize, flags, tile_n, stream);
+}
+
+// Inference: conv (+bias, ReLU) with the eval-mode BatchNorm affine applied in the epilogue (no separate BN pass).
+extern "C" int b2s_conv_fwd_affine(const void* x, int x_cstride, const void* w_packed, const float* bias,
+                                   const float* post_scale, const float* post_shift, void* y, int y_cstride, int N,
+                                   int H, int W, int Cin, int Cout, int ksize, int flags, int tile_n, void* stream) {
+  if (!post_scale || !post_shift) return set_error(B2S_ERR_ARG, "b2s_conv_fwd_affine: null pointer");
+  return conv_fwd_impl(x, x_cstride, w_packed, bias, post_scale, post_shift, y, y_cstride, nullptr, N, H, W, Cin, Cout,
+                       ksize, flags & ~B2S_FLAG_STATS, tile_n, stream);
 }
 
 // nn.Conv2d(Cin,Cout,3,stride=2,padding=1) forward (models/vnet.py:97): x [N,H,W,Cin] -> y [N,H/2,W/2,Cout].

@@ -421,6 +421,34 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __re
   }
 }
 
+// plain F.max_pool2d(x, 2) (inference path, where BN is already applied by the producing conv's epilogue)
+__global__ void __launch_bounds__(kThreads)
+maxpool2x2_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, __nv_bfloat16* __restrict__ pooled, int N, int H, int W,
+                  int C) {
+  const int groups = C / 8;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(N) * Ho * Wo * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int cg = static_cast<int>(i % groups);
+    const long long pp = i / groups;
+    const int wo = static_cast<int>(pp % Wo);
+    const long long t = pp / Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    const long long p00 = (n * H + 2 * ho) * W + 2 * wo;
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[8];
+      unpack8(ldg16(x + (p00 + (q >> 1) * W + (q & 1)) * x_cs + cg * 8), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = q == 0 ? v[k] : fmaxf(m[k], v[k]);
+    }
+    stg16(pooled + pp * C + cg * 8, pack8(m));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // BN (+ReLU, + max-pool routing) backward
 // ------------------------------------------------------------------------------------------------
@@ -1154,6 +1182,16 @@ extern "C" int b2s_bn_apply(const void* r, int r_cstride, const float* scale, co
         rp, r_cstride, scale, shift, yp, y_cstride, nullptr, N, H, W, C);
   }
   return check_launch("bn_apply_kernel");
+}
+
+extern "C" int b2s_maxpool2x2(const void* x, int x_cstride, void* pooled, int N, int H, int W, int C, void* stream) {
+  if (!x || !pooled) return set_error(B2S_ERR_ARG, "b2s_maxpool2x2: null pointer");
+  if (C % 8 || x_cstride % 8 || H % 2 || W % 2) return set_error(B2S_ERR_ARG, "b2s_maxpool2x2: need C % 8 == 0, even H and W");
+  const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
+  count_launch();
+  maxpool2x2_kernel<<<grid_for(items, kThreads * 2), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<__nv_bfloat16*>(pooled), N, H, W, C);
+  return check_launch("maxpool2x2_kernel");
 }
 
 extern "C" int b2s_bn_bwd_reduce(const void* dy, int dy_cstride, const void* dpool, const void* r, int r_cstride,

@@ -184,6 +184,15 @@ class UNetEngine:
             s = pl.stages[(name, idx)]
             s.x = xin
             bn = f"{name}.{idx + 2}"
+            if not train and xin is not None and s.y is not None:
+                # inference: running-statistics BatchNorm applied in the conv epilogue, no separate BN pass
+                ops.bn_eval_affine(P[f"{bn}.weight"], P[f"{bn}.bias"], P[f"{bn}.running_mean"],
+                                   P[f"{bn}.running_var"], BN_EPS, s.scale, s.shift)
+                wf, _ = self._packed[f"{name}.{idx}.weight"]
+                ops.conv_fwd_affine(xin, wf, P[f"{name}.{idx}.bias"], s.scale, s.shift, s.y, ksize=3, relu=True)
+                if pooled is not None:
+                    ops.maxpool2x2(s.y, pooled)
+                return s
             if xin is None:  # first conv on the fp32 image
                 ops.conv3x3_c1_fwd(x, P[f"{name}.{idx}.weight"], P[f"{name}.{idx}.bias"], s.r, relu=True,
                                    stats=pl.stats_partial if train else None)

@@ -131,6 +131,22 @@ def conv_fwd(x, w_packed, bias, y, ksize=3, relu=False, stats=None, tile_n=0):
                                 x.W, x.C, Cout, ksize, flags, tile_n, _stream()), "b2s_conv_fwd"))
 
 
+def conv_fwd_affine(x, w_packed, bias, post_scale, post_shift, y, ksize=3, relu=True, tile_n=0):
+    """inference: y = act(conv(x) + bias) * post_scale + post_shift (eval-mode BatchNorm in the epilogue)"""
+    flags = B2S_FLAG_RELU if relu else 0
+    Cout = y.C
+    flops = 2.0 * x.N * x.H * x.W * x.C * Cout * ksize * ksize
+    _timed(f"conv{ksize}x{ksize}+bn[{x.C}->{Cout}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
+        _lib.lib().b2s_conv_fwd_affine(x.ptr, x.cstride, _p(w_packed), _p(bias), _p(post_scale), _p(post_shift), y.ptr,
+                                       y.cstride, x.N, x.H, x.W, x.C, Cout, ksize, flags, tile_n, _stream()),
+        "b2s_conv_fwd_affine"))
+
+
+def maxpool2x2(x, pooled):
+    _timed("maxpool2x2", "hbm", x.N * x.H * x.W * x.C * 2.5, lambda: check(
+        _lib.lib().b2s_maxpool2x2(x.ptr, x.cstride, pooled.ptr, x.N, x.H, x.W, x.C, _stream()), "b2s_maxpool2x2"))
+
+
 def conv_stats_rows(N, H, W, Cout, tile_n=0):
     """rows of the [rows, 2, Cout] partial-statistics buffer conv_fwd(..., stats=...) fills for this shape"""
     r = _lib.lib().b2s_conv_stats_rows(N, H, W, Cout, tile_n)
