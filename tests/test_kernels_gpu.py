@@ -255,7 +255,7 @@ def test_conv3x3_wgrad(ops, N, H, W, Cin, Cout, tile_n, splits):
 
 
 @pytest.mark.parametrize("N,Hi,Wi,Cin,Cout", [(2, 8, 8, 128, 64), (1, 16, 16, 256, 128), (2, 4, 4, 128, 64),
-                                              (1, 8, 16, 128, 64)])
+                                              (1, 8, 16, 128, 64), (3, 3, 5, 128, 64), (2, 6, 6, 256, 64)])
 def test_conv_transpose_fwd_dgrad_wgrad(ops, N, Hi, Wi, Cin, Cout):
     x = bf(rnd((N, Cin, Hi, Wi), 51))
     w = bf(rnd((Cin, Cout, 2, 2), 52, 0.05))

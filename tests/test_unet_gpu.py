@@ -118,7 +118,7 @@ def _cache_from_plan(plan, x_img):
     return cache
 
 
-@pytest.mark.parametrize("B,S", [(2, 32), (2, 64)])
+@pytest.mark.parametrize("B,S", [(2, 32), (2, 64), (2, (32, 128)), (3, (48, 80))])
 def test_backward_given_forward_state(net, ref_params, B, S):
     """The backward pass is linear in dlogits once the forward state (ReLU masks, pool argmax, BN statistics) is
     fixed. Feeding the oracle's explicit backward with the CUDA forward's own saved tensors removes the chaotic
@@ -126,18 +126,23 @@ def test_backward_given_forward_state(net, ref_params, B, S):
     net.load_state_dict(ref_params, strict=True)
     net.train()
     net.zero_grad(set_to_none=True)
-    x, t = O.synth_batch(B, S, S, seed=77)
+    # (32, 128): 128-pixel-wide rows put the row-halo conv and wgrad kernels on the path; (48, 80): non power-of-two
+    H, W = (S, S) if isinstance(S, int) else S
+    x, t = O.synth_batch(B, H, W, seed=77)
     xg = x.to(DEV)
     logits = net(xg)
+    lq = O.unet_forward({k: (v.double() if v.is_floating_point() else v.clone()) for k, v in ref_params.items()},
+                        x.double(), train=True, q=O.bf16_round)
+    assert float((logits.detach().cpu().double() - lq).abs().mean()) < 8e-3
     dl = O.seg_loss(logits.detach().cpu().double(), t.double())["dlogits"]
     logits.backward(dl.float().to(DEV))
     torch.cuda.synchronize()
-    plan = net._engine.plans[(B, S, S, str(xg.device))]
+    plan = net._engine.plans[(B, H, W, str(xg.device))]
     P = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in ref_params.items()}
     Gq = O.unet_backward(P, _cache_from_plan(plan, x), dl, q=O.bf16_round)
     res = {k: (rel_l2(p.grad, Gq[k]), cosine(p.grad, Gq[k])) for k, p in net.named_parameters()}
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/backward_given_state_{B}x{S}.json", "w") as f:
+    with open(f"gpurun_out/backward_given_state_{B}x{H}x{W}.json", "w") as f:
         json.dump(res, f, indent=1)
     bad = {k: v for k, v in res.items() if v[0] > 0.05 or v[1] < 0.998}
     assert not bad, bad

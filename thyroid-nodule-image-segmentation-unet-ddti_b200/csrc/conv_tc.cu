@@ -605,21 +605,24 @@ extern "C" int b2s_convt2x2_fwd(const void* x, int x_cstride, const void* w_pack
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !w_packed || !y) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: null pointer");
   if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: channels must be multiples of 64");
+  if (N <= 0 || Hi <= 0 || Wi <= 0) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: empty tensor");
   ConvTcParams p{};
   p.a_mode = A_1X1; p.out_mode = OUT_CONVT_5D;
+  // no spatial halo in input space: rows of all images are merged into one dimension (Hm = Hi * N), which is also how
+  // the 5-D view of the up-sampled output addresses them; works for any Hi, Wi
+  const int Hm = Hi * N;
   ConvPlan pl;
-  if (conv_plan(N, Hi, Wi, 4 * Cout, Cout, p.a_mode, p.out_mode, tile_n, &pl))
+  if (conv_plan(1, Hm, Wi, 4 * Cout, Cout, p.a_mode, p.out_mode, tile_n, &pl))
     return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: tile_n must be 64/128/256 and divide Cout");
-  if (pl.bn > 1 && pl.bh != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_fwd: unsupported tiny non-pow2 image");
-  p.W = Wi; p.H = Hi; p.N = N;
+  p.W = Wi; p.H = Hm; p.N = 1;
   p.num_taps = 1; p.k_chunks = Cin / 64;
   p.n_total = 4 * Cout; p.cout_sub = Cout;
   p.flags = 0; p.bias = bias; p.stats = nullptr;
   CUtensorMap tmA, tmB, tmOut;
   int rc;
-  if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hi, N, x_cstride, pl.bw, pl.bh, pl.bn))) return rc;
+  if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hm, 1, x_cstride, pl.bw, pl.bh, pl.bn))) return rc;
   if ((rc = make_weight_map(&tmB, w_packed, Cin, 4 * Cout, pl.block_n))) return rc;
-  if ((rc = make_up_map5(&tmOut, y, Cout, Wi, Hi, N, y_cstride, pl.bw, pl.bh * pl.bn))) return rc;
+  if ((rc = make_up_map5(&tmOut, y, Cout, Wi, Hm, 1, y_cstride, pl.bw, pl.bh * pl.bn))) return rc;
   return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
 }
 
@@ -629,21 +632,22 @@ extern "C" int b2s_convt2x2_dgrad(const void* dy, int dy_cstride, const void* w_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!dy || !w_packed || !dx) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: null pointer");
   if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: channels must be multiples of 64");
+  if (N <= 0 || Hi <= 0 || Wi <= 0) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: empty tensor");
   ConvTcParams p{};
   p.a_mode = A_CONVT_DGRAD; p.out_mode = OUT_4D;
+  const int Hm = Hi * N;   // image rows merged into one dimension (see b2s_convt2x2_fwd)
   ConvPlan pl;
-  if (conv_plan(N, Hi, Wi, Cin, Cin, p.a_mode, p.out_mode, tile_n, &pl))
+  if (conv_plan(1, Hm, Wi, Cin, Cin, p.a_mode, p.out_mode, tile_n, &pl))
     return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: tile_n must be 64/128/256 and divide Cin");
-  if (pl.bn > 1 && pl.bh != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: unsupported tiny non-pow2 image");
-  p.W = Wi; p.H = Hi; p.N = N;
+  p.W = Wi; p.H = Hm; p.N = 1;
   p.num_taps = 4; p.k_chunks = Cout / 64;
   p.n_total = Cin; p.cout_sub = Cin;
   p.flags = 0; p.bias = nullptr; p.stats = nullptr;
   CUtensorMap tmA, tmB, tmOut;
   int rc;
-  if ((rc = make_up_map5(&tmA, dy, Cout, Wi, Hi, N, dy_cstride, pl.bw, pl.bh * pl.bn))) return rc;
+  if ((rc = make_up_map5(&tmA, dy, Cout, Wi, Hm, 1, dy_cstride, pl.bw, pl.bh * pl.bn))) return rc;
   if ((rc = make_weight_map(&tmB, w_packed, Cout, 4 * Cin, pl.block_n))) return rc;
-  if ((rc = make_act_map4(&tmOut, dx, Cin, Wi, Hi, N, dx_cstride, pl.bw, pl.bh, pl.bn))) return rc;
+  if ((rc = make_act_map4(&tmOut, dx, Cin, Wi, Hm, 1, dx_cstride, pl.bw, pl.bh, pl.bn))) return rc;
   return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
 }
 
@@ -729,6 +733,7 @@ extern "C" long long b2s_conv_wgrad_workspace(int N, int H, int W, int Cin, int 
     return static_cast<long long>(s) * taps * Cin * Cout * 4;
   }
   tile_n &= kTileNMask;
+  if (taps == 4) { H *= N; N = 1; }   // the transposed-conv kernel merges the rows of all images (b2s_convt2x2_wgrad)
   if (Cin % 64 || Cout % 64 || wgrad_plan(N, H, W, Cin, Cout, taps, tile_n, splits, &p, &block_n)) {
     set_error(B2S_ERR_ARG, "b2s_conv_wgrad_workspace: unsupported shape");
     return -1;
@@ -785,13 +790,13 @@ extern "C" int b2s_convt2x2_wgrad(const void* x, int x_cstride, const void* dy, 
   if (Cin % 128 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_convt2x2_wgrad: need Cin % 128 == 0, Cout % 64 == 0");
   WgradParams p{};
   int block_n;
-  if (wgrad_plan(N, Hi, Wi, Cin, Cout, 4, tile_n, splits, &p, &block_n))
+  const int Hm = Hi * N;   // image rows merged into one dimension (no spatial halo; see b2s_convt2x2_fwd)
+  if (wgrad_plan(1, Hm, Wi, Cin, Cout, 4, tile_n, splits, &p, &block_n))
     return set_error(B2S_ERR_ARG, "b2s_convt2x2_wgrad: bad tile_n");
-  if (p.pn > 1 && p.ph != Hi) return set_error(B2S_ERR_ARG, "b2s_convt2x2_wgrad: unsupported tiny non-pow2 image");
   p.mode = WG_CONVT; p.ws = ws;
   CUtensorMap tmA, tmB;
   int rc;
-  if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hi, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
-  if ((rc = make_up_map5(&tmB, dy, Cout, Wi, Hi, N, dy_cstride, p.pw, p.ph * p.pn))) return rc;
+  if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hm, 1, x_cstride, p.pw, p.ph, p.pn))) return rc;
+  if ((rc = make_up_map5(&tmB, dy, Cout, Wi, Hm, 1, dy_cstride, p.pw, p.ph * p.pn))) return rc;
   return dispatch_wgrad(block_n, tmA, tmB, p, stream);
 }
