@@ -77,6 +77,12 @@ int b2s_pack_conv_weight(const float* w, void* w_fwd, void* w_dgrad, int Cout, i
 /* w [Cin][Cout][2][2] fp32 -> w_fwd [(a*2+b)*Cout+co][Cin], w_dgrad [(a*2+b)*Cin+ci][Cout] (either may be NULL). */
 int b2s_pack_convt_weight(const float* w, void* w_fwd, void* w_dgrad, int Cin, int Cout, void* stream);
 
+/* every conv / transposed-conv weight of a network in ONE launch (arrays in HOST memory, n <= 40): kind[i] 0 = Conv2d
+ * weight (d0 = Cout, d1 = Cin, taps = k*k in {1, 9}), 1 = ConvTranspose2d weight (d0 = Cin, d1 = Cout, taps = 4); outputs
+ * laid out as by b2s_pack_conv_weight / b2s_pack_convt_weight; wf[i] or wd[i] may be NULL. */
+int b2s_pack_weights_all(int n, const void* const* w, void* const* wf, void* const* wd, const int* d0, const int* d1,
+                         const int* taps, const int* kind, void* stream);
+
 /* ---- bandwidth kernels ------------------------------------------------------------------------------------------ */
 /* first layer nn.Conv2d(1,Cout,3,padding=1)+ReLU (models/model.py:10): x [N,H,W] fp32 -> r [N,H,W,Cout] bf16.
  * stats_partial [b2s_c1_rows(N,H,W)][2][Cout]. Cout multiple of 8, <= 128. */

@@ -323,6 +323,22 @@ def test_pack_weights(ops):
     assert torch.equal(td, tb.permute(2, 3, 0, 1).reshape(4 * 128, 64))
 
 
+def test_pack_all_matches_per_tensor_packing(ops):
+    """one-launch packing of a set of conv / transposed-conv weights == the per-tensor kernels, bit for bit"""
+    ws = [("a", rnd((128, 64, 3, 3), 73).to(DEV), False), ("b", rnd((64, 192, 1, 1), 74).to(DEV), False),
+          ("t", rnd((128, 64, 2, 2), 75).to(DEV), True), ("c", rnd((40, 72, 3, 3), 76).to(DEV), False)]
+    plan = ops.PackPlan(ws, want_dgrad=True)
+    plan.run()
+    torch.cuda.synchronize()
+    for name, w, is_t in ws:
+        wf, wd = plan.packed[name]
+        rf, rd = ops.pack_convt_weight(w) if is_t else ops.pack_conv_weight(w, want_dgrad=True)
+        assert torch.equal(wf, rf) and torch.equal(wd, rd), name
+    plan2 = ops.PackPlan(ws[:2], want_dgrad=False)
+    plan2.run()
+    assert plan2.packed["a"][1] is None and torch.equal(plan2.packed["a"][0], plan.packed["a"][0])
+
+
 # ------------------------------------------------------------------------------------------------------------
 # bandwidth kernels
 # ------------------------------------------------------------------------------------------------------------

@@ -33,6 +33,7 @@ SIGNATURES = {
     "b2s_wgrad_reduce": (I, [P, I, I, I, I, P, I, P]),
     "b2s_pack_conv_weight": (I, [P, P, P, I, I, I, P]),
     "b2s_pack_convt_weight": (I, [P, P, P, I, I, P]),
+    "b2s_pack_weights_all": (I, [I, P, P, P, P, P, P, P, P]),
     "b2s_conv3x3_c1_fwd": (I, [P, P, P, P, P, I, I, I, I, I, P]),
     "b2s_c1_rows": (I, [I, I, I]),
     "b2s_conv3x3_c1_wgrad": (I, [P, P, P, I, I, I, I, P]),

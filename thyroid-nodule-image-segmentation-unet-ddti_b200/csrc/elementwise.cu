@@ -206,23 +206,26 @@ __device__ __forceinline__ void c1_load_window(const float* __restrict__ xi, int
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        __nv_bfloat16* __restrict__ r, float* __restrict__ stats_partial, int N, int H, int W, int Cout,
                        int flags) {
+  // weights live in shared memory ([tap][Cout], read as two broadcast float4 per tap): keeping all 72 of a thread's
+  // weights in registers cost 191 registers and one resident block per SM
   __shared__ float red[kThreads * 16];
+  __shared__ __align__(16) float wsm[9 * 128];
   const int groups = Cout / 8;
   const int qpi = kThreads / groups;        // pixel quads per block iteration
   const int cg = threadIdx.x % groups;
   const int ql = threadIdx.x / groups;
-  float wr[9][8], br[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int co = cg * 8 + k;
-    br[k] = bias ? bias[co] : 0.f;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) wr[t][k] = w[co * 9 + t];
+  for (int i = threadIdx.x; i < 9 * Cout; i += kThreads) {
+    const int t = i / Cout, co = i - t * Cout;
+    wsm[t * Cout + co] = w[co * 9 + t];
   }
+  float br[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) br[k] = bias ? bias[cg * 8 + k] : 0.f;
+  __syncthreads();
   float st[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) st[k] = 0.f;
@@ -238,21 +241,35 @@ conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w,
       const float* xi = x + (p - wq - static_cast<unsigned>(hq) * W);  // image base
       float xv[3][6];
       c1_load_window(xi, hq, wq, H, W, xv);
+      float acc[4][8];
+#pragma unroll
+      for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[px][k] = br[k];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&wsm[t * Cout + cg * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&wsm[t * Cout + cg * 8 + 4]);
+        const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float v = xv[t / 3][px + t % 3];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[px][k] = fmaf(v, wk[k], acc[px][k]);
+        }
+      }
 #pragma unroll
       for (int px = 0; px < 4; ++px) {
-        float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float a = br[k];
-#pragma unroll
-          for (int t = 0; t < 9; ++t) a = fmaf(xv[t / 3][px + t % 3], wr[t][k], a);
+          float a = acc[px][k];
           if (relu) a = fmaxf(a, 0.f);
           a = bf16_round(a);
-          acc[k] = a;
+          acc[px][k] = a;
           st[k] += a;
           st[8 + k] = fmaf(a, a, st[8 + k]);
         }
-        stg16(r + static_cast<size_t>(p + px) * Cout + cg * 8, pack8(acc));
+        stg16(r + static_cast<size_t>(p + px) * Cout + cg * 8, pack8(acc[px]));
       }
     }
   }
@@ -957,6 +974,68 @@ __global__ void pack_convt_weight_kernel(const float* __restrict__ w, __nv_bfloa
   }
 }
 
+// All conv / transposed-conv weights of a network in ONE launch: block -> (tensor, 32x32 tile) through a small table in
+// kernel-parameter space. Same tile transposes as the two kernels above.
+constexpr int kPackMaxTensors = 40;
+struct PackEntry {
+  const float* w;
+  __nv_bfloat16* wf;
+  __nv_bfloat16* wd;
+  int d0, d1, taps;   // kind 0: w [d0=Cout][d1=Cin][taps];  kind 1: w [d0=Cin][d1=Cout][4]
+  int kind;
+  int tile_begin;     // first block of this tensor
+};
+struct PackTable {
+  PackEntry e[kPackMaxTensors];
+  int n;
+};
+
+__global__ void __launch_bounds__(kThreads)
+pack_all_kernel(const __grid_constant__ PackTable tab) {
+  __shared__ float tile[32][32 * 9 + 1];
+  int ti = 0;
+  while (ti + 1 < tab.n && static_cast<int>(blockIdx.x) >= tab.e[ti + 1].tile_begin) ++ti;
+  const PackEntry& E = tab.e[ti];
+  const int local = blockIdx.x - E.tile_begin;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int taps = E.taps;
+  // tiles over (d1 / 32, d0 / 32): tile rows = 32 consecutive d0 indices, each row = 32 d1 indices x taps (contiguous)
+  const int tiles1 = (E.d1 + 31) / 32;
+  const int i1 = (local % tiles1) * 32, i0 = (local / tiles1) * 32;
+  const int n1 = min(32, E.d1 - i1), n0 = min(32, E.d0 - i0);
+  for (int rr = ty; rr < n0; rr += 8) {
+    const float* src = E.w + (static_cast<size_t>(i0 + rr) * E.d1 + i1) * taps;
+    for (int i = tx; i < n1 * taps; i += 32) tile[rr][i] = src[i];
+  }
+  __syncthreads();
+  if (E.kind == 0) {          // rows = co, cols = ci
+    const int Cout = E.d0, Cin = E.d1;
+    for (int t = 0; t < taps; ++t) {
+      if (E.wf)
+        for (int col = ty; col < n0; col += 8)
+          if (tx < n1)
+            E.wf[(static_cast<size_t>(t) * Cout + i0 + col) * Cin + i1 + tx] = __float2bfloat16_rn(tile[col][tx * taps + t]);
+      if (E.wd)
+        for (int cil = ty; cil < n1; cil += 8)
+          if (tx < n0)
+            E.wd[(static_cast<size_t>(taps - 1 - t) * Cin + i1 + cil) * Cout + i0 + tx] =
+                __float2bfloat16_rn(tile[tx][cil * taps + t]);
+    }
+  } else {                    // rows = ci, cols = co; wf [(t*Cout+co)][Cin], wd [(t*Cin+ci)][Cout]
+    const int Cin = E.d0, Cout = E.d1;
+    for (int t = 0; t < 4; ++t) {
+      if (E.wf)
+        for (int col = ty; col < n1; col += 8)
+          if (tx < n0)
+            E.wf[(static_cast<size_t>(t) * Cout + i1 + col) * Cin + i0 + tx] = __float2bfloat16_rn(tile[tx][col * 4 + t]);
+      if (E.wd)
+        for (int row = ty; row < n0; row += 8)
+          if (tx < n1)
+            E.wd[(static_cast<size_t>(t) * Cin + i0 + row) * Cout + i1 + tx] = __float2bfloat16_rn(tile[row][tx * 4 + t]);
+    }
+  }
+}
+
 // ws [splits][taps][Cin][Cout] -> layout 0: dw[co][ci][t]; layout 1: dw[ci][co][t].
 // Block = 8 warps x (32 lanes = 128 co as float4). The warps are split into (8/sgroups) input channels x sgroups
 // split groups, so that shallow layers (tiny K, many K-splits) and deep layers (huge K, 1-2 splits) both stream with
@@ -1359,6 +1438,28 @@ extern "C" int b2s_pack_convt_weight(const float* w, void* w_fwd, void* w_dgrad,
   pack_convt_weight_kernel<<<grid_for(total, kThreads * 4), kThreads, 0, STREAM(stream)>>>(
       w, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad), Cin, Cout);
   return check_launch("pack_convt_weight_kernel");
+}
+
+// n tensors described by parallel arrays (host memory): kind[i] 0 = Conv2d weight [Cout][Cin][k][k] (d0 = Cout, d1 = Cin,
+// taps = k*k), 1 = ConvTranspose2d weight [Cin][Cout][2][2] (d0 = Cin, d1 = Cout). wf / wd entries may be NULL.
+extern "C" int b2s_pack_weights_all(int n, const void* const* w, void* const* wf, void* const* wd, const int* d0,
+                                    const int* d1, const int* taps, const int* kind, void* stream) {
+  if (n < 1 || n > kPackMaxTensors || !w || !wf || !wd || !d0 || !d1 || !taps || !kind)
+    return set_error(B2S_ERR_ARG, "b2s_pack_weights_all: bad argument (1..40 tensors)");
+  PackTable tab;
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!w[i] || (kind[i] != 0 && kind[i] != 1) || (kind[i] == 0 && taps[i] != 1 && taps[i] != 9) ||
+        (kind[i] == 1 && taps[i] != 4) || d0[i] < 1 || d1[i] < 1)
+      return set_error(B2S_ERR_ARG, "b2s_pack_weights_all: bad tensor description");
+    tab.e[i] = PackEntry{static_cast<const float*>(w[i]), static_cast<__nv_bfloat16*>(wf[i]),
+                         static_cast<__nv_bfloat16*>(wd[i]), d0[i], d1[i], taps[i], kind[i], blocks};
+    blocks += ((d0[i] + 31) / 32) * ((d1[i] + 31) / 32);
+  }
+  tab.n = n;
+  count_launch();
+  pack_all_kernel<<<blocks, kThreads, 0, STREAM(stream)>>>(tab);
+  return check_launch("pack_all_kernel");
 }
 
 extern "C" int b2s_wgrad_reduce(const float* ws, int splits, int taps, int Cin, int Cout, float* dw, int layout,

@@ -150,18 +150,23 @@ class UNetEngine:
         self._packed_versions = None
 
     def _pack_weights(self, P, need_dgrad):
-        """fp32 parameters -> bf16 GEMM operands; cached on the parameters' version counters."""
+        """fp32 parameters -> bf16 GEMM operands, all tensors in one launch; skipped while the parameters' version
+        counters and addresses are unchanged."""
         names = [k for k in P if k.endswith(".weight") and P[k].dim() == 4 and k != "encoder1.0.weight"
                  and k != "final.1.weight"]
         versions = tuple((k, P[k]._version, P[k].data_ptr(), need_dgrad) for k in names)
         if versions == self._packed_versions:
             return
-        for k in names:
-            w = P[k]
-            if k.split(".")[0] in ("middle", "decoder3", "decoder2", "decoder1") and w.shape[2] == 2:
-                self._packed[k] = ops.pack_convt_weight(w)
-            else:
-                self._packed[k] = ops.pack_conv_weight(w, want_dgrad=need_dgrad)
+        layout = tuple((k, P[k].data_ptr(), need_dgrad) for k in names)
+        if getattr(self, "_pack_layout", None) != layout:
+            items = []
+            for k in names:
+                is_convt = k.split(".")[0] in ("middle", "decoder3", "decoder2", "decoder1") and P[k].shape[2] == 2
+                items.append((k, P[k].detach(), is_convt))
+            self._pack_plan = ops.PackPlan(items, want_dgrad=need_dgrad)
+            self._packed = self._pack_plan.packed
+            self._pack_layout = layout
+        self._pack_plan.run()
         self._packed_versions = versions
 
     # ---- forward ----------------------------------------------------------------------------------------------

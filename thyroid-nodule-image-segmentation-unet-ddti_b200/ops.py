@@ -118,6 +118,46 @@ def pack_convt_weight(w):
     return wf, wd
 
 
+class PackPlan:
+    """Pre-allocated bf16 operands of a set of conv / transposed-conv weights and the argument arrays of the single
+    b2s_pack_weights_all launch that refreshes all of them."""
+
+    def __init__(self, weights, want_dgrad):
+        """weights: list of (name, fp32 tensor); 4-D [Cout,Cin,k,k] or transposed-conv [Cin,Cout,2,2] (flag in name map)"""
+        self.items = []
+        n = len(weights)
+        self._w = (ctypes.c_void_p * n)()
+        self._wf = (ctypes.c_void_p * n)()
+        self._wd = (ctypes.c_void_p * n)()
+        self._d0, self._d1 = (ctypes.c_int * n)(), (ctypes.c_int * n)()
+        self._taps, self._kind = (ctypes.c_int * n)(), (ctypes.c_int * n)()
+        self.packed, self.nbytes, self.n = {}, 0.0, n
+        for i, (name, w, is_convt) in enumerate(weights):
+            _need_cuda(w)
+            assert w.dtype == torch.float32 and w.is_contiguous()
+            if is_convt:
+                Cin, Cout = w.shape[0], w.shape[1]
+                wf = torch.empty((4 * Cout, Cin), dtype=BF16, device=w.device)
+                wd = torch.empty((4 * Cin, Cout), dtype=BF16, device=w.device)
+                d0, d1, taps, kind = Cin, Cout, 4, 1
+            else:
+                Cout, Cin, k, _ = w.shape
+                wf = torch.empty((k * k, Cout, Cin), dtype=BF16, device=w.device)
+                wd = torch.empty((k * k, Cin, Cout), dtype=BF16, device=w.device) if want_dgrad else None
+                d0, d1, taps, kind = Cout, Cin, k * k, 0
+            self.packed[name] = (wf, wd)
+            self._w[i], self._wf[i] = w.data_ptr(), wf.data_ptr()
+            self._wd[i] = wd.data_ptr() if wd is not None else None
+            self._d0[i], self._d1[i], self._taps[i], self._kind[i] = d0, d1, taps, kind
+            self.nbytes += w.numel() * (4.0 + 2.0 * (2 if wd is not None else 1))
+            self.items.append(w)          # keeps the sources alive (their addresses are baked into the arrays)
+
+    def run(self):
+        _timed("pack_weights_all", "hbm", self.nbytes, lambda: check(
+            _lib.lib().b2s_pack_weights_all(self.n, self._w, self._wf, self._wd, self._d0, self._d1, self._taps,
+                                            self._kind, _stream()), "b2s_pack_weights_all"))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # tensor-core convs
 # ---------------------------------------------------------------------------------------------------------
