@@ -239,6 +239,7 @@ def test_conv3x3_dgrad(ops, N, H, W, Cin, Cout):
     (1, 4, 128, 128, 64, 0, 0),     # Cin 128: one tap per tile, two CTA groups (5 + 4 taps)
     (1, 4, 128, 64, 128, 0, 3),     # Cout 128: two CTA groups (3 + 2 tiles)
     (2, 6, 128, 128, 128, 0, 0),    # three CTA groups, one tap row each
+    (1, 4, 128, 256, 64, 0, 0),     # Cin 256: 18 (tap, half) tiles in three CTA groups
     (1, 4, 128, 64, 64, 1 << 12, 0),  # same shape through the legacy kernel
 ])
 def test_conv3x3_wgrad(ops, N, H, W, Cin, Cout, tile_n, splits):

@@ -7,13 +7,26 @@
 namespace b2s {
 
 // ---- counter-based dropout mask: depends only on (seed, logical NHWC element index) so backward re-derives it ----
+// One 64-bit hash per group of four consecutive channels supplies four 16-bit uniforms: keep iff u16 >= p * 65536.
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
-__device__ __forceinline__ bool drop_keep(unsigned long long idx, uint32_t seed, uint32_t thresh) {
-  const uint32_t h = mix32(static_cast<uint32_t>(idx) ^ mix32(static_cast<uint32_t>(idx >> 32) + seed));
-  return h >= thresh;   // P(keep) = 1 - thresh / 2^32
+// keep mask (bit k = keep element k) of the 8 consecutive elements starting at idx8 (a multiple of 8)
+__device__ __forceinline__ uint32_t drop_keep8(unsigned long long idx8, uint32_t seed, uint32_t thresh16) {
+  const uint32_t lo = static_cast<uint32_t>(idx8 >> 2), hi = static_cast<uint32_t>(idx8 >> 34);
+  const uint32_t base = mix32(hi + seed);
+  uint32_t mask = 0;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const uint32_t h0 = mix32((lo + g) ^ base);
+    const uint32_t h1 = mix32(h0 + 0x9e3779b9U);
+    mask |= ((h0 & 0xFFFFu) >= thresh16 ? 1u : 0u) << (4 * g + 0);
+    mask |= ((h0 >> 16) >= thresh16 ? 1u : 0u) << (4 * g + 1);
+    mask |= ((h1 & 0xFFFFu) >= thresh16 ? 1u : 0u) << (4 * g + 2);
+    mask |= ((h1 >> 16) >= thresh16 ? 1u : 0u) << (4 * g + 3);
+  }
+  return mask;
 }
 
 // out = dropout(relu(z * scale + shift)) + res      (models/vnet.py:51-59)
@@ -36,11 +49,12 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* 
     float v[8], rr[8];
     unpack8(ldg16(z + pix * z_cs + cg * 8), v);
     if (res) unpack8(ldg16(res + pix * res_cs + cg * 8), rr);
+    const uint32_t keep = drop_thresh ? drop_keep8(static_cast<unsigned long long>(pix) * C + cg * 8, seed, drop_thresh) : 0xFFu;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float a = fmaf(v[k], sc[k], sh[k]);
       if (relu) a = fmaxf(a, 0.f);
-      if (drop_thresh) a = drop_keep(static_cast<unsigned long long>(pix) * C + cg * 8 + k, seed, drop_thresh) ? a * drop_scale : 0.f;
+      if (drop_thresh) a = (keep >> k) & 1u ? a * drop_scale : 0.f;
       if (res) a += rr[k];
       v[k] = a;
     }
@@ -80,10 +94,11 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
     float zv[8], g[8], outv[8];
     unpack8(ldg16(z + pix * z_cs + cg * 8), zv);
     unpack8(ldg16(da + pix * da_cs + cg * 8), g);
+    const uint32_t keep = drop_thresh ? drop_keep8(static_cast<unsigned long long>(pix) * C + cg * 8, seed, drop_thresh) : 0xFFu;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float d = g[k];
-      if (drop_thresh) d = drop_keep(static_cast<unsigned long long>(pix) * C + cg * 8 + k, seed, drop_thresh) ? d * drop_scale : 0.f;
+      if (drop_thresh) d = (keep >> k) & 1u ? d * drop_scale : 0.f;
       if (relu && !(fmaf(zv[k], sc[k], sh[k]) > 0.f)) d = 0.f;
       const float xh = (zv[k] - mu[k]) * is[k];
       if (!APPLY) {
@@ -170,7 +185,7 @@ upsample_zero2x_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_b
 }
 
 // ---- squeeze-and-excitation (models/vnet.py:5-26) ------------------------------------------------------------
-constexpr int kSePixPerBlock = 4096;   // pixels of one sample reduced by one block
+constexpr int kSePixPerBlock = 2048;   // pixels of one sample reduced by one block
 
 // partial[n][chunk][C] = sum over the chunk's pixels of x (DOT: of x * y)
 template <bool DOT>
@@ -189,17 +204,29 @@ se_pool_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat1
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  for (long long p = p0 + pl; p < p1; p += ppi) {
-    float v[8];
-    unpack8(ldg16(x + (base + p) * x_cs + cg * 8), v);
-    if (DOT) {
-      float u[8];
-      unpack8(ldg16(y + (base + p) * y_cs + cg * 8), u);
+  constexpr int U = 4;   // pixels in flight per thread
+  for (long long pb = p0 + pl; pb < p1; pb += static_cast<long long>(ppi) * U) {
+    uint4 xr[U], yr[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf(v[k], u[k], acc[k]);
-    } else {
+    for (int u = 0; u < U; ++u) {
+      const long long p = pb + static_cast<long long>(u) * ppi;
+      const bool on = p < p1;
+      xr[u] = on ? ldg16(x + (base + p) * x_cs + cg * 8) : make_uint4(0, 0, 0, 0);
+      if (DOT) yr[u] = on ? ldg16(y + (base + p) * y_cs + cg * 8) : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    for (int u = 0; u < U; ++u) {
+      float v[8];
+      unpack8(xr[u], v);
+      if (DOT) {
+        float w8[8];
+        unpack8(yr[u], w8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(v[k], w8[k], acc[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k];
+      }
     }
   }
 #pragma unroll
@@ -332,11 +359,27 @@ outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float
 using namespace b2s;
 #define STREAM(s) static_cast<cudaStream_t>(s)
 
+// SM count x resident blocks (at most kEwBlocks / kSMs = 4 per SM): one full wave, no partial last wave
+template <typename K>
+static int wave_grid(K kernel) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+  if (occ > kEwBlocks / kSMs) occ = kEwBlocks / kSMs;
+  return kSMs * occ;
+}
+
+// 16-bit threshold: P(drop) = thresh / 65536 (p is quantised to 1/65536; the kept values are scaled by the exact
+// reciprocal of the quantised keep probability so the mask stays unbiased)
 static uint32_t drop_threshold(float p) {
   if (p <= 0.f) return 0u;
-  double t = static_cast<double>(p) * 4294967296.0;
-  if (t > 4294967295.0) t = 4294967295.0;
+  double t = static_cast<double>(p) * 65536.0 + 0.5;
+  if (t < 1.0) t = 1.0;
+  if (t > 65535.0) t = 65535.0;
   return static_cast<uint32_t>(t);
+}
+static float drop_scale_of(float p) {
+  const uint32_t t = drop_threshold(p);
+  return t ? static_cast<float>(65536.0 / (65536.0 - t)) : 1.f;
 }
 
 extern "C" int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale, const float* shift, const void* res,
@@ -350,8 +393,7 @@ extern "C" int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale
   count_launch();
   bn_act_apply_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, static_cast<const __nv_bfloat16*>(res), res_cstride,
-      static_cast<__nv_bfloat16*>(out), out_cstride, npix, C, relu, drop_threshold(dropout_p), 1.f / (1.f - dropout_p),
-      seed);
+      static_cast<__nv_bfloat16*>(out), out_cstride, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed);
   return check_launch("bn_act_apply_kernel");
 }
 
@@ -362,9 +404,10 @@ extern "C" int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void*
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: unsupported C");
   count_launch();
-  bn_act_bwd_kernel<false><<<kSMs * 2, kThreads, 0, STREAM(stream)>>>(
+  static const int grid = wave_grid(bn_act_bwd_kernel<false>);
+  bn_act_bwd_kernel<false><<<grid, kThreads, 0, STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
-      mean, invstd, nullptr, nullptr, 0, partial, npix, C, relu, drop_threshold(dropout_p), 1.f / (1.f - dropout_p), seed);
+      mean, invstd, nullptr, nullptr, 0, partial, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed);
   return check_launch("bn_act_bwd_kernel<reduce>");
 }
 
@@ -376,10 +419,11 @@ extern "C" int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* 
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: unsupported C");
   count_launch();
-  bn_act_bwd_kernel<true><<<kSMs * 2, kThreads, 0, STREAM(stream)>>>(
+  static const int grid = wave_grid(bn_act_bwd_kernel<true>);
+  bn_act_bwd_kernel<true><<<grid, kThreads, 0, STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
       mean, invstd, coef, static_cast<__nv_bfloat16*>(dz), dz_cstride, dbias_partial, npix, C, relu,
-      drop_threshold(dropout_p), 1.f / (1.f - dropout_p), seed);
+      drop_threshold(dropout_p), drop_scale_of(dropout_p), seed);
   return check_launch("bn_act_bwd_kernel<apply>");
 }
 

@@ -20,7 +20,7 @@ namespace b2s {
 constexpr int kWg2Threads = 192;            // warp0 producer (+TMEM alloc), warp1 MMA issuer, warps 2-5 epilogue
 constexpr int kWgHaloRowBytes = 17 * 1024;  // 130 px x 128 B, padded to a multiple of 1024
 constexpr int kWgMaxGroups = 4;
-constexpr int kWgMaxTiles = 12;
+constexpr int kWgMaxTiles = 20;
 
 struct WgHaloParams {
   int strips, H;                  // 128-pixel strips per image row, rows per image
@@ -123,7 +123,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
       const uint32_t b_lo0 = static_cast<uint32_t>(proto) | ((16384u >> 4) << 16);   // dz: 64-channel panels 16 KB apart
       const uint32_t smem_lo = smem_u32(smem) >> 4;
-      constexpr int kMaxT = 512 / BLOCK_N > 5 ? 5 : 512 / BLOCK_N;   // M tiles a CTA group can own
+      constexpr int kMaxT = 512 / BLOCK_N;   // M tiles a CTA group can own (TMEM columns / BLOCK_N)
       uint32_t tl[kMaxT];
 #pragma unroll
       for (int t = 0; t < kMaxT; ++t) tl[t] = p.tile_lo[min(tile0 + t, kWgMaxTiles - 1)];
@@ -205,12 +205,16 @@ static int launch_wg2(int grid, const CUtensorMap& tmX, const CUtensorMap& tmDz,
 }
 
 bool wgrad_halo_eligible(int N, int H, int W, int Cin, int Cout) {
-  return W % 128 == 0 && (Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128) && N > 0 && H > 0;
+  if (W % 128 != 0 || N <= 0 || H <= 0) return false;
+  if ((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128)) return true;
+  return Cin == 256 && Cout == 64;   // 18 tiles of (tap, 128-channel half): three CTA groups of one tap row each
 }
+
+static int wg_num_tiles(int Cin) { return Cin == 64 ? 5 : 9 * (Cin / 128); }
 
 // Splits (CTAs per tap group) the halo kernel uses: one CTA per SM in total.
 int wgrad_halo_splits(int N, int H, int W, int Cin, int Cout, int splits_req) {
-  const int tiles = Cin == 64 ? 5 : 9;
+  const int tiles = wg_num_tiles(Cin);
   const int max_tiles = 512 / Cout;
   const int groups = (tiles + max_tiles - 1) / max_tiles;
   const int rows_total = N * H * (W / 128);
@@ -226,7 +230,8 @@ int launch_wgrad_halo(const void* x, int x_cstride, const void* dz, int dz_cstri
   if (!wgrad_halo_eligible(N, H, W, Cin, Cout)) return set_error(B2S_ERR_ARG, "wgrad halo kernel: unsupported shape");
   WgHaloParams p{};
   const int chunks = Cin / 64;
-  const int tiles = Cin == 64 ? 5 : 9;          // M tiles of 128 (tap, ci) rows; Cin = 64 pairs two taps per tile
+  const int tiles = wg_num_tiles(Cin);          // M tiles of 128 (tap, ci) rows; Cin = 64 pairs two taps per tile
+  const int halves = Cin >= 128 ? Cin / 128 : 1;   // 128-channel halves per tap (Cin >= 128)
   const int max_tiles = 512 / Cout;             // TMEM columns / BLOCK_N
   const int groups = (tiles + max_tiles - 1) / max_tiles;
   const int per = (tiles + groups - 1) / groups;
@@ -239,14 +244,15 @@ int launch_wgrad_halo(const void* x, int x_cstride, const void* dz, int dz_cstri
   int max_slots = 0;
   for (int g = 0; g < groups; ++g) {
     const int a = g * per, b = (a + per < tiles) ? a + per : tiles;
-    const int tap_first = Cin == 64 ? 2 * a : a;
-    const int tap_last = Cin == 64 ? (2 * b - 1 < 8 ? 2 * b - 1 : 8) : b - 1;
+    const int tap_first = Cin == 64 ? 2 * a : a / halves;
+    const int tap_last = Cin == 64 ? (2 * b - 1 < 8 ? 2 * b - 1 : 8) : (b - 1) / halves;
     const int th_lo = tap_first / 3, th_hi = tap_last / 3;
     p.g_tile0[g] = a; p.g_ntiles[g] = b - a; p.g_th_lo[g] = th_lo; p.g_nth[g] = th_hi - th_lo + 1;
     if (p.g_nth[g] * chunks > max_slots) max_slots = p.g_nth[g] * chunks;
     for (int m = a; m < b; ++m) {
-      const int t0 = Cin == 64 ? 2 * m : m;
-      const int off0 = (t0 / 3 - th_lo) * RS + (t0 % 3) * 128;
+      const int t0 = Cin == 64 ? 2 * m : m / halves;
+      // tile m of a Cin >= 128 layer = (tap m / halves, channels 128 * (m % halves) ...): two chunk slots further per half
+      const int off0 = (t0 / 3 - th_lo) * RS + (t0 % 3) * 128 + (Cin >= 128 ? (m % halves) * 2 * kWgHaloRowBytes : 0);
       int lbo;
       if (Cin == 64) {
         const int t1 = t0 + 1;   // second 64-channel panel = the next tap (tile 4: a discarded duplicate)

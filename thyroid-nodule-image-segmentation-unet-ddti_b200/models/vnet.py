@@ -132,9 +132,38 @@ class ImprovedVNet(nn.Module):
             raise NotImplementedError("the B200 path implements in_channels=1 and base_num_filters a multiple of 64 "
                                       "(the reference defaults)")
 
+    def _pack_all_weights(self):
+        """bf16 GEMM operands of every tensor-core conv / transposed-conv weight, refreshed in a few launches whenever
+        a parameter changed (optimizer step, load_state_dict, .to()); registered for the autograd nodes."""
+        from .. import ops
+        ws = [(n, p) for n, p in self.named_parameters()
+              if p.dim() == 4 and p.shape[1] >= 64 and p.shape[0] >= 64 and p.shape[0] % 64 == 0 and p.shape[1] % 64 == 0
+              and ".fc" not in n]
+        key = tuple((p.data_ptr(), p._version) for _, p in ws)
+        if getattr(self, "_pack_key", None) == key:
+            return
+        layout = tuple((p.data_ptr(), self.training) for _, p in ws)
+        if getattr(self, "_pack_layout", None) != layout:
+            items = [(n, p.detach(), n.startswith("up")) for n, p in ws]
+            self._pack_plans = [ops.PackPlan(items[i:i + 40], want_dgrad=self.training) for i in range(0, len(items), 40)]
+            self._pack_layout = layout
+        for old in getattr(self, "_pack_registered", ()):
+            VF.PACKED.pop(old, None)
+        reg = []
+        for plan in self._pack_plans:
+            plan.run()
+        for n, p in ws:
+            for plan in self._pack_plans:
+                if n in plan.packed:
+                    VF.PACKED[p.data_ptr()] = (p._version,) + plan.packed[n]
+                    reg.append(p.data_ptr())
+        self._pack_registered = tuple(reg)
+        self._pack_key = key
+
     def _trunk(self, x):
         assert x.shape[1] == self.in_channels, f"Expected input with {self.in_channels} channel(s)"
         _require_cuda(x)
+        self._pack_all_weights()
         if x.shape[2] % 16 or x.shape[3] % 16:
             raise RuntimeError("Sizes of tensors must match except in dimension 1: H and W must be multiples of 16")
         x = x.float().contiguous()

@@ -388,8 +388,9 @@ def adamw_step_dev(p, g, m, v, hyper):
 
 def copy_channels(src, dst):
     npix = src.N * src.H * src.W
-    check(_lib.lib().b2s_copy_channels(src.ptr, src.cstride, dst.ptr, dst.cstride, npix, src.C, _stream()),
-          "b2s_copy_channels")
+    _timed("copy_channels", "hbm", npix * src.C * 4.0, lambda: check(
+        _lib.lib().b2s_copy_channels(src.ptr, src.cstride, dst.ptr, dst.cstride, npix, src.C, _stream()),
+        "b2s_copy_channels"))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -404,8 +405,9 @@ def conv3x3_s2_fwd(x, w_packed, bias, y, tile_n=0):
 
 
 def upsample_zero2x(src, dst):
-    check(_lib.lib().b2s_upsample_zero2x(src.ptr, src.cstride, dst.ptr, dst.cstride, src.N, src.H, src.W, src.C,
-                                         _stream()), "b2s_upsample_zero2x")
+    _timed("upsample_zero2x", "hbm", 2.0 * src.C * src.N * src.H * src.W * 5.0, lambda: check(
+        _lib.lib().b2s_upsample_zero2x(src.ptr, src.cstride, dst.ptr, dst.cstride, src.N, src.H, src.W, src.C,
+                                       _stream()), "b2s_upsample_zero2x"))
 
 
 def conv1x1_wgrad(x, dz, dw, tile_n=0, splits=0):
@@ -413,16 +415,19 @@ def conv1x1_wgrad(x, dz, dw, tile_n=0, splits=0):
     nbytes, s = wgrad_workspace(x.N, x.H, x.W, x.C, dz.C, 1, tile_n, splits)
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dw.device)
     L = _lib.lib()
-    check(L.b2s_conv1x1_wgrad(x.ptr, x.cstride, dz.ptr, dz.cstride, _p(ws), x.N, x.H, x.W, x.C, dz.C, tile_n, splits,
-                              _stream()), "b2s_conv1x1_wgrad")
+    _timed(f"wgrad1x1[{x.C}->{dz.C}@{x.H}x{x.W}]", "tensor", 2.0 * x.N * x.H * x.W * x.C * dz.C, lambda: check(
+        L.b2s_conv1x1_wgrad(x.ptr, x.cstride, dz.ptr, dz.cstride, _p(ws), x.N, x.H, x.W, x.C, dz.C, tile_n, splits,
+                            _stream()), "b2s_conv1x1_wgrad"))
     check(L.b2s_wgrad_reduce(_p(ws), s, 1, x.C, dz.C, _p(dw), 0, _stream()), "b2s_wgrad_reduce")
 
 
 def bn_act_apply(z, scale, shift, res, out, relu=True, dropout_p=0.0, seed=0):
-    check(_lib.lib().b2s_bn_act_apply(z.ptr, z.cstride, _p(scale), _p(shift), res.ptr if res is not None else None,
-                                      res.cstride if res is not None else 0, out.ptr, out.cstride,
-                                      z.N * z.H * z.W, z.C, int(relu), float(dropout_p), int(seed) & 0xFFFFFFFF,
-                                      _stream()), "b2s_bn_act_apply")
+    nb = z.N * z.H * z.W * z.C * 2.0 * (3.0 if res is not None else 2.0)
+    _timed("bn_act_apply", "hbm", nb, lambda: check(
+        _lib.lib().b2s_bn_act_apply(z.ptr, z.cstride, _p(scale), _p(shift), res.ptr if res is not None else None,
+                                    res.cstride if res is not None else 0, out.ptr, out.cstride,
+                                    z.N * z.H * z.W, z.C, int(relu), float(dropout_p), int(seed) & 0xFFFFFFFF,
+                                    _stream()), "b2s_bn_act_apply"))
 
 
 def bn_act_bwd(da, z, scale, shift, mean, invstd, gamma, count, dz, dgamma, dbeta, dbias, relu=True, dropout_p=0.0,
@@ -436,14 +441,16 @@ def bn_act_bwd(da, z, scale, shift, mean, invstd, gamma, count, dz, dgamma, dbet
     coef = torch.empty(3 * C, dtype=torch.float32, device=dev)
     npix = z.N * z.H * z.W
     seed = int(seed) & 0xFFFFFFFF
-    check(L.b2s_bn_act_bwd_reduce(da.ptr, da.cstride, z.ptr, z.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
-                                  _p(partial), npix, C, int(relu), float(dropout_p), seed, _stream()),
-          "b2s_bn_act_bwd_reduce")
+    _timed("bn_act_bwd_reduce", "hbm", npix * C * 4.0, lambda: check(
+        L.b2s_bn_act_bwd_reduce(da.ptr, da.cstride, z.ptr, z.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
+                                _p(partial), npix, C, int(relu), float(dropout_p), seed, _stream()),
+        "b2s_bn_act_bwd_reduce"))
     check(L.b2s_bn_bwd_finalize(_p(partial), rows, C, float(count), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta),
                                 _p(coef), _p(scratch), _stream()), "b2s_bn_bwd_finalize")
-    check(L.b2s_bn_act_bwd_apply(da.ptr, da.cstride, z.ptr, z.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
-                                 _p(coef), dz.ptr, dz.cstride, _p(partial), npix, C, int(relu), float(dropout_p), seed,
-                                 _stream()), "b2s_bn_act_bwd_apply")
+    _timed("bn_act_bwd_apply", "hbm", npix * C * 6.0, lambda: check(
+        L.b2s_bn_act_bwd_apply(da.ptr, da.cstride, z.ptr, z.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
+                               _p(coef), dz.ptr, dz.cstride, _p(partial), npix, C, int(relu), float(dropout_p), seed,
+                               _stream()), "b2s_bn_act_bwd_apply"))
     check(L.b2s_reduce_rows(_p(partial), rows, C, _p(scratch), _p(dbias), _stream()), "b2s_reduce_rows")
 
 
@@ -453,7 +460,8 @@ def channel_sums(x, out):
     rows, C = L.b2s_ew_rows(), x.C
     partial = torch.empty(rows * C, dtype=torch.float32, device=out.device)
     scratch = torch.empty(128 * C, dtype=torch.float32, device=out.device)
-    check(L.b2s_channel_sums(x.ptr, x.cstride, _p(partial), x.N * x.H * x.W, C, _stream()), "b2s_channel_sums")
+    _timed("channel_sums", "hbm", x.N * x.H * x.W * C * 2.0, lambda: check(
+        L.b2s_channel_sums(x.ptr, x.cstride, _p(partial), x.N * x.H * x.W, C, _stream()), "b2s_channel_sums"))
     check(L.b2s_reduce_rows(_p(partial), rows, C, _p(scratch), _p(out), _stream()), "b2s_reduce_rows")
 
 
@@ -467,10 +475,12 @@ def se_forward(x, w1, b1, w2, b2, y):
     mean = torch.empty((N, C), dtype=torch.float32, device=dev)
     hidden = torch.empty((N, Cr), dtype=torch.float32, device=dev)
     gate = torch.empty((N, C), dtype=torch.float32, device=dev)
-    check(L.b2s_se_pool(x.ptr, x.cstride, None, 0, _p(partial), N, HW, C, _stream()), "b2s_se_pool")
+    _timed("se_pool", "hbm", N * HW * C * 2.0, lambda: check(
+        L.b2s_se_pool(x.ptr, x.cstride, None, 0, _p(partial), N, HW, C, _stream()), "b2s_se_pool"))
     check(L.b2s_se_fc_fwd(_p(partial), chunks, HW, _p(w1), _p(b1), _p(w2), _p(b2), _p(mean), _p(hidden), _p(gate), N, C,
                           Cr, _stream()), "b2s_se_fc_fwd")
-    check(L.b2s_se_scale(x.ptr, x.cstride, _p(gate), None, 0.0, y.ptr, y.cstride, N, HW, C, _stream()), "b2s_se_scale")
+    _timed("se_scale", "hbm", N * HW * C * 4.0, lambda: check(
+        L.b2s_se_scale(x.ptr, x.cstride, _p(gate), None, 0.0, y.ptr, y.cstride, N, HW, C, _stream()), "b2s_se_scale"))
     return mean, hidden, gate
 
 
@@ -485,9 +495,11 @@ def se_backward(dy, x, mean, hidden, gate, w1, w2, dx):
     ds, dh, dmean = torch.empty((N, C), **f32), torch.empty((N, Cr), **f32), torch.empty((N, C), **f32)
     dw1, db1 = torch.empty((Cr, C), **f32), torch.empty(Cr, **f32)
     dw2, db2 = torch.empty((C, Cr), **f32), torch.empty(C, **f32)
-    check(L.b2s_se_pool(dy.ptr, dy.cstride, x.ptr, x.cstride, _p(partial), N, HW, C, _stream()), "b2s_se_pool")
+    _timed("se_pool_dot", "hbm", N * HW * C * 4.0, lambda: check(
+        L.b2s_se_pool(dy.ptr, dy.cstride, x.ptr, x.cstride, _p(partial), N, HW, C, _stream()), "b2s_se_pool"))
     check(L.b2s_se_fc_bwd(_p(partial), chunks, _p(gate), _p(hidden), _p(mean), _p(w1), _p(w2), _p(ds), _p(dh),
                           _p(dmean), _p(dw1), _p(db1), _p(dw2), _p(db2), N, C, Cr, _stream()), "b2s_se_fc_bwd")
-    check(L.b2s_se_scale(dy.ptr, dy.cstride, _p(gate), _p(dmean), 1.0 / HW, dx.ptr, dx.cstride, N, HW, C, _stream()),
-          "b2s_se_scale")
+    _timed("se_scale_bwd", "hbm", N * HW * C * 4.0, lambda: check(
+        L.b2s_se_scale(dy.ptr, dy.cstride, _p(gate), _p(dmean), 1.0 / HW, dx.ptr, dx.cstride, N, HW, C, _stream()),
+        "b2s_se_scale"))
     return dw1, db1, dw2, db2

@@ -33,6 +33,25 @@ def as_act(t):
     return Act(base, c0, C)
 
 
+# Packed bf16 operands registered by the owning module (ImprovedVNet packs every conv weight of the network in a few
+# launches per step): data_ptr -> (version, w_fwd, w_dgrad). The nodes fall back to packing on the spot.
+PACKED = {}
+
+
+def packed_conv(w, want_dgrad):
+    e = PACKED.get(w.data_ptr())
+    if e is not None and e[0] == w._version and (e[2] is not None or not want_dgrad):
+        return e[1], e[2]
+    return ops.pack_conv_weight(w, want_dgrad=want_dgrad)
+
+
+def packed_convt(w):
+    e = PACKED.get(w.data_ptr())
+    if e is not None and e[0] == w._version:
+        return e[1], e[2]
+    return ops.pack_convt_weight(w)
+
+
 def new_act(N, H, W, C, device):
     return torch.empty((N, H, W, C), dtype=BF16, device=device)
 
@@ -73,7 +92,7 @@ class ConvBnAct(torch.autograd.Function):
             stats = torch.empty(rows * 2 * Cout, dtype=torch.float32, device=dev) if training else None
             ops.conv3x3_c1_fwd(x, w.detach(), b.detach(), za, relu=False, stats=stats)
         else:
-            wf, _ = ops.pack_conv_weight(w, want_dgrad=False)
+            wf, _ = packed_conv(w, False)
             rows = ops.conv_stats_rows(N, H, W, Cout)
             stats = torch.empty(rows * 2 * Cout, dtype=torch.float32, device=dev) if training else None
             ops.conv_fwd(xa, wf, b.detach(), za, ksize=3, relu=False, stats=stats)
@@ -116,7 +135,7 @@ class ConvBnAct(torch.autograd.Function):
             ws = torch.empty(nbytes // 4, **f32)
             ops.conv3x3_wgrad(xa, Act(dz), ws, dw)
             if ctx.needs_input_grad[0]:
-                _, wd = ops.pack_conv_weight(w, want_dgrad=True)
+                _, wd = packed_conv(w, True)
                 dx = new_act(N, H, W, Cin, dev)
                 ops.conv_fwd(Act(dz), wd, None, Act(dx), ksize=3)
         dres = dout if has_res else None
@@ -142,7 +161,7 @@ class Conv1x1(torch.autograd.Function):
         else:
             xa = as_act(x)
             N, H, W = xa.N, xa.H, xa.W
-            wf, _ = ops.pack_conv_weight(w, want_dgrad=False)
+            wf, _ = packed_conv(w, False)
             out = new_act(N, H, W, Cout, dev)
             ops.conv_fwd(xa, wf, b.detach(), Act(out), ksize=1)
         ctx.save_for_backward(x, w)
@@ -173,7 +192,7 @@ class Conv1x1(torch.autograd.Function):
             dw = torch.empty((Cout, Cin, 1, 1), **f32)
             ops.conv1x1_wgrad(xa, dy, dw)
             if ctx.needs_input_grad[0]:
-                _, wd = ops.pack_conv_weight(w, want_dgrad=True)
+                _, wd = packed_conv(w, True)
                 dx = new_act(N, H, W, Cin, dev)
                 ops.conv_fwd(dy, wd, None, Act(dx), ksize=1)
         return dx, dw, db
@@ -187,7 +206,7 @@ class ConvS2(torch.autograd.Function):
     def forward(ctx, x, w, b):
         xa = as_act(x)
         Cout = w.shape[0]
-        wf, _ = ops.pack_conv_weight(w, want_dgrad=False)
+        wf, _ = packed_conv(w, False)
         out = new_act(xa.N, xa.H // 2, xa.W // 2, Cout, w.device)
         ops.conv3x3_s2_fwd(xa, wf, b.detach(), Act(out))
         ctx.save_for_backward(x, w)
@@ -211,7 +230,7 @@ class ConvS2(torch.autograd.Function):
         ops.conv3x3_wgrad(xa, Act(up), ws, dw)
         dx = None
         if ctx.needs_input_grad[0]:
-            _, wd = ops.pack_conv_weight(w, want_dgrad=True)
+            _, wd = packed_conv(w, True)
             dx = new_act(xa.N, xa.H, xa.W, Cin, dev)
             ops.conv_fwd(Act(up), wd, None, Act(dx), ksize=3)
         return dx, dw, db
@@ -224,7 +243,7 @@ class ConvT2x2(torch.autograd.Function):
     def forward(ctx, x, w, b):
         xa = as_act(x)
         Cout = w.shape[1]
-        wf, _ = ops.pack_convt_weight(w)
+        wf, _ = packed_convt(w)
         out = new_act(xa.N, 2 * xa.H, 2 * xa.W, Cout, w.device)
         ops.convt_fwd(xa, wf, b.detach(), Act(out))
         ctx.save_for_backward(x, w)
@@ -246,7 +265,7 @@ class ConvT2x2(torch.autograd.Function):
         ops.convt_wgrad(xa, dy, ws, dw)
         dx = None
         if ctx.needs_input_grad[0]:
-            _, wd = ops.pack_convt_weight(w)
+            _, wd = packed_convt(w)
             dx = new_act(xa.N, xa.H, xa.W, Cin, dev)
             ops.convt_dgrad(dy, wd, Act(dx))
         return dx, dw, db

@@ -61,6 +61,19 @@ ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 ms = float(ms) / args.steps
+if rank == 0 and os.environ.get("VNET_PROFILE"):
+    from b200seg import ops as _ops
+    _ops.PROFILE = []
+    step(); torch.cuda.synchronize()
+    agg = {}
+    for n, k, w, s_, e_ in _ops.PROFILE:
+        a = agg.setdefault(n, [k, 0, 0.0, 0.0]); a[1] += 1; a[2] += s_.elapsed_time(e_); a[3] += w
+    _ops.PROFILE = None
+    tot = sum(a[2] for a in agg.values())
+    print(f"profiled kernel time {tot:.2f} ms", file=sys.stderr)
+    for n, a in sorted(agg.items(), key=lambda kv: -kv[1][2])[:45]:
+        rate = a[3] / (a[2] * 1e-3) / (1e12 if a[0] == "tensor" else 1e9)
+        print(f"{n:44s} {a[0]:6s} n={a[1]:3d} ms={a[2]:8.3f} {rate:8.1f} {'TF/s' if a[0]=='tensor' else 'GB/s'}", file=sys.stderr)
 if rank == 0:
     flops = 3894e9 * (args.size / 512) ** 2     # ~3 894 GFLOP per image per training step @512^2
     print(json.dumps({"model": "ImprovedVNet (models/vnet.py)", "n_gpus": world, "batch_per_gpu": args.batch, "image": f"1x{args.size}x{args.size}",
