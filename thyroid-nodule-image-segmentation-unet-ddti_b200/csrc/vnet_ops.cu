@@ -185,7 +185,7 @@ upsample_zero2x_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_b
 }
 
 // ---- squeeze-and-excitation (models/vnet.py:5-26) ------------------------------------------------------------
-constexpr int kSePixPerBlock = 2048;   // pixels of one sample reduced by one block
+constexpr int kSePixPerBlock = 256;    // pixels of one sample reduced by one block (small: deep levels have few pixels)
 
 // partial[n][chunk][C] = sum over the chunk's pixels of x (DOT: of x * y)
 template <bool DOT>

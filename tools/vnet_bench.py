@@ -24,6 +24,7 @@ ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--dropout", type=float, default=0.05)
+ap.add_argument("--graph", action="store_true", help="capture forward + loss + backward + AdamW in one CUDA graph (1 GPU)")
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -33,7 +34,7 @@ if world > 1:
 torch.manual_seed(42)
 net = ImprovedVNet(dropout_rate=args.dropout).to(dev).train()
 model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
-opt = torch.optim.AdamW(net.parameters(), lr=1e-5, fused=True)
+opt = torch.optim.AdamW(net.parameters(), lr=1e-5, fused=True, capturable=args.graph)
 crit = BCEDiceLoss()
 x, t = O.synth_batch(args.batch, args.size, args.size, seed=1234 + rank)
 x, t = x.to(dev), t.to(dev)
@@ -45,6 +46,28 @@ def step():
     opt.step()
     return loss
 
+graph = None
+if args.graph and world == 1:
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    opt.zero_grad(set_to_none=True)
+    l_cap = _lib.launch_count()
+    with torch.cuda.graph(graph):
+        static_loss = crit(model(x), t)
+        static_loss.backward()
+        opt.step()
+    captured_launches = _lib.launch_count() - l_cap
+    eager_step = step
+
+    def step():
+        graph.replay()
+        return static_loss
 for _ in range(args.warmup):
     step()
 torch.cuda.synchronize()
@@ -78,7 +101,7 @@ if rank == 0:
     flops = 3894e9 * (args.size / 512) ** 2     # ~3 894 GFLOP per image per training step @512^2
     print(json.dumps({"model": "ImprovedVNet (models/vnet.py)", "n_gpus": world, "batch_per_gpu": args.batch, "image": f"1x{args.size}x{args.size}",
                       "ms_per_step": ms, "images_per_s": world * args.batch / (ms * 1e-3), "algorithmic_tflops_per_gpu": args.batch * flops / (ms * 1e-3) / 1e12,
-                      "loss": float(loss), "libb2s_launches_per_step": (_lib.launch_count() - l0) / args.steps,
+                      "loss": float(loss), "libb2s_launches_per_step": captured_launches if graph is not None else (_lib.launch_count() - l0) / args.steps, "cuda_graph": graph is not None,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
 if world > 1:
     dist.destroy_process_group()
