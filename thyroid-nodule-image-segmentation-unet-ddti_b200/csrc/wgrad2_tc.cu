@@ -47,7 +47,7 @@ struct Wg2Cfg {
   static_assert(kDynBytes <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
-template <int BLOCK_N, int A_SLOTS, int STAGES>
+template <int BLOCK_N, int A_SLOTS, int STAGES, int MAXT>
 __global__ void __launch_bounds__(kWg2Threads, 1)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDz,
                   const WgHaloParams p) {
@@ -123,7 +123,10 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t desc_hi = static_cast<uint32_t>(proto >> 32);
       const uint32_t b_lo0 = static_cast<uint32_t>(proto) | ((16384u >> 4) << 16);   // dz: 64-channel panels 16 KB apart
       const uint32_t smem_lo = smem_u32(smem) >> 4;
-      constexpr int kMaxT = 512 / BLOCK_N;   // M tiles a CTA group can own (TMEM columns / BLOCK_N)
+      // MAXT = M tiles a CTA group of this instantiation can own. Kept tight: at BLOCK_N = 64 an MMA lasts 32 clocks
+      // and every predicated slot of the unrolled issue loop costs issue time.
+      constexpr int kMaxT = MAXT;
+      static_assert(MAXT * BLOCK_N <= 512, "accumulators exceed TMEM");
       uint32_t tl[kMaxT];
 #pragma unroll
       for (int t = 0; t < kMaxT; ++t) tl[t] = p.tile_lo[min(tile0 + t, kWgMaxTiles - 1)];
@@ -189,11 +192,11 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
-template <int BLOCK_N, int A_SLOTS, int STAGES>
+template <int BLOCK_N, int A_SLOTS, int STAGES, int MAXT>
 static int launch_wg2(int grid, const CUtensorMap& tmX, const CUtensorMap& tmDz, const WgHaloParams& p,
                       cudaStream_t stream) {
   using L = Wg2Cfg<BLOCK_N, A_SLOTS, STAGES>;
-  auto kfn = wgrad_halo_kernel<BLOCK_N, A_SLOTS, STAGES>;
+  auto kfn = wgrad_halo_kernel<BLOCK_N, A_SLOTS, STAGES, MAXT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes);
@@ -268,10 +271,14 @@ int launch_wgrad_halo(const void* x, int x_cstride, const void* dz, int dz_cstri
   if ((rc = make_act_map4(&tmX, x, Cin, W, H, N, x_cstride, 130, 1, 1))) return rc;
   if ((rc = make_act_map4(&tmDz, dz, Cout, W, H, N, dz_cstride, 128, 1, 1))) return rc;
   const int grid = groups * splits;
+  int max_tiles_group = 0;
+  for (int g = 0; g < groups; ++g)
+    if (p.g_ntiles[g] > max_tiles_group) max_tiles_group = p.g_ntiles[g];
   count_launch();
-  if (Cout == 64 && max_slots <= 3) return launch_wg2<64, 3, 3>(grid, tmX, tmDz, p, stream);
-  if (Cout == 64 && max_slots <= 4) return launch_wg2<64, 4, 2>(grid, tmX, tmDz, p, stream);
-  if (Cout == 128 && max_slots <= 2) return launch_wg2<128, 2, 3>(grid, tmX, tmDz, p, stream);
+  if (Cout == 64 && max_slots <= 3 && max_tiles_group <= 5) return launch_wg2<64, 3, 3, 5>(grid, tmX, tmDz, p, stream);
+  if (Cout == 64 && max_slots <= 4 && max_tiles_group <= 5) return launch_wg2<64, 4, 2, 5>(grid, tmX, tmDz, p, stream);
+  if (Cout == 64 && max_slots <= 4 && max_tiles_group <= 6) return launch_wg2<64, 4, 2, 6>(grid, tmX, tmDz, p, stream);
+  if (Cout == 128 && max_slots <= 2 && max_tiles_group <= 3) return launch_wg2<128, 2, 3, 3>(grid, tmX, tmDz, p, stream);
   return set_error(B2S_ERR_ARG, "wgrad halo kernel: no instantiation for this shape");
 }
 
