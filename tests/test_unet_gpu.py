@@ -375,3 +375,9 @@ def test_focal_tversky_gradient_with_global_sums():
     assert torch.allclose(torch.cat([d0, d1]), dl_full, rtol=1e-5, atol=1e-9)
     r = O.seg_loss(logits.double().cpu(), targets.double().cpu(), w_bce=0, w_dice=0, w_ft=1)
     assert float((dl_full.double().cpu() - r["dlogits"]).abs().max()) < 1e-6 * float(r["dlogits"].abs().max()) + 1e-9
+
+
+def test_graft_entry_smoke():
+    """the driver's round-end smoke (one small forward + loss + backward on cuda:0 checked against the oracle)"""
+    import __graft_entry__ as g
+    g.smoke()
