@@ -200,6 +200,14 @@ int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* z, int z_cs
                          const float* shift, const float* mean, const float* invstd, const float* coef, void* dz,
                          int dz_cstride, float* dbias_partial, long long npix, int C, int relu, float dropout_p,
                          unsigned seed, void* stream);
+/* models/mod.py variants (Conv -> BN -> ReLU blocks, ResidualBlock: relu(BN(conv) + skip), models/mod.py:43-51,71-84):
+ * b2s_bn_act_apply's `relu` argument is a mode: 0 none, 1 ReLU before the residual add (V-Net ConvBlock), 2 ReLU after it
+ * (ResidualBlock). b2s_relu_bwd: dx = dy * (y > 0) from the ReLU OUTPUT y. b2s_maxpool2x2_bwd: nn.MaxPool2d(2,2) backward,
+ * gradient to the first maximum of each window (x = the pooling input), dx dense. */
+int b2s_relu_bwd(const void* dy, int dy_cstride, const void* y, int y_cstride, void* dx, int dx_cstride, long long npix,
+                 int C, void* stream);
+int b2s_maxpool2x2_bwd(const void* x, int x_cstride, const void* dpool, int dpool_cstride, void* dx, int dx_cstride, int N,
+                       int H, int W, int C, void* stream);
 /* partial [b2s_ew_rows][C] = per-channel sums over pixels (bias gradient of a conv that is not followed by BN). */
 int b2s_channel_sums(const void* x, int x_cstride, float* partial, long long npix, int C, void* stream);
 

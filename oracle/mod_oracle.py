@@ -1,0 +1,73 @@
+"""ORACLE (test infrastructure, not product code) — CPU restatement of the reference's models/mod.py UNet and ResUNet.
+
+Only tests/ may import this module. Elementary tensor algebra from unet_oracle.py (shift + einsum convolutions, explicit
+BatchNorm formulas); gradients come from autograd over these elementary ops. Pinned against the unmodified reference by
+oracle/make_golden_mod.py -> tests/golden/mod_golden.pt.
+
+Call sites restated (reference file:line):
+  UNet._block / forward          models/mod.py:43-66   (conv(bias=False) -> BN -> ReLU, twice; cat([skip, x]))
+  ResidualBlock.forward          models/mod.py:83-84   (relu(BN(conv(relu(BN(conv x)))) + skip_1x1(x)))
+  ResUNet.forward                models/mod.py:119-131
+  nn.MaxPool2d(2,2)              models/mod.py:27,104  (first maximum in row-major window order)
+"""
+import torch
+
+from . import unet_oracle as O
+from .vnet_oracle import bn_train_or_eval
+
+
+def maxpool_first(x):
+    """2x2/2 max-pool selecting the FIRST maximum of each window (differentiable through the selected element)"""
+    N, C, H, W = x.shape
+    win = torch.stack([x[:, :, 0::2, 0::2], x[:, :, 0::2, 1::2], x[:, :, 1::2, 0::2], x[:, :, 1::2, 1::2]], dim=-1)
+    best = win[..., 0]
+    arg = torch.zeros_like(best, dtype=torch.long)
+    for q in range(1, 4):
+        better = win[..., q] > best
+        best = torch.where(better, win[..., q], best)
+        arg = torch.where(better, torch.full_like(arg, q), arg)
+    return torch.gather(win, -1, arg.unsqueeze(-1)).squeeze(-1)
+
+
+def _cbr(P, conv, bn, x, train, q, w_round, relu=True, stats_out=None):
+    z = q(O.conv3x3(x, w_round(P[f"{conv}.weight"]), None))
+    y = bn_train_or_eval(z, P, bn, train, stats_out)
+    return torch.clamp_min(y, 0) if relu else y
+
+
+def plain_block(P, prefix, x, train, q, first, stats_out=None):
+    """models/mod.py:43-51"""
+    wr = (lambda w: w) if first else q
+    a = q(_cbr(P, f"{prefix}.0", f"{prefix}.1", x, train, q, wr, True, stats_out))
+    return q(_cbr(P, f"{prefix}.3", f"{prefix}.4", a, train, q, q, True, stats_out))
+
+
+def residual_block(P, prefix, x, train, q, first, stats_out=None):
+    """models/mod.py:71-84"""
+    wr = (lambda w: w) if first else q
+    s = q(O.conv1x1(x, wr(P[f"{prefix}.skip.weight"]), None))
+    a = q(_cbr(P, f"{prefix}.conv.0", f"{prefix}.conv.1", x, train, q, wr, True, stats_out))
+    y = _cbr(P, f"{prefix}.conv.3", f"{prefix}.conv.4", a, train, q, q, False, stats_out)
+    return q(torch.clamp_min(y + s, 0))
+
+
+def _net(P, x, depth, train, q, block, stats_out):
+    skips = []
+    for i in range(depth):
+        x = block(P, f"encoders.{i}", x, train, q, i == 0, stats_out)
+        skips.append(x)
+        x = maxpool_first(x)
+    x = block(P, "bottleneck", x, train, q, False, stats_out)
+    for i, skip in enumerate(reversed(skips)):
+        x = q(O.conv_transpose2x2(x, q(P[f"upconvs.{i}.weight"]), P[f"upconvs.{i}.bias"]))
+        x = torch.cat([skip, x], dim=1)
+        x = block(P, f"decoders.{i}", x, train, q, False, stats_out)
+    return O.conv1x1(x, P["final_conv.weight"], P["final_conv.bias"])
+
+
+def resunet_forward(P, x, depth, train=True, q=O.identity, stats_out=None):
+    return _net(P, x, depth, train, q, residual_block, stats_out)
+
+
+def unet_forward(P, x, depth, train=True, q=O.identity, stats_out=None):
+    return _net(P, x, depth, train, q, plain_block, stats_out)

@@ -1,0 +1,111 @@
+"""models/mod.py variants on the B200 path against the CPU oracle (oracle/mod_oracle.py) and the reference goldens:
+max-pool backward and ReLU-after-add kernels, then whole-net train step and eval masks of ResUNet and UNet (depth 3)."""
+import os
+
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+from oracle import mod_oracle as M
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mod_golden.pt")
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(DEV)
+
+
+def nchw(y):
+    return y.permute(0, 3, 1, 2).float().cpu()
+
+
+def test_maxpool_forward_backward_first_max():
+    import b200seg  # noqa: F401
+    from b200seg import vnet_functional as VF
+    g = torch.Generator().manual_seed(1)
+    x = torch.randint(0, 3, (2, 64, 8, 12), generator=g).float()      # many exact ties
+    dp = torch.randn((2, 64, 4, 6), generator=g).to(torch.bfloat16).float()
+    xg = nhwc(x).requires_grad_(True)
+    y = VF.MaxPool2x2.apply(xg)
+    y.backward(nhwc(dp))
+    torch.cuda.synchronize()
+    xr = x.double().requires_grad_(True)
+    yr = M.maxpool_first(xr)
+    yr.backward(dp.double())
+    assert torch.equal(nchw(y.detach()).double(), yr.detach())
+    assert torch.equal(nchw(xg.grad).double(), xr.grad)
+    tr = x.clone().requires_grad_(True)                               # and torch's own max_pool2d agrees
+    torch.nn.functional.max_pool2d(tr, 2).backward(dp)
+    assert torch.equal(nchw(xg.grad), tr.grad)
+
+
+def test_residual_block_forward_backward():
+    import b200seg  # noqa: F401
+    from b200seg.models.mod import ResidualBlock
+    torch.manual_seed(3)
+    blk = ResidualBlock(128, 64).train()
+    sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((2, 128, 16, 16), generator=g).to(torch.bfloat16).float()
+    dy = torch.randn((2, 64, 16, 16), generator=g).to(torch.bfloat16).float()
+    blk = blk.to(DEV)
+    xg = nhwc(x).requires_grad_(True)
+    y = blk.forward_nhwc(xg)
+    y.backward(nhwc(dy))
+    torch.cuda.synchronize()
+    P = {f"b.{k}": (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    xr = x.double().requires_grad_(True)
+    yr = M.residual_block(P, "b", xr, True, O.bf16_round, False)
+    yr.backward(dy.double())
+    err = (nchw(y.detach()).double() - yr.detach()).abs()
+    assert float(err.max()) < 2 ** -7 * float(yr.abs().max()) + 1e-2
+    rel = float((nchw(xg.grad).double() - xr.grad).norm() / xr.grad.norm())
+    assert rel < 0.03, f"dx rel L2 {rel}"
+    for k, p in blk.named_parameters():
+        ref = P[f"b.{k}"].grad
+        rel = float((p.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
+        assert rel < 0.05, f"{k}: rel L2 {rel}"
+
+
+@pytest.mark.parametrize("name", ["ResUNet", "UNet"])
+def test_whole_net_train_step_and_eval_mask(name):
+    import b200seg  # noqa: F401
+    from b200seg.models import mod
+    from b200seg.models.loss import BCEDiceLoss
+    g = torch.load(GOLDEN, weights_only=False)[name]
+    torch.manual_seed(42)
+    net = getattr(mod, name)(depth=3)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV).train()
+    logits = net(g["x"].to(DEV))
+    loss = BCEDiceLoss()(logits, g["t"].to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    P = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    fwd = M.resunet_forward if name == "ResUNet" else M.unet_forward
+    lq = fwd(P, g["x"].double(), 3, train=True, q=O.bf16_round)
+    Lq = O.seg_loss(lq.detach(), g["t"].double())
+    assert float((logits.detach().cpu().double() - lq.detach()).abs().mean()) < 1e-2
+    assert float((logits.detach().cpu() - g["logits"]).abs().mean()) < 3e-2
+    assert abs(float(loss) - float(Lq["total"])) < 2e-3 and abs(float(loss) - (g["bce"] + g["dice"])) < 5e-3
+    lq.backward(Lq["dlogits"])
+    stats = {}
+    for k, p in net.named_parameters():
+        ref = P[k].grad
+        gg = p.grad.double().cpu()
+        stats[k] = (float((gg - ref).norm() / (ref.norm() + 1e-30)), float((gg * ref).sum() / (gg.norm() * ref.norm() + 1e-30)))
+    rels = sorted(v[0] for v in stats.values()); coss = sorted(v[1] for v in stats.values())
+    # statistical bar (bf16 storage of activations and gradients vs the fp64 oracle; see tests/test_vnet_gpu.py), tight
+    # next to the loss
+    assert rels[len(rels) // 2] < 0.3 and coss[len(coss) // 2] > 0.95 and coss[0] > 0.75, (rels[len(rels) // 2], coss[0])
+    assert stats["final_conv.weight"][0] < 0.03, stats["final_conv.weight"]
+    net.eval()
+    with torch.no_grad():
+        le = net(g["x"].to(DEV)).cpu()
+    assert float((le - g["eval_logits"]).abs().mean()) < 3e-2
+    band = g["eval_logits"].abs() > 0.1
+    assert bool(((torch.sigmoid(le) > 0.5)[band] == g["eval_mask"][band]).all())

@@ -29,7 +29,8 @@ __device__ __forceinline__ uint32_t drop_keep8(unsigned long long idx8, uint32_t
   return mask;
 }
 
-// out = dropout(relu(z * scale + shift)) + res      (models/vnet.py:51-59)
+// relu == 1: out = dropout(relu(z * scale + shift)) + res      (models/vnet.py:51-59)
+// relu == 2: out = relu(z * scale + shift + res)                (ResidualBlock, models/mod.py:84);  relu == 0: no ReLU
 __global__ void __launch_bounds__(kThreads)
 bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* __restrict__ scale,
                     const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_cs,
@@ -53,9 +54,10 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float a = fmaf(v[k], sc[k], sh[k]);
-      if (relu) a = fmaxf(a, 0.f);
+      if (relu == 1) a = fmaxf(a, 0.f);
       if (drop_thresh) a = (keep >> k) & 1u ? a * drop_scale : 0.f;
       if (res) a += rr[k];
+      if (relu == 2) a = fmaxf(a, 0.f);
       v[k] = a;
     }
     stg16(out + pix * out_cs + cg * 8, pack8(v));
@@ -99,7 +101,7 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
     for (int k = 0; k < 8; ++k) {
       float d = g[k];
       if (drop_thresh) d = (keep >> k) & 1u ? d * drop_scale : 0.f;
-      if (relu && !(fmaf(zv[k], sc[k], sh[k]) > 0.f)) d = 0.f;
+      if (relu == 1 && !(fmaf(zv[k], sc[k], sh[k]) > 0.f)) d = 0.f;
       const float xh = (zv[k] - mu[k]) * is[k];
       if (!APPLY) {
         acc[k] += d;
@@ -181,6 +183,62 @@ upsample_zero2x_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_b
     uint4 v = make_uint4(0, 0, 0, 0);
     if (!(h & 1) && !(w & 1)) v = ldg16(src + ((n * Hs + (h >> 1)) * Ws + (w >> 1)) * src_cs + cg * 8);
     stg16(dst + pix * dst_cs + cg * 8, v);
+  }
+}
+
+// dx = dy * (y > 0): gradient through a ReLU given its OUTPUT (ResidualBlock's ReLU after the add, models/mod.py:84)
+__global__ void __launch_bounds__(kThreads)
+relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat16* __restrict__ y, int y_cs,
+                __nv_bfloat16* __restrict__ dx, int dx_cs, long long npix, int C) {
+  const int groups = C / 8;
+  const long long total = npix * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int cg = static_cast<int>(i % groups);
+    const long long pix = i / groups;
+    float g[8], v[8];
+    unpack8(ldg16(dy + pix * dy_cs + cg * 8), g);
+    unpack8(ldg16(y + pix * y_cs + cg * 8), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = v[k] > 0.f ? g[k] : 0.f;
+    stg16(dx + pix * dx_cs + cg * 8, pack8(g));
+  }
+}
+
+// F.max_pool2d(x, 2) backward: the whole gradient goes to the FIRST maximum of each 2x2 window in row-major order
+// (torch semantics); dx is written densely (zeros elsewhere).
+__global__ void __launch_bounds__(kThreads)
+maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat16* __restrict__ dpool, int dp_cs,
+                      __nv_bfloat16* __restrict__ dx, int dx_cs, int N, int H, int W, int C) {
+  const int groups = C / 8;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(N) * Ho * Wo * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int cg = static_cast<int>(i % groups);
+    const long long pp = i / groups;
+    const int wo = static_cast<int>(pp % Wo);
+    const long long t = pp / Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    const long long p00 = (n * H + 2 * ho) * W + 2 * wo;
+    float v[4][8], dp[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) unpack8(ldg16(x + (p00 + (q >> 1) * W + (q & 1)) * x_cs + cg * 8), v[q]);
+    unpack8(ldg16(dpool + pp * dp_cs + cg * 8), dp);
+    float o[4][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int arg = 0;
+      float best = v[0][k];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q][k] > best) { best = v[q][k]; arg = q; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q][k] = arg == q ? dp[k] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) stg16(dx + (p00 + (q >> 1) * W + (q & 1)) * dx_cs + cg * 8, pack8(o[q]));
   }
 }
 
@@ -425,6 +483,30 @@ extern "C" int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* 
       mean, invstd, coef, static_cast<__nv_bfloat16*>(dz), dz_cstride, dbias_partial, npix, C, relu,
       drop_threshold(dropout_p), drop_scale_of(dropout_p), seed);
   return check_launch("bn_act_bwd_kernel<apply>");
+}
+
+extern "C" int b2s_relu_bwd(const void* dy, int dy_cstride, const void* y, int y_cstride, void* dx, int dx_cstride,
+                            long long npix, int C, void* stream) {
+  if (!dy || !y || !dx) return set_error(B2S_ERR_ARG, "b2s_relu_bwd: null pointer");
+  if (C % 8 || dy_cstride % 8 || y_cstride % 8 || dx_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_relu_bwd: need multiples of 8");
+  count_launch();
+  relu_bwd_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), dy_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride,
+      static_cast<__nv_bfloat16*>(dx), dx_cstride, npix, C);
+  return check_launch("relu_bwd_kernel");
+}
+
+extern "C" int b2s_maxpool2x2_bwd(const void* x, int x_cstride, const void* dpool, int dpool_cstride, void* dx,
+                                  int dx_cstride, int N, int H, int W, int C, void* stream) {
+  if (!x || !dpool || !dx) return set_error(B2S_ERR_ARG, "b2s_maxpool2x2_bwd: null pointer");
+  if (C % 8 || x_cstride % 8 || dpool_cstride % 8 || dx_cstride % 8 || H % 2 || W % 2)
+    return set_error(B2S_ERR_ARG, "b2s_maxpool2x2_bwd: need C % 8 == 0, even H and W");
+  const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
+  count_launch();
+  maxpool2x2_bwd_kernel<<<ew_grid_for(items, kThreads * 2), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(dpool), dpool_cstride,
+      static_cast<__nv_bfloat16*>(dx), dx_cstride, N, H, W, C);
+  return check_launch("maxpool2x2_bwd_kernel");
 }
 
 extern "C" int b2s_channel_sums(const void* x, int x_cstride, float* partial, long long npix, int C, void* stream) {

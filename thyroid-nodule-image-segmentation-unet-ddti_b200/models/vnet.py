@@ -85,7 +85,7 @@ class ConvBlock(nn.Module):
         for i, (conv, bn) in enumerate(zip(self.convs, self.bns)):
             res = residual if i == n - 1 else None       # the residual add is fused into the last stage's apply pass
             x = VF.ConvBnAct.apply(x, res, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                   bn.num_batches_tracked, self.training, p, _next_seed() if (self.training and p > 0) else 0)
+                                   bn.num_batches_tracked, self.training, p, _next_seed() if (self.training and p > 0) else 0, 1)
         return x
 
     def forward(self, x):

@@ -454,6 +454,18 @@ def bn_act_bwd(da, z, scale, shift, mean, invstd, gamma, count, dz, dgamma, dbet
     check(L.b2s_reduce_rows(_p(partial), rows, C, _p(scratch), _p(dbias), _stream()), "b2s_reduce_rows")
 
 
+def relu_bwd(dy, y, dx):
+    _timed("relu_bwd", "hbm", y.N * y.H * y.W * y.C * 6.0, lambda: check(
+        _lib.lib().b2s_relu_bwd(dy.ptr, dy.cstride, y.ptr, y.cstride, dx.ptr, dx.cstride, y.N * y.H * y.W, y.C, _stream()),
+        "b2s_relu_bwd"))
+
+
+def maxpool2x2_bwd(x, dpool, dx):
+    _timed("maxpool2x2_bwd", "hbm", x.N * x.H * x.W * x.C * 4.5, lambda: check(
+        _lib.lib().b2s_maxpool2x2_bwd(x.ptr, x.cstride, dpool.ptr, dpool.cstride, dx.ptr, dx.cstride, x.N, x.H, x.W, x.C,
+                                      _stream()), "b2s_maxpool2x2_bwd"))
+
+
 def channel_sums(x, out):
     """out [C] fp32 = sum over pixels of x (Act)"""
     L = _lib.lib()

@@ -75,8 +75,11 @@ class ConvBnAct(torch.autograd.Function):
     x: NHWC bf16 activation, or the fp32 image [N,1,H,W] for the first conv of a branch (Cin = 1 kernel)."""
 
     @staticmethod
-    def forward(ctx, x, res, w, b, gamma, beta, rm, rv, nbt, training, p_drop, seed):
+    def forward(ctx, x, res, w, b, gamma, beta, rm, rv, nbt, training, p_drop, seed, relu_mode=1):
+        """relu_mode 1: ReLU before the residual add (V-Net ConvBlock); 2: after it (ResidualBlock, models/mod.py:84);
+        b may be None (bias=False convs of models/mod.py)."""
         dev = w.device
+        bias = b.detach() if b is not None else None
         Cout = w.shape[0]
         first = x.dtype == torch.float32
         if first:
@@ -90,26 +93,26 @@ class ConvBnAct(torch.autograd.Function):
         if first:
             rows = ops.c1_rows(N, H, W)
             stats = torch.empty(rows * 2 * Cout, dtype=torch.float32, device=dev) if training else None
-            ops.conv3x3_c1_fwd(x, w.detach(), b.detach(), za, relu=False, stats=stats)
+            ops.conv3x3_c1_fwd(x, w.detach(), bias, za, relu=False, stats=stats)
         else:
             wf, _ = packed_conv(w, False)
             rows = ops.conv_stats_rows(N, H, W, Cout)
             stats = torch.empty(rows * 2 * Cout, dtype=torch.float32, device=dev) if training else None
-            ops.conv_fwd(xa, wf, b.detach(), za, ksize=3, relu=False, stats=stats)
+            ops.conv_fwd(xa, wf, bias, za, ksize=3, relu=False, stats=stats)
         scale, shift, mean, invstd = _bn_affine(training, stats, rows, float(N * H * W), gamma.detach(), beta.detach(),
                                                 rm, rv, nbt, Cout, dev)
         out = new_act(N, H, W, Cout, dev)
-        ops.bn_act_apply(za, scale, shift, as_act(res) if res is not None else None, Act(out), relu=True,
+        ops.bn_act_apply(za, scale, shift, as_act(res) if res is not None else None, Act(out), relu=relu_mode,
                          dropout_p=p_drop if training else 0.0, seed=seed)
         ctx.save_for_backward(x, z, w, gamma, scale, shift, mean if mean is not None else scale,
-                              invstd if invstd is not None else scale)
-        ctx.cfg = (first, training, p_drop, seed, res is not None)
+                              invstd if invstd is not None else scale, out if relu_mode == 2 else scale)
+        ctx.cfg = (first, training, p_drop, seed, res is not None, relu_mode, b is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, z, w, gamma, scale, shift, mean, invstd = ctx.saved_tensors
-        first, training, p_drop, seed, has_res = ctx.cfg
+        x, z, w, gamma, scale, shift, mean, invstd, out_saved = ctx.saved_tensors
+        first, training, p_drop, seed, has_res, relu_mode, has_bias = ctx.cfg
         if not training:
             raise RuntimeError("b200seg V-Net: backward through eval-mode BatchNorm is not implemented")
         dev = w.device
@@ -117,11 +120,15 @@ class ConvBnAct(torch.autograd.Function):
         za = Act(z)
         N, H, W = za.N, za.H, za.W
         da = as_act(dout)
+        if relu_mode == 2:     # ReLU after the add: mask the incoming gradient with the saved output once, for both branches
+            dmasked = new_act(N, H, W, Cout, dev)
+            ops.relu_bwd(da, Act(out_saved), Act(dmasked))
+            dout, da = dmasked, Act(dmasked)
         f32 = dict(dtype=torch.float32, device=dev)
         dz = new_act(N, H, W, Cout, dev)
         dgamma, dbeta, dbias = torch.empty(Cout, **f32), torch.empty(Cout, **f32), torch.empty(Cout, **f32)
         ops.bn_act_bwd(da, za, scale, shift, mean, invstd, gamma.detach(), float(N * H * W), Act(dz), dgamma, dbeta,
-                       dbias, relu=True, dropout_p=p_drop, seed=seed)
+                       dbias, relu=1 if relu_mode == 1 else 0, dropout_p=p_drop, seed=seed)
         dw = torch.empty((Cout, Cin, 3, 3), **f32)
         dx = None
         if first:
@@ -139,7 +146,7 @@ class ConvBnAct(torch.autograd.Function):
                 dx = new_act(N, H, W, Cin, dev)
                 ops.conv_fwd(Act(dz), wd, None, Act(dx), ksize=3)
         dres = dout if has_res else None
-        return dx, dres, dw, dbias, dgamma, dbeta, None, None, None, None, None, None
+        return dx, dres, dw, (dbias if has_bias else None), dgamma, dbeta, None, None, None, None, None, None, None
 
 
 class Conv1x1(torch.autograd.Function):
@@ -157,15 +164,16 @@ class Conv1x1(torch.autograd.Function):
             w3 = torch.zeros((Cout, 1, 3, 3), dtype=torch.float32, device=dev)
             w3[:, :, 1, 1] = w.detach()[:, :, 0, 0]
             out = new_act(N, H, W, Cout, dev)
-            ops.conv3x3_c1_fwd(x, w3, b.detach(), Act(out), relu=False, stats=None)
+            ops.conv3x3_c1_fwd(x, w3, b.detach() if b is not None else None, Act(out), relu=False, stats=None)
         else:
             xa = as_act(x)
             N, H, W = xa.N, xa.H, xa.W
             wf, _ = packed_conv(w, False)
             out = new_act(N, H, W, Cout, dev)
-            ops.conv_fwd(xa, wf, b.detach(), Act(out), ksize=1)
+            ops.conv_fwd(xa, wf, b.detach() if b is not None else None, Act(out), ksize=1)
         ctx.save_for_backward(x, w)
         ctx.first = first
+        ctx.has_bias = b is not None
         return out
 
     @staticmethod
@@ -176,8 +184,10 @@ class Conv1x1(torch.autograd.Function):
         dy = as_act(dout)
         N, H, W = dy.N, dy.H, dy.W
         f32 = dict(dtype=torch.float32, device=dev)
-        db = torch.empty(Cout, **f32)
-        ops.channel_sums(dy, db)
+        db = None
+        if ctx.has_bias:
+            db = torch.empty(Cout, **f32)
+            ops.channel_sums(dy, db)
         dx = None
         if ctx.first:
             dyc = Act(dout.contiguous()) if dy.c0 or dy.cstride != dy.C else dy
@@ -293,6 +303,26 @@ class SE(torch.autograd.Function):
         dw1, db1, dw2, db2 = ops.se_backward(dy, xa, mean, hidden, gate, w1m, w2m, Act(dx))
         Cr, C = dw1.shape
         return dx, dw1.view(Cr, C, 1, 1), db1, dw2.view(C, Cr, 1, 1), db2
+
+
+class MaxPool2x2(torch.autograd.Function):
+    """nn.MaxPool2d(2, 2) (models/mod.py:27): backward routes the gradient to the first maximum of each window"""
+
+    @staticmethod
+    def forward(ctx, x):
+        xa = as_act(x)
+        out = new_act(xa.N, xa.H // 2, xa.W // 2, xa.C, x.device)
+        ops.maxpool2x2(xa, Act(out))
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        xa = as_act(x)
+        dx = new_act(xa.N, xa.H, xa.W, xa.C, x.device)
+        ops.maxpool2x2_bwd(xa, as_act(dout), Act(dx))
+        return dx
 
 
 class Cat(torch.autograd.Function):
