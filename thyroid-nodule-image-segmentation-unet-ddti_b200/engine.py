@@ -130,8 +130,7 @@ class UNetEngine:
     def __init__(self, out_channels=1):
         self.O = out_channels
         self.plans = {}
-        self._packed_versions = None
-        self._packed = {}
+        self._pack_state = {}
 
     # ---- plumbing -----------------------------------------------------------------------------------------
     def plan(self, N, H, W, device, train):
@@ -147,27 +146,31 @@ class UNetEngine:
     def invalidate_packed(self):
         """Call after parameters were updated outside torch (e.g. by b2s_adamw_step, which does not bump tensor
         version counters): forces the next forward to re-pack the bf16 operands."""
-        self._packed_versions = None
+        for st in self._pack_state.values():
+            st["versions"] = None
 
     def _pack_weights(self, P, need_dgrad):
         """fp32 parameters -> bf16 GEMM operands, all tensors in one launch; skipped while the parameters' version
-        counters and addresses are unchanged."""
+        counters and addresses are unchanged. State is kept per device: nn.DataParallel (utils/trainer.py:30) runs
+        replicas of one module — sharing this engine object — concurrently, one thread per GPU."""
         names = [k for k in P if k.endswith(".weight") and P[k].dim() == 4 and k != "encoder1.0.weight"
                  and k != "final.1.weight"]
+        dev = str(P[names[0]].device)
+        st = self._pack_state.setdefault(dev, {"versions": None, "layout": None, "plan": None})
         versions = tuple((k, P[k]._version, P[k].data_ptr(), need_dgrad) for k in names)
-        if versions == self._packed_versions:
-            return
+        if versions == st["versions"]:
+            return st["plan"].packed
         layout = tuple((k, P[k].data_ptr(), need_dgrad) for k in names)
-        if getattr(self, "_pack_layout", None) != layout:
+        if st["layout"] != layout:
             items = []
             for k in names:
                 is_convt = k.split(".")[0] in ("middle", "decoder3", "decoder2", "decoder1") and P[k].shape[2] == 2
                 items.append((k, P[k].detach(), is_convt))
-            self._pack_plan = ops.PackPlan(items, want_dgrad=need_dgrad)
-            self._packed = self._pack_plan.packed
-            self._pack_layout = layout
-        self._pack_plan.run()
-        self._packed_versions = versions
+            st["plan"] = ops.PackPlan(items, want_dgrad=need_dgrad)
+            st["layout"] = layout
+        st["plan"].run()
+        st["versions"] = versions
+        return st["plan"].packed
 
     # ---- forward ----------------------------------------------------------------------------------------------
     def forward(self, P, x, train, want_mask=False, need_backward=None):
@@ -182,7 +185,7 @@ class UNetEngine:
         pl.generation += 1
         x = x.contiguous().float()
         pl.x = x
-        self._pack_weights(P, need_dgrad=need_backward)
+        pl.packed = self._pack_weights(P, need_dgrad=need_backward)
         count = lambda l: float(N * pl.dims[l][0] * pl.dims[l][1])
 
         def stage(name, idx, xin, pooled=None):
@@ -193,7 +196,7 @@ class UNetEngine:
                 # inference: running-statistics BatchNorm applied in the conv epilogue, no separate BN pass
                 ops.bn_eval_affine(P[f"{bn}.weight"], P[f"{bn}.bias"], P[f"{bn}.running_mean"],
                                    P[f"{bn}.running_var"], BN_EPS, s.scale, s.shift)
-                wf, _ = self._packed[f"{name}.{idx}.weight"]
+                wf, _ = pl.packed[f"{name}.{idx}.weight"]
                 ops.conv_fwd_affine(xin, wf, P[f"{name}.{idx}.bias"], s.scale, s.shift, s.y, ksize=3, relu=True)
                 if pooled is not None:
                     ops.maxpool2x2(s.y, pooled)
@@ -203,7 +206,7 @@ class UNetEngine:
                                    stats=pl.stats_partial if train else None)
                 rows = ops.c1_rows(N, H, W)
             else:
-                wf, _ = self._packed[f"{name}.{idx}.weight"]
+                wf, _ = pl.packed[f"{name}.{idx}.weight"]
                 ops.conv_fwd(xin, wf, P[f"{name}.{idx}.bias"], s.r, ksize=3, relu=True,
                              stats=pl.stats_partial if train else None)
                 rows = ops.conv_stats_rows(N, s.r.H, s.r.W, s.cout)
@@ -229,7 +232,7 @@ class UNetEngine:
         s = block("middle.1", cur)
         for l in (3, 2, 1, 0):
             ct = CONVT_INTO[l]
-            wf, _ = self._packed[f"{ct}.weight"]
+            wf, _ = pl.packed[f"{ct}.weight"]
             C = pl.dims[l][2]
             ops.convt_fwd(s.y, wf, P[f"{ct}.bias"], pl.cat[l].slice(0, C))
             s = block(DEC[l] if l else "final.0", pl.cat[l])
@@ -275,7 +278,7 @@ class UNetEngine:
                 return
             ops.conv3x3_wgrad(s.x, dz, pl.wgrad_ws, G[wname])
             ready(wname)
-            _, wd = self._packed[wname]
+            _, wd = pl.packed[wname]
             ops.conv_fwd(dz, wd, None, dx_out, ksize=3, relu=False, stats=pl.stats_partial if dx_stats else None)
 
         def block_bwd(name, dy1, dx_out, dpool=None, dx_stats=False):
@@ -306,7 +309,7 @@ class UNetEngine:
             dY = pl.dcat[l].slice(0, C)
             ops.convt_wgrad(up_in, dY, pl.wgrad_ws, G[f"{ct}.weight"])
             ready(f"{ct}.weight")
-            _, wd = self._packed[f"{ct}.weight"]
+            _, wd = pl.packed[f"{ct}.weight"]
             ops.convt_dgrad(dY, wd, pl.ga[l + 1])
             dy = pl.ga[l + 1]
         block_bwd("middle.1", dy, pl.dpool[3])

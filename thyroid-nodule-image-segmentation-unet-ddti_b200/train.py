@@ -139,16 +139,20 @@ class TrainStep:
     # ~230 kernel launches per step cost more host time than the GPU needs to run them at batch 64; the graph removes
     # the host from the loop. Everything that changes between steps lives in device memory: the batch (copied into
     # static input buffers), BatchNorm counters (updated in-kernel), and the AdamW scalars (lr, bias corrections),
-    # an 8-float device vector refreshed by a stream-ordered copy from pageable host memory before each replay
-    # (staged by the driver at call time, so the host may run ahead safely).
+    # an 8-float device vector refreshed before each replay by an asynchronous copy from a small ring of pinned host
+    # vectors (a slot is reused only after the copy that read it has completed, so the host may run ahead).
     def _write_hyper(self, lr):
         self.step_count += 1
         # betas rounded to fp32 first: the same double-precision bias corrections b2s_adamw_step derives from its
         # float arguments, so the graphed and the host-launched step stay bit-identical
         b1, b2 = (torch.tensor(b, dtype=torch.float32).item() for b in self.betas)
-        h = torch.tensor([lr if lr is not None else self.lr, b1, b2, self.eps, self.wd, 1.0 - b1 ** self.step_count,
-                          math.sqrt(1.0 - b2 ** self.step_count), 1.0 / self.world], dtype=torch.float32)
-        self._hyper_dev.copy_(h)
+        i = self.step_count % len(self._hyper_ring)
+        h, ev = self._hyper_ring[i]
+        ev.synchronize()
+        h[0], h[1], h[2], h[3], h[4] = lr if lr is not None else self.lr, b1, b2, self.eps, self.wd
+        h[5], h[6], h[7] = 1.0 - b1 ** self.step_count, math.sqrt(1.0 - b2 ** self.step_count), 1.0 / self.world
+        self._hyper_dev.copy_(h, non_blocking=True)
+        ev.record()
 
     def _graph_body(self):
         # Single GPU: the whole step is one graph. Data parallel: the graph ends after backward; the gradient
@@ -166,6 +170,7 @@ class TrainStep:
         from . import _lib
         self._gx, self._gt = torch.empty_like(x), torch.empty_like(t)
         self._hyper_dev = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._hyper_ring = [(torch.zeros(8, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
         self._graph = None
         for _ in range(2):
             self.step(x, t)
