@@ -89,6 +89,9 @@ int b2s_pack_weights_all(int n, const void* const* w, void* const* wf, void* con
 int b2s_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, void* r, float* stats_partial, int N, int H,
                        int W, int Cout, int flags, void* stream);
 int b2s_c1_rows(int N, int H, int W);
+/* inference variant: y = act(conv(x) + bias) * post_scale + post_shift (eval-mode BatchNorm in the same pass). */
+int b2s_conv3x3_c1_fwd_affine(const float* x, const float* w, const float* bias, const float* post_scale,
+                              const float* post_shift, void* y, int N, int H, int W, int Cout, int flags, void* stream);
 /* its weight gradient: partial [b2s_c1_rows][Cout*9] fp32 (reduce with b2s_reduce_rows). */
 int b2s_conv3x3_c1_wgrad(const float* x, const void* dz, float* partial, int N, int H, int W, int Cout, void* stream);
 

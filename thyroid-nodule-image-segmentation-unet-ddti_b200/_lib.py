@@ -36,6 +36,7 @@ SIGNATURES = {
     "b2s_pack_weights_all": (I, [I, P, P, P, P, P, P, P, P]),
     "b2s_conv3x3_c1_fwd": (I, [P, P, P, P, P, I, I, I, I, I, P]),
     "b2s_c1_rows": (I, [I, I, I]),
+    "b2s_conv3x3_c1_fwd_affine": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "b2s_conv3x3_c1_wgrad": (I, [P, P, P, I, I, I, I, P]),
     "b2s_reduce_rows": (I, [P, I, I, P, P, P]),
     "b2s_bn_finalize": (I, [P, I, I, c_double, P, P, P, P, P, F, F, P, P, P, P, P, P]),

@@ -74,17 +74,19 @@ int reduce_to_small(const float* in, int rows, int K, float* scratch, const floa
 __global__ void __launch_bounds__(kThreads)
 conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       __nv_bfloat16* __restrict__ r, float* __restrict__ stats_partial, int N, int H, int W, int Cout,
-                      int flags) {
+                      int flags, const float* __restrict__ post_scale, const float* __restrict__ post_shift) {
   __shared__ float red[kThreads * 16];
   const int groups = Cout / 8;              // threads per pixel
   const int ppi = kThreads / groups;        // pixels per block iteration
   const int cg = threadIdx.x % groups;
   const int pl = threadIdx.x / groups;
-  float wr[9][8], br[8];
+  float wr[9][8], br[8], ps[8], pt[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int co = cg * 8 + k;
     br[k] = bias ? bias[co] : 0.f;
+    ps[k] = post_scale ? post_scale[co] : 1.f;
+    pt[k] = post_scale ? post_shift[co] : 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[t][k] = w[co * 9 + t];
   }
@@ -113,6 +115,7 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 #pragma unroll
         for (int t = 0; t < 9; ++t) a = fmaf(xv[t], wr[t][k], a);
         if (relu) a = fmaxf(a, 0.f);
+        if (post_scale) a = fmaf(a, ps[k], pt[k]);
         a = bf16_round(a);
         acc[k] = a;
         st[k] += a;
@@ -209,7 +212,7 @@ __device__ __forceinline__ void c1_load_window(const float* __restrict__ xi, int
 __global__ void __launch_bounds__(kThreads, 2)
 conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        __nv_bfloat16* __restrict__ r, float* __restrict__ stats_partial, int N, int H, int W, int Cout,
-                       int flags) {
+                       int flags, const float* __restrict__ post_scale, const float* __restrict__ post_shift) {
   // weights live in shared memory ([tap][Cout], read as two broadcast float4 per tap): keeping all 72 of a thread's
   // weights in registers cost 191 registers and one resident block per SM
   __shared__ float red[kThreads * 16];
@@ -222,9 +225,13 @@ conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w,
     const int t = i / Cout, co = i - t * Cout;
     wsm[t * Cout + co] = w[co * 9 + t];
   }
-  float br[8];
+  float br[8], ps[8], pt[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) br[k] = bias ? bias[cg * 8 + k] : 0.f;
+  for (int k = 0; k < 8; ++k) {
+    br[k] = bias ? bias[cg * 8 + k] : 0.f;
+    ps[k] = post_scale ? post_scale[cg * 8 + k] : 1.f;
+    pt[k] = post_scale ? post_shift[cg * 8 + k] : 0.f;
+  }
   __syncthreads();
   float st[16];
 #pragma unroll
@@ -264,6 +271,7 @@ conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w,
         for (int k = 0; k < 8; ++k) {
           float a = acc[px][k];
           if (relu) a = fmaxf(a, 0.f);
+          if (post_scale) a = fmaf(a, ps[k], pt[k]);
           a = bf16_round(a);
           acc[px][k] = a;
           st[k] += a;
@@ -1188,8 +1196,9 @@ extern "C" int b2s_c1_rows(int N, int H, int W) {
   return grid_for(npix, 32 * 16);
 }
 
-extern "C" int b2s_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, void* r, float* stats_partial,
-                                  int N, int H, int W, int Cout, int flags, void* stream) {
+static int c1_fwd_impl(const float* x, const float* w, const float* bias, const float* post_scale,
+                       const float* post_shift, void* r, float* stats_partial, int N, int H, int W, int Cout, int flags,
+                       void* stream) {
   if (!x || !w || !r) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: null pointer");
   if (!ew_channels_ok(Cout) || Cout > 128) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: unsupported Cout");
   if ((flags & B2S_FLAG_STATS) && !stats_partial) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd: stats missing");
@@ -1198,8 +1207,22 @@ extern "C" int b2s_conv3x3_c1_fwd(const float* x, const float* w, const float* b
   count_launch();
   auto kfn = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? conv3x3_c1_fwd4_kernel : conv3x3_c1_fwd_kernel;
   kfn<<<grid, kThreads, 0, STREAM(stream)>>>(x, w, bias, static_cast<__nv_bfloat16*>(r),
-                                             (flags & B2S_FLAG_STATS) ? stats_partial : nullptr, N, H, W, Cout, flags);
+                                             (flags & B2S_FLAG_STATS) ? stats_partial : nullptr, N, H, W, Cout, flags,
+                                             post_scale, post_shift);
   return check_launch("conv3x3_c1_fwd_kernel");
+}
+
+extern "C" int b2s_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, void* r, float* stats_partial,
+                                  int N, int H, int W, int Cout, int flags, void* stream) {
+  return c1_fwd_impl(x, w, bias, nullptr, nullptr, r, stats_partial, N, H, W, Cout, flags, stream);
+}
+
+// inference variant: eval-mode BatchNorm affine applied after the ReLU (see b2s_conv_fwd_affine)
+extern "C" int b2s_conv3x3_c1_fwd_affine(const float* x, const float* w, const float* bias, const float* post_scale,
+                                         const float* post_shift, void* y, int N, int H, int W, int Cout, int flags,
+                                         void* stream) {
+  if (!post_scale || !post_shift) return set_error(B2S_ERR_ARG, "b2s_conv3x3_c1_fwd_affine: null pointer");
+  return c1_fwd_impl(x, w, bias, post_scale, post_shift, y, nullptr, N, H, W, Cout, flags & ~B2S_FLAG_STATS, stream);
 }
 
 extern "C" int b2s_conv3x3_c1_wgrad(const float* x, const void* dz, float* partial, int N, int H, int W, int Cout,

@@ -201,6 +201,11 @@ class UNetEngine:
                 if pooled is not None:
                     ops.maxpool2x2(s.y, pooled)
                 return s
+            if xin is None and not train and s.y is not None and s.y.c0 == 0 and s.y.C == s.y.cstride:
+                ops.bn_eval_affine(P[f"{bn}.weight"], P[f"{bn}.bias"], P[f"{bn}.running_mean"],
+                                   P[f"{bn}.running_var"], BN_EPS, s.scale, s.shift)
+                ops.conv3x3_c1_fwd_affine(x, P[f"{name}.{idx}.weight"], P[f"{name}.{idx}.bias"], s.scale, s.shift, s.y)
+                return s
             if xin is None:  # first conv on the fp32 image
                 ops.conv3x3_c1_fwd(x, P[f"{name}.{idx}.weight"], P[f"{name}.{idx}.bias"], s.r, relu=True,
                                    stats=pl.stats_partial if train else None)

@@ -262,6 +262,15 @@ def conv3x3_c1_fwd(x, w, bias, r, relu=True, stats=None):
                                       _stream()), "b2s_conv3x3_c1_fwd"))
 
 
+def conv3x3_c1_fwd_affine(x, w, bias, post_scale, post_shift, y, relu=True):
+    """inference: y = act(conv(x) + bias) * post_scale + post_shift"""
+    assert x.dtype == torch.float32 and x.is_contiguous() and y.c0 == 0 and y.C == y.cstride
+    npix = y.N * y.H * y.W
+    _timed("conv3x3_c1_fwd+bn", "hbm", npix * (4.0 + 2.0 * y.C), lambda: check(
+        _lib.lib().b2s_conv3x3_c1_fwd_affine(_p(x), _p(w), _p(bias), _p(post_scale), _p(post_shift), y.ptr, y.N, y.H, y.W,
+                                             y.C, B2S_FLAG_RELU if relu else 0, _stream()), "b2s_conv3x3_c1_fwd_affine"))
+
+
 def conv3x3_c1_wgrad(x, dz, partial, scratch, dw):
     assert dz.c0 == 0 and dz.C == dz.cstride
     L = _lib.lib()
