@@ -179,6 +179,16 @@ int b2s_copy_channels(const void* src, int src_cstride, void* dst, int dst_cstri
  * weights) and b2s_conv3x3_wgrad applied to the zero-inserted output gradient from b2s_upsample_zero2x. */
 int b2s_conv3x3_s2_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y, int y_cstride,
                        int N, int H, int W, int Cin, int Cout, int tile_n, void* stream);
+/* its input gradient without zero insertion: four launches, one per output parity class (1/2/2/4 taps each), written
+ * to the four sub-lattices of dx [N,H,W,Cin] through a 5-D TMA store; w_dgrad_packed [9][Cin][Cout] from
+ * b2s_pack_conv_weight. Returns 1 (no error, nothing launched) for images too small for that store: use the
+ * zero-insertion path then. */
+int b2s_conv3x3_s2_dgrad(const void* dz, int dz_cstride, const void* w_dgrad_packed, void* dx, int dx_cstride, int N,
+                         int H, int W, int Cin, int Cout, int tile_n, void* stream);
+/* its weight gradient: x boxes loaded with elementStrides = 2; workspace / splits from
+ * b2s_conv_wgrad_workspace(N, H/2, W/2, Cin, Cout, 3, tile_n | 4096, splits, &s). */
+int b2s_conv3x3_s2_wgrad(const void* x, int x_cstride, const void* dz, int dz_cstride, float* ws, int N, int H, int W,
+                         int Cin, int Cout, int tile_n, int splits, void* stream);
 /* dst [N,2Hs,2Ws,C]: dst[n,2i,2j,:] = src[n,i,j,:], zero elsewhere. */
 int b2s_upsample_zero2x(const void* src, int src_cstride, void* dst, int dst_cstride, int N, int Hs, int Ws, int C,
                         void* stream);

@@ -53,7 +53,9 @@ def leaf(t):
     return t.clone().to(DEV).requires_grad_(True)
 
 
-@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (1, 32, 64, 128, 256), (3, 8, 8, 64, 64)])
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (1, 32, 64, 128, 256), (3, 8, 8, 64, 64),
+                                            (2, 12, 12, 64, 64),       # 6x6 output: zero-insertion fallback of the dgrad
+                                            (1, 8, 256, 64, 128)])     # wide rows
 def test_strided_conv_forward_backward(VF, N, H, W, Cin, Cout):
     x, w, b = bf(rnd((N, Cin, H, W), 1)), bf(rnd((Cout, Cin, 3, 3), 2, 0.05)), rnd((Cout,), 3, 0.5)
     dy = bf(rnd((N, Cout, H // 2, W // 2), 4))

@@ -57,6 +57,8 @@ SIGNATURES = {
     "b2s_adamw_step_dev": (I, [P, P, P, P, LL, P, P]),
     "b2s_copy_channels": (I, [P, I, P, I, LL, I, P]),
     "b2s_conv3x3_s2_fwd": (I, [P, I, P, P, P, I, I, I, I, I, I, I, P]),
+    "b2s_conv3x3_s2_dgrad": (I, [P, I, P, P, I, I, I, I, I, I, I, P]),
+    "b2s_conv3x3_s2_wgrad": (I, [P, I, P, I, P, I, I, I, I, I, I, I, P]),
     "b2s_upsample_zero2x": (I, [P, I, P, I, I, I, I, I, P]),
     "b2s_conv1x1_wgrad": (I, [P, I, P, I, P, I, I, I, I, I, I, I, P]),
     "b2s_bn_act_apply": (I, [P, I, P, P, P, I, P, I, LL, I, I, F, ctypes.c_uint, P]),

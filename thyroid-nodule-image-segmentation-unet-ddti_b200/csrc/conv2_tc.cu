@@ -165,6 +165,9 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               } else if (p.a_mode == A_CONV3_S2) {   // stride 2: the map steps two input pixels per box element
                 const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;
                 tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, 2 * w0[mt] + dw, 2 * h0[mt] + dh, n0[mt]);
+              } else if (p.a_mode == A_TAPLIST) {    // explicit tap offsets (stride-2 conv input gradient, one parity class)
+                tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0[mt] + p.tap_dw[tap], h0[mt] + p.tap_dh[tap],
+                            n0[mt]);
               } else if (p.a_mode == A_1X1) {
                 tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0[mt], h0[mt], n0[mt]);
               } else {  // A_CONVT_DGRAD: dY viewed as (C, b, j, a, i*N)
@@ -172,7 +175,8 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             n0[mt] * p.H + h0[mt]);
               }
             }
-            tma_load_2d(&tmB, &full_bar[stage], st + L::kAInStage, kc * kBlockK, tap * p.n_total + ncol0);
+            tma_load_2d(&tmB, &full_bar[stage], st + L::kAInStage, kc * kBlockK,
+                        (p.a_mode == A_TAPLIST ? p.tap_w[tap] : tap) * p.n_total + ncol0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -347,6 +351,8 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (row == 0) {
           if (p.out_mode == OUT_4D) {
             tma_store_4d(&tmOut, stage_buf, col_base, w0, h0, n0);
+          } else if (p.out_mode == OUT_SUB_5D) {   // one fixed sub-lattice of the 2x larger output
+            tma_store_5d(&tmOut, stage_buf, col_base, p.sub_b, w0, p.sub_a, n0 * p.H + h0);
           } else {  // convT forward: the 64-column block belongs to one (a,b) sub-position
             const int ab = col_base / p.cout_sub;
             tma_store_5d(&tmOut, stage_buf, col_base - ab * p.cout_sub, ab & 1, w0, ab >> 1, n0 * p.H + h0);

@@ -10,8 +10,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 
-enum AMode : int { A_CONV3 = 0, A_1X1 = 1, A_CONVT_DGRAD = 2, A_CONV3_S2 = 3 };
-enum OutMode : int { OUT_4D = 0, OUT_CONVT_5D = 1 };
+enum AMode : int { A_CONV3 = 0, A_1X1 = 1, A_CONVT_DGRAD = 2, A_CONV3_S2 = 3, A_TAPLIST = 4 };
+enum OutMode : int { OUT_4D = 0, OUT_CONVT_5D = 1, OUT_SUB_5D = 2 };
 
 struct ConvTcParams {
   int bw, bh, bn;                  // pixel box of one M tile, bw*bh*bn == 128
@@ -24,6 +24,8 @@ struct ConvTcParams {
   int cout_sub;                    // convT forward: Cout per (a,b) sub-position; else n_total
   int tiles_nn;                    // n_total / BLOCK_N
   int flags;                       // B2S_FLAG_*
+  int tap_dh[4], tap_dw[4], tap_w[4];  // A_TAPLIST: pixel offsets of tap t and its row block in the packed weights
+  int sub_a, sub_b;                // OUT_SUB_5D: sub-lattice (row, column parity) of the 2x up-sampled output
   const float* bias;               // [cout_sub] or nullptr
   const float* post_scale;         // eval-mode BatchNorm folded into the epilogue: y = act(acc + bias) * post_scale +
   const float* post_shift;         // post_shift per output channel (both nullptr in training)

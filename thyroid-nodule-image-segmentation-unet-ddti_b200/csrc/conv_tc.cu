@@ -279,7 +279,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // wgrad: D[(tap,ci), co] = sum_pix A[pix, (tap,ci)] * B[pix, co], both operands MN-major in smem
 // ------------------------------------------------------------------------------------------------
-enum WgMode : int { WG_CONV3 = 0, WG_CONVT = 1, WG_1X1 = 2 };
+enum WgMode : int { WG_CONV3 = 0, WG_CONVT = 1, WG_1X1 = 2, WG_CONV3_S2 = 3 };
 
 struct WgradParams {
   int pw, ph, pn;                 // pixel box of one K chunk, pw*ph*pn == 64
@@ -382,8 +382,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < NRB; ++j) {
           int dh = 0, dw = 0;
-          if (p.mode == WG_CONV3) { dh = tap_j[j] / 3 - 1; dw = tap_j[j] % 3 - 1; }
-          tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 8192, cib_j[j] * 64, w0 + dw, h0 + dh, n0);
+          if (p.mode == WG_CONV3 || p.mode == WG_CONV3_S2) { dh = tap_j[j] / 3 - 1; dw = tap_j[j] % 3 - 1; }
+          if (p.mode == WG_CONV3_S2)   // the x map steps two input pixels per box element (stride-2 conv)
+            tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 8192, cib_j[j] * 64, 2 * w0 + dw, 2 * h0 + dh, n0);
+          else
+            tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 8192, cib_j[j] * 64, w0 + dw, h0 + dh, n0);
         }
         if (p.mode != WG_CONVT) {
 #pragma unroll
@@ -591,6 +594,50 @@ extern "C" int b2s_conv3x3_s2_fwd(const void* x, int x_cstride, const void* w_pa
   return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
 }
 
+// Input gradient of nn.Conv2d(Cin,Cout,3,stride=2,padding=1): dz [N,H/2,W/2,Cout] -> dx [N,H,W,Cin], w_dgrad_packed
+// [9][Cin][Cout] from b2s_pack_conv_weight. Four launches, one per output parity class (h%2, w%2) with 1/2/2/4 taps: no
+// zero-insertion, no redundant FLOPs. Returns 1 (not an error) when the image is too small for the sub-lattice store;
+// the caller then uses the zero-insertion path.
+extern "C" int b2s_conv3x3_s2_dgrad(const void* dz, int dz_cstride, const void* w_dgrad_packed, void* dx, int dx_cstride,
+                                    int N, int H, int W, int Cin, int Cout, int tile_n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!dz || !w_dgrad_packed || !dx) return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_dgrad: null pointer");
+  if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_dgrad: channels must be multiples of 64");
+  if (N <= 0 || H < 2 || W < 2 || H % 2 || W % 2) return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_dgrad: H and W must be even");
+  const int Ho = H / 2, Wo = W / 2;
+  ConvTcParams p{};
+  p.a_mode = A_TAPLIST; p.out_mode = OUT_SUB_5D;
+  ConvPlan pl;
+  if (conv_plan(N, Ho, Wo, Cin, Cin, p.a_mode, p.out_mode, (tile_n & kTileNMask) | kVarPair, &pl))
+    return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_dgrad: tile_n must be 64/128/256 and divide Cin");
+  if (pl.bn > 1 && pl.bh != Ho) return 1;   // tile would straddle images in the merged-row output view
+  p.W = Wo; p.H = Ho; p.N = N;
+  p.k_chunks = Cout / 64;
+  p.n_total = Cin; p.cout_sub = Cin;
+  p.flags = 0; p.bias = nullptr; p.stats = nullptr;
+  CUtensorMap tmA, tmB, tmOut;
+  int rc;
+  if ((rc = make_act_map4(&tmA, dz, Cout, Wo, Ho, N, dz_cstride, pl.bw, pl.bh, pl.bn))) return rc;
+  if ((rc = make_weight_map(&tmB, w_dgrad_packed, Cout, 9 * Cin, pl.block_n))) return rc;
+  if ((rc = make_up_map5(&tmOut, dx, Cin, Wo, Ho, N, dx_cstride, pl.bw, pl.bh * pl.bn))) return rc;
+  // dx[2i+ph, 2j+pw] = sum over (a, dh) in taps(ph), (b, dw) in taps(pw) of dz[i+dh, j+dw] * w[a, b];
+  // taps(0) = {(1, 0)}, taps(1) = {(0, +1), (2, 0)}. The dgrad packing stores w[a, b] at tap row 8 - (3a + b).
+  static const int ka[2][2] = {{1, -1}, {0, 2}}, kd[2][2] = {{0, 0}, {1, 0}}, kn[2] = {1, 2};
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      int nt = 0;
+      for (int i = 0; i < kn[ph]; ++i)
+        for (int j = 0; j < kn[pw]; ++j) {
+          p.tap_dh[nt] = kd[ph][i]; p.tap_dw[nt] = kd[pw][j];
+          p.tap_w[nt] = 8 - (3 * ka[ph][i] + ka[pw][j]);
+          ++nt;
+        }
+      p.num_taps = nt; p.sub_a = ph; p.sub_b = pw;
+      if ((rc = dispatch_conv(pl, tmA, tmB, tmOut, p, stream))) return rc;
+    }
+  return B2S_OK;
+}
+
 // Rows of the stats_partial buffer b2s_conv_fwd (ksize 3) writes for this shape: 2 per CTA row-group of the
 // persistent grid of whichever kernel variant conv_plan picks.
 extern "C" int b2s_conv_stats_rows(int N, int H, int W, int Cout, int tile_n) {
@@ -760,6 +807,28 @@ extern "C" int b2s_conv3x3_wgrad(const void* x, int x_cstride, const void* dz, i
   int rc;
   if ((rc = make_act_map4(&tmA, x, Cin, W, H, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
   if ((rc = make_act_map4(&tmB, dz, Cout, W, H, N, dz_cstride, p.pw, p.ph, p.pn))) return rc;
+  return dispatch_wgrad(block_n, tmA, tmB, p, stream);
+}
+
+// Weight gradient of nn.Conv2d(Cin,Cout,3,stride=2,padding=1): x [N,H,W,Cin], dz [N,H/2,W/2,Cout] -> ws[split][tap*Cin+ci][co];
+// workspace from b2s_conv_wgrad_workspace(N, H/2, W/2, Cin, Cout, 3, tile_n | 4096, ...) (the one-box-per-tap kernel).
+extern "C" int b2s_conv3x3_s2_wgrad(const void* x, int x_cstride, const void* dz, int dz_cstride, float* ws, int N, int H,
+                                    int W, int Cin, int Cout, int tile_n, int splits, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !dz || !ws) return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_wgrad: null pointer");
+  if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_wgrad: channels must be multiples of 64");
+  if (N <= 0 || H < 2 || W < 2 || H % 2 || W % 2) return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_wgrad: H and W must be even");
+  const int Ho = H / 2, Wo = W / 2;
+  tile_n &= kTileNMask;
+  WgradParams p{};
+  int block_n;
+  if (wgrad_plan(N, Ho, Wo, Cin, Cout, 9, tile_n, splits, &p, &block_n))
+    return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_wgrad: bad tile_n");
+  p.mode = WG_CONV3_S2; p.ws = ws;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_act_map4_s2(&tmA, x, Cin, W, H, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
+  if ((rc = make_act_map4(&tmB, dz, Cout, Wo, Ho, N, dz_cstride, p.pw, p.ph, p.pn))) return rc;
   return dispatch_wgrad(block_n, tmA, tmB, p, stream);
 }
 

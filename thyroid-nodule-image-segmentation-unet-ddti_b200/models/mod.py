@@ -50,7 +50,7 @@ class _PackMixin:
         for n, p in ws:
             for plan in self._pack_plans:
                 if n in plan.packed:
-                    VF.PACKED[p.data_ptr()] = (p._version,) + plan.packed[n]
+                    VF.register_packed(p, *plan.packed[n])
                     reg.append(p.data_ptr())
         self._pack_registered = tuple(reg)
         self._pack_key = key

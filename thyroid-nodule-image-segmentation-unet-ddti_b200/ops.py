@@ -413,6 +413,30 @@ def conv3x3_s2_fwd(x, w_packed, bias, y, tile_n=0):
                                       y.C, tile_n, _stream()), "b2s_conv3x3_s2_fwd"))
 
 
+def conv3x3_s2_dgrad(dz, w_packed_d, dx, tile_n=0):
+    """dx [N,H,W,Cin] from dz [N,H/2,W/2,Cout]; returns False when the image is too small (use zero insertion)"""
+    flops = 18.0 * dz.N * dz.H * dz.W * dx.C * dz.C
+    rc = _timed(f"dgrad3x3s2[{dx.C}<-{dz.C}@{dx.H}x{dx.W}]", "tensor", flops, lambda: _lib.lib().b2s_conv3x3_s2_dgrad(
+        dz.ptr, dz.cstride, _p(w_packed_d), dx.ptr, dx.cstride, dx.N, dx.H, dx.W, dx.C, dz.C, tile_n, _stream()))
+    if rc == 1:
+        return False
+    check(rc, "b2s_conv3x3_s2_dgrad")
+    return True
+
+
+def conv3x3_s2_wgrad(x, dz, dw, tile_n=0, splits=0):
+    """dw [Cout,Cin,3,3] fp32 of the stride-2 conv"""
+    LEGACY = 1 << 12
+    nbytes, s = wgrad_workspace(dz.N, dz.H, dz.W, x.C, dz.C, 9, tile_n | LEGACY, splits)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dw.device)
+    L = _lib.lib()
+    flops = 18.0 * dz.N * dz.H * dz.W * x.C * dz.C
+    _timed(f"wgrad3x3s2[{x.C}->{dz.C}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
+        L.b2s_conv3x3_s2_wgrad(x.ptr, x.cstride, dz.ptr, dz.cstride, _p(ws), x.N, x.H, x.W, x.C, dz.C, tile_n, splits,
+                               _stream()), "b2s_conv3x3_s2_wgrad"))
+    check(L.b2s_wgrad_reduce(_p(ws), s, 9, x.C, dz.C, _p(dw), 0, _stream()), "b2s_wgrad_reduce")
+
+
 def upsample_zero2x(src, dst):
     _timed("upsample_zero2x", "hbm", 2.0 * src.C * src.N * src.H * src.W * 5.0, lambda: check(
         _lib.lib().b2s_upsample_zero2x(src.ptr, src.cstride, dst.ptr, dst.cstride, src.N, src.H, src.W, src.C,

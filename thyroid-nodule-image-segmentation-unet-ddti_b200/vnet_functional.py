@@ -33,23 +33,38 @@ def as_act(t):
     return Act(base, c0, C)
 
 
-# Packed bf16 operands registered by the owning module (ImprovedVNet packs every conv weight of the network in a few
-# launches per step): data_ptr -> (version, w_fwd, w_dgrad). The nodes fall back to packing on the spot.
+# Packed bf16 operands registered by the owning module (the nets pack every conv weight in a few launches per step):
+# data_ptr -> (weakref to the parameter, version, w_fwd, w_dgrad). An entry is honoured only while its parameter is
+# alive (a freed parameter's address can be reused by an unrelated tensor) and unchanged; otherwise the node packs
+# the weight on the spot.
 PACKED = {}
 
 
-def packed_conv(w, want_dgrad):
+def register_packed(param, wf, wd):
+    import weakref
+    PACKED[param.data_ptr()] = (weakref.ref(param), param._version, wf, wd)
+
+
+def _lookup(w, need_dgrad):
     e = PACKED.get(w.data_ptr())
-    if e is not None and e[0] == w._version and (e[2] is not None or not want_dgrad):
-        return e[1], e[2]
-    return ops.pack_conv_weight(w, want_dgrad=want_dgrad)
+    if e is None:
+        return None
+    owner = e[0]()
+    if owner is None or owner.data_ptr() != w.data_ptr() or owner.shape != w.shape or e[1] != w._version:
+        return None
+    if need_dgrad and e[3] is None:
+        return None
+    return e[2], e[3]
+
+
+def packed_conv(w, want_dgrad):
+    hit = _lookup(w, want_dgrad)
+    return hit if hit is not None else ops.pack_conv_weight(w, want_dgrad=want_dgrad)
 
 
 def packed_convt(w):
-    e = PACKED.get(w.data_ptr())
-    if e is not None and e[0] == w._version:
-        return e[1], e[2]
-    return ops.pack_convt_weight(w)
+    hit = _lookup(w, True)
+    return hit if hit is not None else ops.pack_convt_weight(w)
 
 
 def new_act(N, H, W, C, device):
@@ -209,8 +224,8 @@ class Conv1x1(torch.autograd.Function):
 
 
 class ConvS2(torch.autograd.Function):
-    """nn.Conv2d(C, 2C, 3, stride=2, padding=1) (models/vnet.py:97). Backward = stride-1 kernels on the zero-inserted
-    output gradient."""
+    """nn.Conv2d(C, 2C, 3, stride=2, padding=1) (models/vnet.py:97). Forward and weight gradient read x through TMA
+    boxes with elementStrides = 2; the input gradient is four parity-class convolutions over dz."""
 
     @staticmethod
     def forward(ctx, x, w, b):
@@ -232,17 +247,16 @@ class ConvS2(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         db = torch.empty(Cout, **f32)
         ops.channel_sums(dy, db)
-        up = new_act(xa.N, xa.H, xa.W, Cout, dev)
-        ops.upsample_zero2x(dy, Act(up))
         dw = torch.empty((Cout, Cin, 3, 3), **f32)
-        nbytes, _ = ops.wgrad_workspace(xa.N, xa.H, xa.W, Cin, Cout, 9)
-        ws = torch.empty(nbytes // 4, **f32)
-        ops.conv3x3_wgrad(xa, Act(up), ws, dw)
+        ops.conv3x3_s2_wgrad(xa, dy, dw)                 # x boxes with elementStrides = 2: no zero insertion
         dx = None
         if ctx.needs_input_grad[0]:
             _, wd = packed_conv(w, True)
             dx = new_act(xa.N, xa.H, xa.W, Cin, dev)
-            ops.conv_fwd(Act(up), wd, None, Act(dx), ksize=3)
+            if not ops.conv3x3_s2_dgrad(dy, wd, Act(dx)):   # tiny image: stride-1 dgrad of the zero-inserted gradient
+                up = new_act(xa.N, xa.H, xa.W, Cout, dev)
+                ops.upsample_zero2x(dy, Act(up))
+                ops.conv_fwd(Act(up), wd, None, Act(dx), ksize=3)
         return dx, dw, db
 
 
