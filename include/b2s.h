@@ -199,20 +199,22 @@ int b2s_conv1x1_wgrad(const void* x, int x_cstride, const void* dz, int dz_cstri
 
 /* BatchNorm -> ReLU -> Dropout (+ residual) of ConvBlock (models/vnet.py:51-59):
  * out = dropout_p(relu(z*scale + shift)) + res; scale/shift/res may be NULL, relu is a flag. The dropout mask is a
- * counter-based hash of (seed, NHWC element index): P(keep) = 1-p, kept values scaled by 1/(1-p); p = 0 disables it. */
+ * counter-based hash of (seed, NHWC element index): P(keep) = 1-p, kept values scaled by 1/(1-p); p = 0 disables it.
+ * step_counter (optional DEVICE int64, e.g. the layer's BatchNorm num_batches_tracked) is mixed into the seed at run time,
+ * so a captured CUDA graph draws a new mask at every replay; forward and backward of one step must see the same value. */
 int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale, const float* shift, const void* res,
                      int res_cstride, void* out, int out_cstride, long long npix, int C, int relu, float dropout_p,
-                     unsigned seed, void* stream);
+                     unsigned seed, const long long* step_counter, void* stream);
 /* its backward in two passes (same finalize as the UNet path, b2s_bn_bwd_finalize): pass 1 partial [b2s_ew_rows][2][C]
  * = sum dy, sum dy*xhat with dy = da * mask/(1-p) * (z*scale+shift > 0); pass 2 dz = c0 (dy - c1 - xhat c2) and the
  * conv-bias gradient partials [b2s_ew_rows][C]. */
 int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void* z, int z_cstride, const float* scale,
                           const float* shift, const float* mean, const float* invstd, float* partial, long long npix,
-                          int C, int relu, float dropout_p, unsigned seed, void* stream);
+                          int C, int relu, float dropout_p, unsigned seed, const long long* step_counter, void* stream);
 int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* z, int z_cstride, const float* scale,
                          const float* shift, const float* mean, const float* invstd, const float* coef, void* dz,
                          int dz_cstride, float* dbias_partial, long long npix, int C, int relu, float dropout_p,
-                         unsigned seed, void* stream);
+                         unsigned seed, const long long* step_counter, void* stream);
 /* models/mod.py variants (Conv -> BN -> ReLU blocks, ResidualBlock: relu(BN(conv) + skip), models/mod.py:43-51,71-84):
  * b2s_bn_act_apply's `relu` argument is a mode: 0 none, 1 ReLU before the residual add (V-Net ConvBlock), 2 ReLU after it
  * (ResidualBlock). b2s_relu_bwd: dx = dy * (y > 0) from the ReLU OUTPUT y. b2s_maxpool2x2_bwd: nn.MaxPool2d(2,2) backward,

@@ -170,6 +170,15 @@ def test_dropout_mask_is_consistent_between_forward_and_backward():
     assert torch.equal(o, out2.buf.float()), "dropout mask must be a pure function of (seed, index)"
     kept = o > 0
     assert abs(float(kept.float().mean()) - (1 - p)) < 0.02
+    # a device-side step counter mixed into the seed: same value -> same mask, next value -> a different mask
+    ctr = torch.tensor(5, dtype=torch.int64, device=DEV)
+    a, b2, c = (ops.Act.empty(N, H, W, C, DEV) for _ in range(3))
+    ops.bn_act_apply(z, None, None, None, a, relu=True, dropout_p=p, seed=1234, step_counter=ctr)
+    ops.bn_act_apply(z, None, None, None, b2, relu=True, dropout_p=p, seed=1234, step_counter=ctr)
+    ctr += 1
+    ops.bn_act_apply(z, None, None, None, c, relu=True, dropout_p=p, seed=1234, step_counter=ctr)
+    assert torch.equal(a.buf, b2.buf) and not torch.equal(a.buf, c.buf) and not torch.equal(a.buf, out.buf)
+    assert abs(float((c.buf.float() > 0).float().mean()) - (1 - p)) < 0.02
     assert torch.allclose(o[kept], torch.full_like(o[kept], 1 / (1 - p)), rtol=1e-2)
     f32 = dict(dtype=torch.float32, device=DEV)
     one, zero = torch.ones(C, **f32), torch.zeros(C, **f32)

@@ -61,9 +61,9 @@ SIGNATURES = {
     "b2s_conv3x3_s2_wgrad": (I, [P, I, P, I, P, I, I, I, I, I, I, I, P]),
     "b2s_upsample_zero2x": (I, [P, I, P, I, I, I, I, I, P]),
     "b2s_conv1x1_wgrad": (I, [P, I, P, I, P, I, I, I, I, I, I, I, P]),
-    "b2s_bn_act_apply": (I, [P, I, P, P, P, I, P, I, LL, I, I, F, ctypes.c_uint, P]),
-    "b2s_bn_act_bwd_reduce": (I, [P, I, P, I, P, P, P, P, P, LL, I, I, F, ctypes.c_uint, P]),
-    "b2s_bn_act_bwd_apply": (I, [P, I, P, I, P, P, P, P, P, P, I, P, LL, I, I, F, ctypes.c_uint, P]),
+    "b2s_bn_act_apply": (I, [P, I, P, P, P, I, P, I, LL, I, I, F, ctypes.c_uint, P, P]),
+    "b2s_bn_act_bwd_reduce": (I, [P, I, P, I, P, P, P, P, P, LL, I, I, F, ctypes.c_uint, P, P]),
+    "b2s_bn_act_bwd_apply": (I, [P, I, P, I, P, P, P, P, P, P, I, P, LL, I, I, F, ctypes.c_uint, P, P]),
     "b2s_relu_bwd": (I, [P, I, P, I, P, I, LL, I, P]),
     "b2s_maxpool2x2_bwd": (I, [P, I, P, I, P, I, I, I, I, I, P]),
     "b2s_channel_sums": (I, [P, I, P, LL, I, P]),

@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(kThreads)
 bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* __restrict__ scale,
                     const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_cs,
                     __nv_bfloat16* __restrict__ out, int out_cs, long long npix, int C, int relu, uint32_t drop_thresh,
-                    float drop_scale, uint32_t seed) {
+                    float drop_scale, uint32_t seed, const long long* __restrict__ step_counter) {
+  if (step_counter) seed ^= mix32(static_cast<uint32_t>(*step_counter) + 0x632be5abU);
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
   const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
@@ -73,8 +74,9 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dz,
                   int dz_cs, float* __restrict__ partial, long long npix, int C, int relu, uint32_t drop_thresh,
-                  float drop_scale, uint32_t seed) {
+                  float drop_scale, uint32_t seed, const long long* __restrict__ step_counter) {
   __shared__ float red[kThreads * 16];
+  if (step_counter) seed ^= mix32(static_cast<uint32_t>(*step_counter) + 0x632be5abU);
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
   const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
@@ -442,7 +444,7 @@ static float drop_scale_of(float p) {
 
 extern "C" int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale, const float* shift, const void* res,
                                 int res_cstride, void* out, int out_cstride, long long npix, int C, int relu,
-                                float dropout_p, unsigned seed, void* stream) {
+                                float dropout_p, unsigned seed, const long long* step_counter, void* stream) {
   if (!z || !out) return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: C/8 must be a power of two <= 256");
   if (z_cstride % 8 || out_cstride % 8 || (res && res_cstride % 8))
@@ -451,13 +453,15 @@ extern "C" int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale
   count_launch();
   bn_act_apply_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, static_cast<const __nv_bfloat16*>(res), res_cstride,
-      static_cast<__nv_bfloat16*>(out), out_cstride, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed);
+      static_cast<__nv_bfloat16*>(out), out_cstride, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed,
+      step_counter);
   return check_launch("bn_act_apply_kernel");
 }
 
 extern "C" int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void* z, int z_cstride, const float* scale,
                                      const float* shift, const float* mean, const float* invstd, float* partial,
-                                     long long npix, int C, int relu, float dropout_p, unsigned seed, void* stream) {
+                                     long long npix, int C, int relu, float dropout_p, unsigned seed,
+                                     const long long* step_counter, void* stream) {
   if (!da || !z || !scale || !shift || !mean || !invstd || !partial)
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: unsupported C");
@@ -465,14 +469,15 @@ extern "C" int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void*
   static const int grid = wave_grid(bn_act_bwd_kernel<false>);
   bn_act_bwd_kernel<false><<<grid, kThreads, 0, STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
-      mean, invstd, nullptr, nullptr, 0, partial, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed);
+      mean, invstd, nullptr, nullptr, 0, partial, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed,
+      step_counter);
   return check_launch("bn_act_bwd_kernel<reduce>");
 }
 
 extern "C" int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* z, int z_cstride, const float* scale,
                                     const float* shift, const float* mean, const float* invstd, const float* coef,
                                     void* dz, int dz_cstride, float* dbias_partial, long long npix, int C, int relu,
-                                    float dropout_p, unsigned seed, void* stream) {
+                                    float dropout_p, unsigned seed, const long long* step_counter, void* stream) {
   if (!da || !z || !scale || !shift || !mean || !invstd || !coef || !dz || !dbias_partial)
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: unsupported C");
@@ -481,7 +486,7 @@ extern "C" int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* 
   bn_act_bwd_kernel<true><<<grid, kThreads, 0, STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
       mean, invstd, coef, static_cast<__nv_bfloat16*>(dz), dz_cstride, dbias_partial, npix, C, relu,
-      drop_threshold(dropout_p), drop_scale_of(dropout_p), seed);
+      drop_threshold(dropout_p), drop_scale_of(dropout_p), seed, step_counter);
   return check_launch("bn_act_bwd_kernel<apply>");
 }
 

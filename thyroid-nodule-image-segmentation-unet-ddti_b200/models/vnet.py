@@ -74,6 +74,12 @@ class ConvBlock(nn.Module):
             self.bns.append(nn.BatchNorm2d(out_channels))
         self.res_proj = nn.Conv2d(in_channels, out_channels, kernel_size=1) if in_channels != out_channels else None
 
+    def _layer_seed(self, i):
+        """fixed per (process seed, block, conv): the per-step variation comes from the device-side step counter"""
+        if not hasattr(self, "_seed_base"):
+            self._seed_base = _next_seed()
+        return (self._seed_base + 7919 * i) & 0xFFFFFFFF
+
     def forward_nhwc(self, x):
         """x: NHWC bf16, or the fp32 image [N,1,H,W] when in_channels == 1"""
         if self.res_proj is not None:
@@ -85,7 +91,7 @@ class ConvBlock(nn.Module):
         for i, (conv, bn) in enumerate(zip(self.convs, self.bns)):
             res = residual if i == n - 1 else None       # the residual add is fused into the last stage's apply pass
             x = VF.ConvBnAct.apply(x, res, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                   bn.num_batches_tracked, self.training, p, _next_seed() if (self.training and p > 0) else 0, 1)
+                                   bn.num_batches_tracked, self.training, p, self._layer_seed(i) if (self.training and p > 0) else 0, 1)
         return x
 
     def forward(self, x):

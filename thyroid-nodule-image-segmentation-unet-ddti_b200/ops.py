@@ -454,17 +454,17 @@ def conv1x1_wgrad(x, dz, dw, tile_n=0, splits=0):
     check(L.b2s_wgrad_reduce(_p(ws), s, 1, x.C, dz.C, _p(dw), 0, _stream()), "b2s_wgrad_reduce")
 
 
-def bn_act_apply(z, scale, shift, res, out, relu=True, dropout_p=0.0, seed=0):
+def bn_act_apply(z, scale, shift, res, out, relu=True, dropout_p=0.0, seed=0, step_counter=None):
     nb = z.N * z.H * z.W * z.C * 2.0 * (3.0 if res is not None else 2.0)
     _timed("bn_act_apply", "hbm", nb, lambda: check(
         _lib.lib().b2s_bn_act_apply(z.ptr, z.cstride, _p(scale), _p(shift), res.ptr if res is not None else None,
                                     res.cstride if res is not None else 0, out.ptr, out.cstride,
                                     z.N * z.H * z.W, z.C, int(relu), float(dropout_p), int(seed) & 0xFFFFFFFF,
-                                    _stream()), "b2s_bn_act_apply"))
+                                    _p(step_counter), _stream()), "b2s_bn_act_apply"))
 
 
 def bn_act_bwd(da, z, scale, shift, mean, invstd, gamma, count, dz, dgamma, dbeta, dbias, relu=True, dropout_p=0.0,
-               seed=0):
+               seed=0, step_counter=None):
     """BatchNorm(train) -> ReLU -> Dropout backward: writes dz (Act), dgamma, dbeta, dbias (fp32 [C])."""
     L = _lib.lib()
     rows, C = L.b2s_ew_rows(), z.C
@@ -476,14 +476,14 @@ def bn_act_bwd(da, z, scale, shift, mean, invstd, gamma, count, dz, dgamma, dbet
     seed = int(seed) & 0xFFFFFFFF
     _timed("bn_act_bwd_reduce", "hbm", npix * C * 4.0, lambda: check(
         L.b2s_bn_act_bwd_reduce(da.ptr, da.cstride, z.ptr, z.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
-                                _p(partial), npix, C, int(relu), float(dropout_p), seed, _stream()),
+                                _p(partial), npix, C, int(relu), float(dropout_p), seed, _p(step_counter), _stream()),
         "b2s_bn_act_bwd_reduce"))
     check(L.b2s_bn_bwd_finalize(_p(partial), rows, C, float(count), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta),
                                 _p(coef), _p(scratch), _stream()), "b2s_bn_bwd_finalize")
     _timed("bn_act_bwd_apply", "hbm", npix * C * 6.0, lambda: check(
         L.b2s_bn_act_bwd_apply(da.ptr, da.cstride, z.ptr, z.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
                                _p(coef), dz.ptr, dz.cstride, _p(partial), npix, C, int(relu), float(dropout_p), seed,
-                               _stream()), "b2s_bn_act_bwd_apply"))
+                               _p(step_counter), _stream()), "b2s_bn_act_bwd_apply"))
     check(L.b2s_reduce_rows(_p(partial), rows, C, _p(scratch), _p(dbias), _stream()), "b2s_reduce_rows")
 
 

@@ -117,8 +117,12 @@ class ConvBnAct(torch.autograd.Function):
         scale, shift, mean, invstd = _bn_affine(training, stats, rows, float(N * H * W), gamma.detach(), beta.detach(),
                                                 rm, rv, nbt, Cout, dev)
         out = new_act(N, H, W, Cout, dev)
+        # the dropout mask is keyed on (seed, this layer's num_batches_tracked as read on the device): a replayed CUDA
+        # graph therefore draws a fresh mask every step, and backward re-derives the mask of its own step
+        use_drop = training and p_drop > 0
         ops.bn_act_apply(za, scale, shift, as_act(res) if res is not None else None, Act(out), relu=relu_mode,
-                         dropout_p=p_drop if training else 0.0, seed=seed)
+                         dropout_p=p_drop if training else 0.0, seed=seed, step_counter=nbt if use_drop else None)
+        ctx.nbt = nbt if use_drop else None
         ctx.save_for_backward(x, z, w, gamma, scale, shift, mean if mean is not None else scale,
                               invstd if invstd is not None else scale, out if relu_mode == 2 else scale)
         ctx.cfg = (first, training, p_drop, seed, res is not None, relu_mode, b is not None)
@@ -143,7 +147,7 @@ class ConvBnAct(torch.autograd.Function):
         dz = new_act(N, H, W, Cout, dev)
         dgamma, dbeta, dbias = torch.empty(Cout, **f32), torch.empty(Cout, **f32), torch.empty(Cout, **f32)
         ops.bn_act_bwd(da, za, scale, shift, mean, invstd, gamma.detach(), float(N * H * W), Act(dz), dgamma, dbeta,
-                       dbias, relu=1 if relu_mode == 1 else 0, dropout_p=p_drop, seed=seed)
+                       dbias, relu=1 if relu_mode == 1 else 0, dropout_p=p_drop, seed=seed, step_counter=ctx.nbt)
         dw = torch.empty((Cout, Cin, 3, 3), **f32)
         dx = None
         if first:
