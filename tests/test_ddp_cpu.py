@@ -144,3 +144,35 @@ def test_bucketed_allreduce_world2_gloo(tmp_path):
     port = 29000 + os.getpid() % 2000
     mp.spawn(_ddp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def test_host_side_planners_over_many_shapes():
+    """the launch planners behind the C ABI are pure host code: exercise them without a GPU over the UNet / V-Net layer
+    shapes and odd sizes (grid <= SM count per wave, partial-statistics rows, split-K workspace consistency)"""
+    L = _lib.lib()
+    s = ctypes.c_int(0)
+    PAIR, HALO, LEGACY = 1 << 10, 1 << 11, 1 << 12
+    for N in (1, 2, 3, 16, 64):
+        for (H, W) in ((16, 16), (32, 32), (48, 80), (64, 64), (128, 128), (256, 256), (32, 128), (512, 512)):
+            for C in (64, 128, 256, 512, 1024):
+                if N * H * W * C > 64 * 512 * 512 * 128:
+                    continue
+                rows = L.b2s_conv_stats_rows(N, H, W, C, 0)
+                assert 2 <= rows <= 2 * 148 and rows % 2 == 0, (N, H, W, C, rows)
+                for forced in (PAIR, LEGACY) + ((HALO,) if W % 128 == 0 and H % 2 == 0 else ()):
+                    r = L.b2s_conv_stats_rows(N, H, W, C, forced)
+                    assert 2 <= r <= 2 * 148, (N, H, W, C, forced, r)
+                if not (W % 128 == 0 and H % 2 == 0):
+                    assert L.b2s_conv_stats_rows(N, H, W, C, HALO) < 0          # halo kernel refuses narrow images
+                for cin in (64, 128, 256):
+                    nbytes = L.b2s_conv_wgrad_workspace(N, H, W, cin, C, 3, 0, 0, ctypes.byref(s))
+                    assert nbytes == s.value * 9 * cin * C * 4 and 1 <= s.value <= 148, (N, H, W, cin, C, s.value)
+                    nb1 = L.b2s_conv_wgrad_workspace(N, H, W, cin, C, 1, 0, 0, ctypes.byref(s))
+                    assert nb1 == s.value * cin * C * 4 and s.value >= 1
+                    if cin % 128 == 0:
+                        nb4 = L.b2s_conv_wgrad_workspace(N, H, W, cin, C, 4, 0, 0, ctypes.byref(s))
+                        assert nb4 == s.value * 4 * cin * C * 4 and s.value >= 1
+                    forced_splits = L.b2s_conv_wgrad_workspace(N, H, W, cin, C, 3, LEGACY, 3, ctypes.byref(s))
+                    assert forced_splits > 0 and 1 <= s.value <= 3
+    assert L.b2s_se_chunks(512 * 512) >= 1 and L.b2s_metrics_blocks(1) == 1 and L.b2s_loss_chunks(65536) >= 1
+    assert L.b2s_c1_rows(64, 256, 256) % 148 == 0
