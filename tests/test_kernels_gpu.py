@@ -449,6 +449,82 @@ def test_bn_relu_pool_backward(ops, C, pool):
     report("dbias", dbias, dz.to_nchw_float().double().sum(dim=(0, 2, 3)), rel=1e-4, abs_frac=1e-4)
 
 
+def _close_on_gpu(name, got, ref, rel, abs_frac):
+    """report() without the trip to the host (tens of millions of elements)"""
+    got, ref = got.double(), ref.double()
+    err = (got - ref).abs()
+    tol = rel * ref.abs() + abs_frac * float(ref.abs().max()) + 1e-30
+    nbad = int((err > tol).sum())
+    assert nbad == 0, f"{name}: {nbad}/{err.numel()} out of tolerance, max err {float(err.max()):.4g}"
+
+
+@pytest.mark.parametrize("pool", [False, True])
+def test_bn_streaming_kernels_many_items_per_thread(ops, pool):
+    """BN apply / backward at a size where every thread walks its prefetch ring (ew_common.cuh PrefetchRing) several
+    times around (the 8x8 cases above give a thread at most one work item); reference = plain torch ops on the GPU."""
+    N, H, W, C = 8, 256, 256, 64
+    g = torch.Generator(device=DEV).manual_seed(7)
+    r = torch.randn((N, H, W, C), generator=g, device=DEV).clamp_min(0).to(torch.bfloat16)
+    dyb = torch.zeros((N, H, W, 2 * C), dtype=torch.bfloat16, device=DEV)       # dy is a channel slice (concat buffer)
+    dyb[..., C:] = torch.randn((N, H, W, C), generator=g, device=DEV).to(torch.bfloat16)
+    gamma = torch.randn(C, generator=g, device=DEV) * 0.5 + 1.0
+    beta = torch.randn(C, generator=g, device=DEV) * 0.1
+    rd = r.double()
+    mean = rd.mean(dim=(0, 1, 2))
+    var = rd.var(dim=(0, 1, 2), unbiased=False)
+    invstd = 1.0 / torch.sqrt(var + 1e-5)
+    scale, shift = (gamma.double() * invstd).float(), (beta.double() - mean * gamma.double() * invstd).float()
+    mean32, invstd32 = mean.float(), invstd.float()
+    ra, dya = ops.Act(r), ops.Act(dyb, C, C)
+    # forward: y (written into a channel slice) and the pooled copy
+    ybuf = torch.zeros((N, H, W, 2 * C), dtype=torch.bfloat16, device=DEV)
+    y = ops.Act(ybuf, C, C)
+    pooled = ops.Act.empty(N, H // 2, W // 2, C, DEV) if pool else None
+    ops.bn_apply(ra, scale, shift, y, pooled)
+    yref = torch.addcmul(shift, r.float(), scale).to(torch.bfloat16)
+    _close_on_gpu("bn apply", y.view(), yref, rel=2 ** -7, abs_frac=1e-6)
+    assert bool((ybuf[..., :C] == 0).all())
+    dy_total = dyb[..., C:].double()
+    dpool = None
+    if pool:
+        ypl = y.view().float().permute(0, 3, 1, 2)
+        pref, idx = torch.nn.functional.max_pool2d(ypl, 2, return_indices=True)
+        assert torch.equal(pooled.view().float().permute(0, 3, 1, 2), pref)
+        dpool = ops.Act(torch.randn((N, H // 2, W // 2, C), generator=g, device=DEV).to(torch.bfloat16))
+        # torch's max_pool2d backward routes to the first maximum in window order, like the kernel (SURVEY App. B.3)
+        routed = torch.nn.functional.max_unpool2d(dpool.view().double().permute(0, 3, 1, 2), idx, 2, output_size=(H, W))
+        dy_total = dy_total + routed.permute(0, 2, 3, 1)
+    # backward
+    f32 = dict(dtype=torch.float32, device=DEV)
+    dz = ops.Act.empty(N, H, W, C, DEV)
+    partial = torch.empty(ops.ew_rows() * 2 * C, **f32)
+    scratch = torch.empty(128 * 2 * C, **f32)
+    coef = torch.empty(3 * C, **f32)
+    dgamma, dbeta, dbias = (torch.empty(C, **f32) for _ in range(3))
+    ops.bn_bwd(dya, dpool, ra, scale, shift, mean32, invstd32, gamma, N * H * W, dz, partial, scratch, coef, dgamma, dbeta,
+               dbias)
+    torch.cuda.synchronize()
+    xh = (rd - mean) * invstd
+    rdb, rdg = dy_total.sum(dim=(0, 1, 2)), (dy_total * xh).sum(dim=(0, 1, 2))
+    cnt = float(N * H * W)
+    dr = gamma.double() * invstd * (dy_total - rdb / cnt - xh * rdg / cnt)
+    rdz = torch.where(rd > 0, dr, torch.zeros_like(dr))
+    _close_on_gpu("dgamma", dgamma, rdg, rel=1e-4, abs_frac=1e-4)
+    _close_on_gpu("dbeta", dbeta, rdb, rel=1e-4, abs_frac=1e-4)
+    _close_on_gpu("dz", dz.view(), rdz, rel=2 ** -7, abs_frac=2e-3)
+    _close_on_gpu("dbias", dbias, dz.view().double().sum(dim=(0, 1, 2)), rel=1e-4, abs_frac=1e-4)
+
+
+def test_copy_channels_many_items_per_thread(ops):
+    """slice copy at a size where every thread runs its unrolled loop several times, into / out of channel slices"""
+    N, H, W = 4, 256, 256
+    g = torch.Generator(device=DEV).manual_seed(9)
+    srcb = torch.randn((N, H, W, 192), generator=g, device=DEV).to(torch.bfloat16)
+    dstb = torch.zeros((N, H, W, 128), dtype=torch.bfloat16, device=DEV)
+    ops.copy_channels(ops.Act(srcb, 64, 64), ops.Act(dstb, 64, 64))
+    assert torch.equal(dstb[..., 64:], srcb[..., 64:128]) and bool((dstb[..., :64] == 0).all())
+
+
 @pytest.mark.parametrize("O_", [1, 3])
 def test_head_fwd_bwd_and_mask(ops, O_):
     N, H, W, C = 2, 16, 16, 64

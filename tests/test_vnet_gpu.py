@@ -118,6 +118,81 @@ def test_se_block_forward_backward(VF, N, H, W, C):
         check(f"se {name}", g.grad, r.grad, rel=1e-3, abs_frac=1e-3)
 
 
+def _gpu_close(name, got, ref, rel=2 ** -8, abs_frac=1e-3):
+    got, ref = got.double(), ref.double()
+    err = (got - ref).abs()
+    tol = rel * ref.abs() + abs_frac * float(ref.abs().max()) + 1e-30
+    nbad = int((err > tol).sum())
+    assert nbad == 0, f"{name}: {nbad}/{err.numel()} out of tolerance, max err {float(err.max()):.4g}"
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 512, 512, 64), (3, 128, 128, 128)])
+def test_se_block_large_images(VF, N, H, W, C):
+    """SE pooling with the 4096- and 1024-pixel chunks of high-resolution levels (b2s_se_chunks), and the scale kernel
+    with every thread looping; reference = the same formulas in torch fp64 on the GPU (models/vnet.py:18-26)"""
+    Cr = C // 4
+    g = torch.Generator(device=DEV).manual_seed(31)
+    x = torch.randn((N, H, W, C), generator=g, device=DEV).to(torch.bfloat16)
+    dy = torch.randn((N, H, W, C), generator=g, device=DEV).to(torch.bfloat16)
+    w1, b1, w2, b2 = rnd((Cr, C, 1, 1), 23, 0.2), rnd((Cr,), 24, 0.2), rnd((C, Cr, 1, 1), 25, 0.2), rnd((C,), 26, 0.2)
+    xg = x.clone().requires_grad_(True)
+    pg = [leaf(t) for t in (w1, b1, w2, b2)]
+    y = VF.SE.apply(xg, *pg)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    xr = x.double().requires_grad_(True)
+    pr = [t.double().to(DEV).requires_grad_(True) for t in (w1, b1, w2, b2)]
+    m = xr.mean(dim=(1, 2))
+    h = torch.relu(m @ pr[0].view(Cr, C).t() + pr[1])
+    gate = torch.sigmoid(h @ pr[2].view(C, Cr).t() + pr[3])
+    yr = xr * gate[:, None, None, :]
+    yr.backward(dy.double())
+    _gpu_close("se fwd", y.detach(), yr.detach())
+    _gpu_close("se dx", xg.grad, xr.grad, abs_frac=2e-3)
+    for name, gp, rp in zip(("dw1", "db1", "dw2", "db2"), pg, pr):
+        _gpu_close(f"se {name}", gp.grad, rp.grad, rel=1e-3, abs_frac=1e-3)
+
+
+@pytest.mark.parametrize("with_res", [False, True])
+def test_bn_act_streaming_kernels_many_items_per_thread(with_res):
+    """BN -> ReLU (+ residual) apply and its backward at a size where every thread walks its prefetch ring several times
+    around (the block tests below give a thread at most a few items); dropout off so torch formulas are the reference"""
+    import b200seg  # noqa: F401
+    from b200seg import ops
+    N, H, W, C = 6, 256, 256, 64
+    g = torch.Generator(device=DEV).manual_seed(17)
+    z = torch.randn((N, H, W, C), generator=g, device=DEV).to(torch.bfloat16)
+    da = torch.randn((N, H, W, C), generator=g, device=DEV).to(torch.bfloat16)
+    res = torch.randn((N, H, W, C), generator=g, device=DEV).to(torch.bfloat16) if with_res else None
+    gamma = torch.randn(C, generator=g, device=DEV) * 0.5 + 1.0
+    beta = torch.randn(C, generator=g, device=DEV) * 0.1
+    zd = z.double()
+    mean, var = zd.mean(dim=(0, 1, 2)), zd.var(dim=(0, 1, 2), unbiased=False)
+    invstd = 1.0 / torch.sqrt(var + 1e-5)
+    scale, shift = (gamma.double() * invstd).float(), (beta.double() - mean * gamma.double() * invstd).float()
+    out = ops.Act.empty(N, H, W, C, DEV)
+    ops.bn_act_apply(ops.Act(z), scale, shift, ops.Act(res) if with_res else None, out, relu=1)
+    ref = torch.relu(zd * scale.double() + shift.double()) + (res.double() if with_res else 0.0)
+    _gpu_close("bn_act_apply", out.view(), ref, rel=2 ** -7, abs_frac=1e-6)
+    f32 = dict(dtype=torch.float32, device=DEV)
+    dz = ops.Act.empty(N, H, W, C, DEV)
+    dgamma, dbeta, dbias = (torch.empty(C, **f32) for _ in range(3))
+    ops.bn_act_bwd(ops.Act(da), ops.Act(z), scale, shift, mean.float(), invstd.float(), gamma, float(N * H * W), dz, dgamma,
+                   dbeta, dbias, relu=1)
+    torch.cuda.synchronize()
+    pre = zd * scale.double() + shift.double()
+    d = torch.where(pre > 0, da.double(), torch.zeros_like(pre))
+    xh = (zd - mean) * invstd
+    rdb, rdg = d.sum(dim=(0, 1, 2)), (d * xh).sum(dim=(0, 1, 2))
+    cnt = float(N * H * W)
+    rdz = gamma.double() * invstd * (d - rdb / cnt - xh * rdg / cnt)
+    _gpu_close("dgamma", dgamma, rdg, rel=1e-4, abs_frac=1e-4)
+    _gpu_close("dbeta", dbeta, rdb, rel=1e-4, abs_frac=1e-4)
+    safe = (pre.abs() > 1e-5).double()      # the kernel's fp32 ReLU mask may differ from fp64 within rounding of zero
+    _gpu_close("dz", dz.view().double() * safe, rdz * safe, rel=2 ** -7, abs_frac=2e-3)
+    _gpu_close("dbias", dbias, dz.view().double().sum(dim=(0, 1, 2)), rel=1e-4, abs_frac=1e-4)
+
+
 @pytest.mark.parametrize("cin,cout,n", [(64, 64, 2), (256, 64, 3)])
 def test_conv_block_forward_backward(VF, cin, cout, n):
     """ConvBlock (conv -> BN -> ReLU, residual identity / 1x1 projection), train mode, dropout 0"""

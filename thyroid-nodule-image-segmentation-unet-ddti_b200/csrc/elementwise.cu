@@ -11,6 +11,10 @@ namespace b2s {
 // ------------------------------------------------------------------------------------------------
 constexpr int kRedY = 32;  // row groups per block of the small reduction kernels (block = 32 x 32 threads)
 
+// Rows a thread fetches before it starts adding: the loads of one batch are independent, so a thread waits for one
+// memory round trip per kRedBatch rows instead of one per row (these kernels are latency-, not bandwidth-bound).
+constexpr int kRedBatch = 8;
+
 __global__ void __launch_bounds__(32 * kRedY)
 reduce_rows_kernel(const float* __restrict__ in, int rows, int K, int rows_per_slice, float* __restrict__ out) {
   // grid (ceil(K/32), slices); block (32, kRedY): lane = column (coalesced), threadIdx.y strides over the rows
@@ -20,7 +24,17 @@ reduce_rows_kernel(const float* __restrict__ in, int rows, int K, int rows_per_s
   const int r1 = min(r0 + rows_per_slice, rows);
   double acc = 0.0;
   if (k < K)
-    for (int r = r0 + threadIdx.y; r < r1; r += kRedY) acc += static_cast<double>(in[static_cast<size_t>(r) * K + k]);
+    for (int r = r0 + threadIdx.y; r < r1; r += kRedY * kRedBatch) {
+      float v[kRedBatch];
+#pragma unroll
+      for (int j = 0; j < kRedBatch; ++j) {
+        const int rr = r + j * kRedY;          // rows past the end re-read the last row (unconditional load) and add 0
+        const float x = __ldg(in + static_cast<size_t>(min(rr, r1 - 1)) * K + k);
+        v[j] = rr < r1 ? x : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kRedBatch; ++j) acc += static_cast<double>(v[j]);   // same order as row by row
+    }
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && k < K) {
@@ -38,9 +52,18 @@ __device__ __forceinline__ void block_sum_pairs(const float* __restrict__ partia
   __shared__ double red[2][kRedY][33];
   double a0 = 0.0, a1 = 0.0;
   if (c < C)
-    for (int r = threadIdx.y; r < rows; r += kRedY) {
-      a0 += static_cast<double>(partial[(static_cast<size_t>(r) * 2) * C + c]);
-      a1 += static_cast<double>(partial[(static_cast<size_t>(r) * 2 + 1) * C + c]);
+    for (int r = threadIdx.y; r < rows; r += kRedY * kRedBatch) {
+      float v0[kRedBatch], v1[kRedBatch];
+#pragma unroll
+      for (int j = 0; j < kRedBatch; ++j) {
+        const int rr = r + j * kRedY;          // rows past the end re-read the last row (unconditional load) and add 0
+        const float* row = partial + (static_cast<size_t>(min(rr, rows - 1)) * 2) * C + c;
+        const float x0 = __ldg(row), x1 = __ldg(row + C);
+        v0[j] = rr < rows ? x0 : 0.f;
+        v1[j] = rr < rows ? x1 : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kRedBatch; ++j) { a0 += static_cast<double>(v0[j]); a1 += static_cast<double>(v1[j]); }
     }
   red[0][threadIdx.y][threadIdx.x] = a0;
   red[1][threadIdx.y][threadIdx.x] = a1;
@@ -396,11 +419,17 @@ __global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, con
 // ------------------------------------------------------------------------------------------------
 // BN apply (+ fused 2x2 max-pool)
 // ------------------------------------------------------------------------------------------------
+template <bool POOL> constexpr int bn_apply_depth() { return POOL ? 4 : 8; }
+template <bool POOL> constexpr int bn_apply_nv() { return POOL ? 4 : 1; }
+
 template <bool POOL>
 __global__ void __launch_bounds__(kThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __restrict__ scale,
                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int y_cs,
                 __nv_bfloat16* __restrict__ pooled, int N, int H, int W, int C) {
+  extern __shared__ uint4 ring_smem[];
+  constexpr int Q = bn_apply_nv<POOL>(), DEPTH = bn_apply_depth<POOL>();
+  const PrefetchRing<Q, DEPTH> ring(ring_smem);
   const int groups = C / 8;               // power of two (host-checked)
   const int gshift = __ffs(groups) - 1;
   const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
@@ -409,39 +438,61 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __re
   float sc[8], sh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sc[k] = scale[cg * 8 + k]; sh[k] = shift[cg * 8 + k]; }
-  if (!POOL) {
-    const long long total = static_cast<long long>(N) * H * W * groups;
-    for (long long i = tid; i < total; i += stride) {
-      const long long pix = i >> gshift;
+  const int Ho = POOL ? H / 2 : H, Wo = POOL ? W / 2 : W;
+  const long long total = static_cast<long long>(N) * Ho * Wo * groups;
+  // first pixel of work item i (a pixel, or the top-left pixel of a 2x2 pooling window)
+  auto first_pixel = [&](long long i) -> long long {
+    const unsigned pp = static_cast<unsigned>(i >> gshift);   // (pooled) pixel index < 2^31
+    if (!POOL) return pp;
+    const unsigned prow = pp / Wo;
+    const int wo = static_cast<int>(pp - prow * Wo);
+    const unsigned n = prow / Ho;
+    const int ho = static_cast<int>(prow - n * Ho);
+    return (static_cast<long long>(n) * H + 2 * ho) * W + 2 * wo;
+  };
+  auto fetch = [&](int stage, long long i) {
+    const long long p00 = first_pixel(i);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) ring.fetch(stage, q, r + (p00 + (q >> 1) * W + (q & 1)) * r_cs + cg * 8);
+  };
+  long long inext = tid;
+#pragma unroll
+  for (int s = 0; s < DEPTH; ++s) {
+    if (inext < total) fetch(s, inext);
+    cp_async_commit();
+    inext += stride;
+  }
+  int stage = 0;
+  for (long long i = tid; i < total; i += stride) {
+    cp_async_wait<DEPTH - 1>();
+    uint4 raw[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) raw[q] = ring.get(stage, q);
+    if (inext < total) fetch(stage, inext);     // the item is in registers: refill its slots
+    cp_async_commit();
+    inext += stride;
+    stage = stage + 1 == DEPTH ? 0 : stage + 1;
+    const long long p00 = first_pixel(i);
+    if (!POOL) {
       float v[8];
-      unpack8(ldg16(r + pix * r_cs + cg * 8), v);
+      unpack8(raw[0], v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
-      stg16(y + pix * y_cs + cg * 8, pack8(v));
-    }
-  } else {
-    const int Ho = H / 2, Wo = W / 2;
-    const long long total = static_cast<long long>(N) * Ho * Wo * groups;
-    for (long long i = tid; i < total; i += stride) {
-      const unsigned pp = static_cast<unsigned>(i >> gshift);   // pooled pixel index < 2^31
-      const unsigned prow = pp / Wo;
-      const int wo = static_cast<int>(pp - prow * Wo);
-      const unsigned n = prow / Ho;
-      const int ho = static_cast<int>(prow - n * Ho);
-      const long long p00 = (static_cast<long long>(n) * H + 2 * ho) * W + 2 * wo;
+      stg16(y + p00 * y_cs + cg * 8, pack8(v));
+    } else {
       float m[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const long long pix = p00 + (q >> 1) * W + (q & 1);
         float v[8];
-        unpack8(ldg16(r + pix * r_cs + cg * 8), v);
+        unpack8(raw[q], v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = bf16_round(fmaf(v[k], sc[k], sh[k]));
         stg16(y + pix * y_cs + cg * 8, pack8(v));
 #pragma unroll
         for (int k = 0; k < 8; ++k) m[k] = q == 0 ? v[k] : fmaxf(m[k], v[k]);
       }
-      stg16(pooled + static_cast<size_t>(pp) * C + cg * 8, pack8(m));
+      stg16(pooled + static_cast<size_t>(i >> gshift) * C + cg * 8, pack8(m));
     }
   }
 }
@@ -477,16 +528,21 @@ maxpool2x2_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, __nv_bfloat16* 
 // ------------------------------------------------------------------------------------------------
 // BN (+ReLU, + max-pool routing) backward
 // ------------------------------------------------------------------------------------------------
-// Loads dy for the 2x2 window (or single pixel) handled by this thread. With POOL, adds dpool to the FIRST
-// maximum of y = bf16(r*scale+shift) in row-major window order (torch max_pool2d backward semantics).
+template <bool POOL, bool APPLY> constexpr int bn_bwd_depth() { return POOL ? (APPLY ? 4 : 2) : 6; }
+template <bool POOL> constexpr int bn_bwd_nv() { return POOL ? 9 : 2; }
+
 template <bool POOL, bool APPLY>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (POOL && !APPLY) ? 2 : 1)
 bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat16* __restrict__ dpool,
               const __nv_bfloat16* __restrict__ r, int r_cs, const float* __restrict__ scale,
               const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
               const float* __restrict__ coef, __nv_bfloat16* __restrict__ dz, int dz_cs, float* __restrict__ partial,
               int N, int H, int W, int C) {
-  __shared__ float red[kThreads * 16];
+  extern __shared__ uint4 ring_smem[];      // prefetch ring; reused for the block reduction after the loop
+  constexpr int Q = POOL ? 4 : 1;           // pixels per work item (one 2x2 pooling window, or one pixel)
+  constexpr int NV = bn_bwd_nv<POOL>(), DEPTH = bn_bwd_depth<POOL, APPLY>();
+  static_assert(PrefetchRing<NV, DEPTH>::kBytes >= kThreads * 16 * 4, "ring too small for the block reduction");
+  const PrefetchRing<NV, DEPTH> ring(ring_smem);   // vectors [0,Q): r, [Q,2Q): dy, 2Q: dpool
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
   const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
@@ -504,85 +560,89 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
 
-  constexpr int Q = POOL ? 4 : 1;      // pixels per work item (one 2x2 pooling window, or one pixel)
-  constexpr int U = 1;                 // work items per loop trip (more loads in flight per thread measured no gain)
   const int Ho = POOL ? H / 2 : H, Wo = POOL ? W / 2 : W;
   const long long total = static_cast<long long>(N) * Ho * Wo * groups;
-  for (long long i0 = tid; i0 < total; i0 += stride * U) {
-    uint4 rraw[U][Q], graw[U][Q], praw[U];
-    long long p00[U];
+  auto first_pixel = [&](long long i) -> long long {
+    const unsigned pp = static_cast<unsigned>(i >> gshift);
+    if (!POOL) return pp;
+    const unsigned prow = pp / Wo;
+    const int wo = static_cast<int>(pp - prow * Wo);
+    const unsigned n = prow / Ho;
+    const int ho = static_cast<int>(prow - n * Ho);
+    return (static_cast<long long>(n) * H + 2 * ho) * W + 2 * wo;
+  };
+  auto fetch = [&](int stage, long long i) {
+    const long long p00 = first_pixel(i);
+    if (POOL) ring.fetch(stage, 2 * Q, dpool + static_cast<size_t>(i >> gshift) * C + cg * 8);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      const bool on = i < total;
-      const unsigned pp = static_cast<unsigned>((on ? i : i0) >> gshift);
-      p00[u] = pp;
-      if (POOL) {
-        const unsigned prow = pp / Wo;
-        const int wo = static_cast<int>(pp - prow * Wo);
-        const unsigned n = prow / Ho;
-        const int ho = static_cast<int>(prow - n * Ho);
-        p00[u] = (static_cast<long long>(n) * H + 2 * ho) * W + 2 * wo;
-        praw[u] = ldg16(dpool + static_cast<size_t>(pp) * C + cg * 8);
-      }
+    for (int q = 0; q < Q; ++q) {
+      const long long pix = p00 + (q >> 1) * W + (q & 1);
+      ring.fetch(stage, q, r + pix * r_cs + cg * 8);
+      ring.fetch(stage, Q + q, dy + pix * dy_cs + cg * 8);
+    }
+  };
+  long long inext = tid;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const long long pix = POOL ? p00[u] + (q >> 1) * W + (q & 1) : p00[u];
-        rraw[u][q] = ldg16(r + pix * r_cs + cg * 8);
-        graw[u][q] = ldg16(dy + pix * dy_cs + cg * 8);
+  for (int s = 0; s < DEPTH; ++s) {
+    if (inext < total) fetch(s, inext);
+    cp_async_commit();
+    inext += stride;
+  }
+  int stage = 0;
+  for (long long i = tid; i < total; i += stride) {
+    cp_async_wait<DEPTH - 1>();
+    float rv[Q][8], g[Q][8], dp[8];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { unpack8(ring.get(stage, q), rv[q]); unpack8(ring.get(stage, Q + q), g[q]); }
+    if (POOL) unpack8(ring.get(stage, 2 * Q), dp);
+    if (inext < total) fetch(stage, inext);     // the item is in registers: refill its slots
+    cp_async_commit();
+    inext += stride;
+    stage = stage + 1 == DEPTH ? 0 : stage + 1;
+    const long long p00 = first_pixel(i);
+    // With POOL, dpool goes to the FIRST maximum of y = bf16(r*scale+shift) in row-major window order (torch
+    // max_pool2d backward semantics).
+    if (POOL) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float best = bf16_round(fmaf(rv[0][k], sc[k], sh[k]));
+        int arg = 0;
+#pragma unroll
+        for (int q = 1; q < Q; ++q) {
+          const float yv = bf16_round(fmaf(rv[q][k], sc[k], sh[k]));
+          if (yv > best) { best = yv; arg = q; }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) g[q][k] += (arg == q) ? dp[k] : 0.f;
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (i0 + u * stride >= total) break;
-      float rv[Q][8], g[Q][8];
+    for (int q = 0; q < Q; ++q) {
+      float out[8];
 #pragma unroll
-      for (int q = 0; q < Q; ++q) { unpack8(rraw[u][q], rv[q]); unpack8(graw[u][q], g[q]); }
-      if (POOL) {
-        float dp[8];
-        unpack8(praw[u], dp);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float best = bf16_round(fmaf(rv[0][k], sc[k], sh[k]));
-          int arg = 0;
-#pragma unroll
-          for (int q = 1; q < Q; ++q) {
-            const float yv = bf16_round(fmaf(rv[q][k], sc[k], sh[k]));
-            if (yv > best) { best = yv; arg = q; }
-          }
-#pragma unroll
-          for (int q = 0; q < Q; ++q) g[q][k] += (arg == q) ? dp[k] : 0.f;
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (rv[q][k] - mu[k]) * is[k];
+        if (!APPLY) {
+          acc[k] += g[q][k];
+          acc[8 + k] = fmaf(g[q][k], xh, acc[8 + k]);
+        } else {
+          float d = c0[k] * (g[q][k] - c1[k] - xh * c2[k]);
+          d = rv[q][k] > 0.f ? d : 0.f;
+          d = bf16_round(d);
+          out[k] = d;
+          acc[k] += d;
         }
       }
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        float out[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float xh = (rv[q][k] - mu[k]) * is[k];
-          if (!APPLY) {
-            acc[k] += g[q][k];
-            acc[8 + k] = fmaf(g[q][k], xh, acc[8 + k]);
-          } else {
-            float d = c0[k] * (g[q][k] - c1[k] - xh * c2[k]);
-            d = rv[q][k] > 0.f ? d : 0.f;
-            d = bf16_round(d);
-            out[k] = d;
-            acc[k] += d;
-          }
-        }
-        if (APPLY) {
-          const long long pix = POOL ? p00[u] + (q >> 1) * W + (q & 1) : p00[u];
-          stg16(dz + pix * dz_cs + cg * 8, pack8(out));
-        }
-      }
+      if (APPLY) stg16(dz + (p00 + (q >> 1) * W + (q & 1)) * dz_cs + cg * 8, pack8(out));
     }
   }
   // block partials: !APPLY -> row [2][C] (sum dy, sum dy*xhat); APPLY -> row [C] (sum dz = conv bias gradient)
-  constexpr int NV = APPLY ? 8 : 16;
+  constexpr int NV_RED = APPLY ? 8 : 16;
+  float* red = reinterpret_cast<float*>(ring_smem);
+  cp_async_wait<0>();
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NV; ++k) red[threadIdx.x * NV + k] = acc[k];
+  for (int k = 0; k < NV_RED; ++k) red[threadIdx.x * NV_RED + k] = acc[k];
   __syncthreads();
   const int per_group = kThreads / groups;
   const int nout = APPLY ? C : 2 * C;
@@ -592,7 +652,7 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
     const int which = o / C, ch = o - which * C;
     const int gi = ch / 8, k = ch % 8;
     float s = 0.f;
-    for (int t = 0; t < per_group; ++t) s += red[(t * groups + gi) * NV + which * 8 + k];
+    for (int t = 0; t < per_group; ++t) s += red[(t * groups + gi) * NV_RED + which * 8 + k];
     row[o] = s;
   }
   // the partial buffer always has kEwBlocks rows; rows beyond the (occupancy-sized) grid are zero-filled
@@ -1145,12 +1205,27 @@ __global__ void __launch_bounds__(kThreads)
 copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_bfloat16* __restrict__ dst, int dst_cs,
                      long long npix, int C) {
   const int groups = C / 8;
+  const bool pow2 = (groups & (groups - 1)) == 0;
+  const int gshift = __ffs(groups) - 1;
   const long long total = npix * groups;
-  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
-    const long long pix = static_cast<unsigned long long>(i) / static_cast<unsigned>(groups);
-    const int cg = static_cast<int>(i - pix * groups);
-    stg16(dst + pix * dst_cs + cg * 8, ldg16(src + pix * src_cs + cg * 8));
+  const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  constexpr int U = 4;   // independent 16-byte loads in flight per thread
+  for (long long i0 = tid; i0 < total; i0 += stride * U) {
+    uint4 raw[U];
+    long long off[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      const long long ic = i < total ? i : i0;
+      const long long pix = pow2 ? ic >> gshift : ic / groups;
+      const int cg = static_cast<int>(ic - pix * groups);
+      raw[u] = ldg16(src + pix * src_cs + cg * 8);
+      off[u] = pix * dst_cs + cg * 8;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * stride < total) stg16(dst + off[u], raw[u]);
   }
 }
 
@@ -1161,15 +1236,6 @@ static int grid_for(long long work_items, int per_block) {
   return static_cast<int>(blocks);
 }
 static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
-// One full wave: SM count x resident blocks of this kernel (at most kEwBlocks = 4 per SM), so that a grid-stride
-// kernel whose every block does the same amount of work has no partial last wave.
-template <typename K>
-static int one_wave_grid(K kernel) {
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
-  if (occ > kEwBlocks / kSMs) occ = kEwBlocks / kSMs;
-  return kSMs * occ;
-}
 // channel counts the vectorised element-wise kernels accept: C/8 must divide 256
 static bool ew_channels_ok(int C) { return C >= 8 && C % 8 == 0 && pow2(C / 8) && C / 8 <= kThreads; }
 
@@ -1275,13 +1341,20 @@ extern "C" int b2s_bn_apply(const void* r, int r_cstride, const float* scale, co
   count_launch();
   if (pooled) {
     if (H % 2 || W % 2) return set_error(B2S_ERR_ARG, "b2s_bn_apply: pooling needs even H and W");
+    constexpr int smem = PrefetchRing<bn_apply_nv<true>(), bn_apply_depth<true>()>::kBytes;
+    ew_allow_smem(bn_apply_kernel<true>, smem);
     const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-    bn_apply_kernel<true><<<grid_for(items, kThreads * 2), kThreads, 0, STREAM(stream)>>>(
-        rp, r_cstride, scale, shift, yp, y_cstride, static_cast<__nv_bfloat16*>(pooled), N, H, W, C);
+    static const int wave = ew_wave_blocks(bn_apply_kernel<true>, smem);
+    bn_apply_kernel<true><<<ew_clamp_grid(wave, items, kThreads * 2), kThreads, smem,
+                            STREAM(stream)>>>(rp, r_cstride, scale, shift, yp, y_cstride,
+                                              static_cast<__nv_bfloat16*>(pooled), N, H, W, C);
   } else {
+    constexpr int smem = PrefetchRing<bn_apply_nv<false>(), bn_apply_depth<false>()>::kBytes;
+    ew_allow_smem(bn_apply_kernel<false>, smem);
     const long long items = static_cast<long long>(N) * H * W * (C / 8);
-    bn_apply_kernel<false><<<grid_for(items, kThreads * 4), kThreads, 0, STREAM(stream)>>>(
-        rp, r_cstride, scale, shift, yp, y_cstride, nullptr, N, H, W, C);
+    static const int wave = ew_wave_blocks(bn_apply_kernel<false>, smem);
+    bn_apply_kernel<false><<<ew_clamp_grid(wave, items, kThreads * 4), kThreads, smem,
+                             STREAM(stream)>>>(rp, r_cstride, scale, shift, yp, y_cstride, nullptr, N, H, W, C);
   }
   return check_launch("bn_apply_kernel");
 }
@@ -1307,15 +1380,22 @@ extern "C" int b2s_bn_bwd_reduce(const void* dy, int dy_cstride, const void* dpo
   const auto* rp = static_cast<const __nv_bfloat16*>(r);
   count_launch();
   // one full wave of blocks; the kernel zero-fills the partial rows beyond its grid
-  static const int grid_pool = one_wave_grid(bn_bwd_kernel<true, false>);
-  static const int grid_flat = one_wave_grid(bn_bwd_kernel<false, false>);
-  if (dpool)
-    bn_bwd_kernel<true, false><<<grid_pool, kThreads, 0, STREAM(stream)>>>(
+  constexpr int smem_pool = PrefetchRing<bn_bwd_nv<true>(), bn_bwd_depth<true, false>()>::kBytes;
+  constexpr int smem_flat = PrefetchRing<bn_bwd_nv<false>(), bn_bwd_depth<false, false>()>::kBytes;
+  if (dpool) {
+    ew_allow_smem(bn_bwd_kernel<true, false>, smem_pool);
+    static const int wave = ew_wave_blocks(bn_bwd_kernel<true, false>, smem_pool);
+    bn_bwd_kernel<true, false><<<wave, kThreads, smem_pool,
+                                 STREAM(stream)>>>(
         dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, nullptr,
         nullptr, 0, partial, N, H, W, C);
-  else
-    bn_bwd_kernel<false, false><<<grid_flat, kThreads, 0, STREAM(stream)>>>(
+  } else {
+    ew_allow_smem(bn_bwd_kernel<false, false>, smem_flat);
+    static const int wave = ew_wave_blocks(bn_bwd_kernel<false, false>, smem_flat);
+    bn_bwd_kernel<false, false><<<wave, kThreads, smem_flat,
+                                  STREAM(stream)>>>(
         dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, nullptr, nullptr, 0, partial, N, H, W, C);
+  }
   return check_launch("bn_bwd_kernel<reduce>");
 }
 
@@ -1345,16 +1425,23 @@ extern "C" int b2s_bn_bwd_apply(const void* dy, int dy_cstride, const void* dpoo
   const auto* rp = static_cast<const __nv_bfloat16*>(r);
   auto* dzp = static_cast<__nv_bfloat16*>(dz);
   count_launch();
-  static const int grid_pool = one_wave_grid(bn_bwd_kernel<true, true>);
-  static const int grid_flat = one_wave_grid(bn_bwd_kernel<false, true>);
-  if (dpool)
-    bn_bwd_kernel<true, true><<<grid_pool, kThreads, 0, STREAM(stream)>>>(
+  constexpr int smem_pool = PrefetchRing<bn_bwd_nv<true>(), bn_bwd_depth<true, true>()>::kBytes;
+  constexpr int smem_flat = PrefetchRing<bn_bwd_nv<false>(), bn_bwd_depth<false, true>()>::kBytes;
+  if (dpool) {
+    ew_allow_smem(bn_bwd_kernel<true, true>, smem_pool);
+    static const int wave = ew_wave_blocks(bn_bwd_kernel<true, true>, smem_pool);
+    bn_bwd_kernel<true, true><<<wave, kThreads, smem_pool,
+                                STREAM(stream)>>>(
         dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, coef, dzp,
         dz_cstride, dbias_partial, N, H, W, C);
-  else
-    bn_bwd_kernel<false, true><<<grid_flat, kThreads, 0, STREAM(stream)>>>(
+  } else {
+    ew_allow_smem(bn_bwd_kernel<false, true>, smem_flat);
+    static const int wave = ew_wave_blocks(bn_bwd_kernel<false, true>, smem_flat);
+    bn_bwd_kernel<false, true><<<wave, kThreads, smem_flat,
+                                 STREAM(stream)>>>(
         dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, coef, dzp, dz_cstride, dbias_partial, N, H,
         W, C);
+  }
   return check_launch("bn_bwd_kernel<apply>");
 }
 

@@ -31,11 +31,17 @@ __device__ __forceinline__ uint32_t drop_keep8(unsigned long long idx8, uint32_t
 
 // relu == 1: out = dropout(relu(z * scale + shift)) + res      (models/vnet.py:51-59)
 // relu == 2: out = relu(z * scale + shift + res)                (ResidualBlock, models/mod.py:84);  relu == 0: no ReLU
+constexpr int kBnActDepth = 6;   // work items each thread keeps in flight (PrefetchRing, ew_common.cuh)
+
+template <bool HAS_RES>
 __global__ void __launch_bounds__(kThreads)
 bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* __restrict__ scale,
                     const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_cs,
                     __nv_bfloat16* __restrict__ out, int out_cs, long long npix, int C, int relu, uint32_t drop_thresh,
                     float drop_scale, uint32_t seed, const long long* __restrict__ step_counter) {
+  extern __shared__ uint4 ring_smem[];
+  constexpr int NV = HAS_RES ? 2 : 1, DEPTH = kBnActDepth;
+  const PrefetchRing<NV, DEPTH> ring(ring_smem);   // vector 0: z, 1: res
   if (step_counter) seed ^= mix32(static_cast<uint32_t>(*step_counter) + 0x632be5abU);
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
@@ -46,18 +52,36 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* 
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sc[k] = scale ? scale[cg * 8 + k] : 1.f; sh[k] = shift ? shift[cg * 8 + k] : 0.f; }
   const long long total = npix * groups;
-  for (long long i = tid; i < total; i += stride) {
+  auto fetch = [&](int stage, long long i) {
     const long long pix = i >> gshift;
+    ring.fetch(stage, 0, z + pix * z_cs + cg * 8);
+    if (HAS_RES) ring.fetch(stage, 1, res + pix * res_cs + cg * 8);
+  };
+  long long inext = tid;
+#pragma unroll
+  for (int s = 0; s < DEPTH; ++s) {
+    if (inext < total) fetch(s, inext);
+    cp_async_commit();
+    inext += stride;
+  }
+  int stage = 0;
+  for (long long i = tid; i < total; i += stride) {
+    cp_async_wait<DEPTH - 1>();
     float v[8], rr[8];
-    unpack8(ldg16(z + pix * z_cs + cg * 8), v);
-    if (res) unpack8(ldg16(res + pix * res_cs + cg * 8), rr);
+    unpack8(ring.get(stage, 0), v);
+    if (HAS_RES) unpack8(ring.get(stage, 1), rr);
+    if (inext < total) fetch(stage, inext);     // the item is in registers: refill its slots
+    cp_async_commit();
+    inext += stride;
+    stage = stage + 1 == DEPTH ? 0 : stage + 1;
+    const long long pix = i >> gshift;
     const uint32_t keep = drop_thresh ? drop_keep8(static_cast<unsigned long long>(pix) * C + cg * 8, seed, drop_thresh) : 0xFFu;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float a = fmaf(v[k], sc[k], sh[k]);
       if (relu == 1) a = fmaxf(a, 0.f);
       if (drop_thresh) a = (keep >> k) & 1u ? a * drop_scale : 0.f;
-      if (res) a += rr[k];
+      if (HAS_RES) a += rr[k];
       if (relu == 2) a = fmaxf(a, 0.f);
       v[k] = a;
     }
@@ -75,7 +99,9 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
                   const float* __restrict__ invstd, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dz,
                   int dz_cs, float* __restrict__ partial, long long npix, int C, int relu, uint32_t drop_thresh,
                   float drop_scale, uint32_t seed, const long long* __restrict__ step_counter) {
-  __shared__ float red[kThreads * 16];
+  extern __shared__ uint4 ring_smem[];      // prefetch ring; reused for the block reduction after the loop
+  constexpr int DEPTH = kBnActDepth;
+  const PrefetchRing<2, DEPTH> ring(ring_smem);    // vector 0: z, 1: da
   if (step_counter) seed ^= mix32(static_cast<uint32_t>(*step_counter) + 0x632be5abU);
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
@@ -93,11 +119,29 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
   const long long total = npix * groups;
-  for (long long i = tid; i < total; i += stride) {
+  auto fetch = [&](int stage, long long i) {
     const long long pix = i >> gshift;
+    ring.fetch(stage, 0, z + pix * z_cs + cg * 8);
+    ring.fetch(stage, 1, da + pix * da_cs + cg * 8);
+  };
+  long long inext = tid;
+#pragma unroll
+  for (int s = 0; s < DEPTH; ++s) {
+    if (inext < total) fetch(s, inext);
+    cp_async_commit();
+    inext += stride;
+  }
+  int stage = 0;
+  for (long long i = tid; i < total; i += stride) {
+    cp_async_wait<DEPTH - 1>();
     float zv[8], g[8], outv[8];
-    unpack8(ldg16(z + pix * z_cs + cg * 8), zv);
-    unpack8(ldg16(da + pix * da_cs + cg * 8), g);
+    unpack8(ring.get(stage, 0), zv);
+    unpack8(ring.get(stage, 1), g);
+    if (inext < total) fetch(stage, inext);     // the item is in registers: refill its slots
+    cp_async_commit();
+    inext += stride;
+    stage = stage + 1 == DEPTH ? 0 : stage + 1;
+    const long long pix = i >> gshift;
     const uint32_t keep = drop_thresh ? drop_keep8(static_cast<unsigned long long>(pix) * C + cg * 8, seed, drop_thresh) : 0xFFu;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -116,6 +160,8 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
     }
     if (APPLY) stg16(dz + pix * dz_cs + cg * 8, pack8(outv));
   }
+  float* red = reinterpret_cast<float*>(ring_smem);
+  cp_async_wait<0>();
   constexpr int NV = APPLY ? 8 : 16;
   __syncthreads();
 #pragma unroll
@@ -148,11 +194,21 @@ channel_sums_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, float* __rest
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   const long long total = npix * groups;
-  for (long long i = tid; i < total; i += stride) {
-    float v[8];
-    unpack8(ldg16(x + (i >> gshift) * x_cs + cg * 8), v);
+  constexpr int U = 4;   // independent 16-byte loads in flight per thread
+  for (long long i0 = tid; i0 < total; i0 += stride * U) {
+    uint4 raw[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      raw[u] = i < total ? ldg16(x + (i >> gshift) * x_cs + cg * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float v[8];
+      unpack8(raw[u], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
@@ -245,7 +301,11 @@ maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_
 }
 
 // ---- squeeze-and-excitation (models/vnet.py:5-26) ------------------------------------------------------------
-constexpr int kSePixPerBlock = 256;    // pixels of one sample reduced by one block (small: deep levels have few pixels)
+// Pixels of one sample reduced by one block: 256 at the deep levels (few pixels per sample), more at high resolution
+// so that a block streams >= 0.5 MB instead of paying a launch + block reduction per 32 KB.
+__host__ __device__ constexpr int se_pix_per_block(long long HW) {
+  return HW >= (1ll << 18) ? 4096 : HW >= (1ll << 14) ? 1024 : 256;
+}
 
 // partial[n][chunk][C] = sum over the chunk's pixels of x (DOT: of x * y)
 template <bool DOT>
@@ -258,8 +318,9 @@ se_pool_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat1
   const int pl = threadIdx.x / groups;
   const int ppi = kThreads / groups;
   const int n = blockIdx.y, chunk = blockIdx.x;
-  const long long p0 = static_cast<long long>(chunk) * kSePixPerBlock;
-  const long long p1 = min(p0 + kSePixPerBlock, HW);
+  const int ppb = se_pix_per_block(HW);
+  const long long p0 = static_cast<long long>(chunk) * ppb;
+  const long long p1 = min(p0 + ppb, HW);
   const long long base = static_cast<long long>(n) * HW;
   float acc[8];
 #pragma unroll
@@ -341,23 +402,42 @@ se_scale_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const float* __re
                 int C, long long npix) {
   // forward: y = x * gate;  backward (add != nullptr): dx = dy * gate + add[n][c] * add_scale, with x := dy
   const int groups = C / 8;
+  const bool pow2 = (groups & (groups - 1)) == 0;
+  const int gshift = __ffs(groups) - 1;
   const long long total = npix * groups;
-  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
-    const int cg = static_cast<int>(i % groups);
-    const long long pix = i / groups;
-    const long long n = pix / HW;
-    float v[8];
-    unpack8(ldg16(x + pix * x_cs + cg * 8), v);
-    const float* gp = gate + n * C + cg * 8;
+  const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  constexpr int U = 4;   // independent 16-byte loads in flight per thread
+  for (long long i0 = tid; i0 < total; i0 += stride * U) {
+    uint4 raw[U];
+    long long pixs[U];
+    int cgs[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] *= gp[k];
-    if (add) {
-      const float* ap = add + n * C + cg * 8;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaf(ap[k], add_scale, v[k]);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      const long long ic = i < total ? i : i0;
+      pixs[u] = pow2 ? ic >> gshift : ic / groups;
+      cgs[u] = static_cast<int>(pow2 ? ic & (groups - 1) : ic - pixs[u] * groups);
+      raw[u] = ldg16(x + pixs[u] * x_cs + cgs[u] * 8);
     }
-    stg16(y + pix * y_cs + cg * 8, pack8(v));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= total) break;
+      const long long n = static_cast<unsigned long long>(pixs[u]) / static_cast<unsigned long long>(HW);
+      float v[8];
+      unpack8(raw[u], v);
+      const float4* gp = reinterpret_cast<const float4*>(gate + n * C + cgs[u] * 8);
+      const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+      v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+      if (add) {
+        const float4* ap = reinterpret_cast<const float4*>(add + n * C + cgs[u] * 8);
+        const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+        v[0] = fmaf(a0.x, add_scale, v[0]); v[1] = fmaf(a0.y, add_scale, v[1]); v[2] = fmaf(a0.z, add_scale, v[2]);
+        v[3] = fmaf(a0.w, add_scale, v[3]); v[4] = fmaf(a1.x, add_scale, v[4]); v[5] = fmaf(a1.y, add_scale, v[5]);
+        v[6] = fmaf(a1.z, add_scale, v[6]); v[7] = fmaf(a1.w, add_scale, v[7]);
+      }
+      stg16(y + pixs[u] * y_cs + cgs[u] * 8, pack8(v));
+    }
   }
 }
 
@@ -419,15 +499,6 @@ outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float
 using namespace b2s;
 #define STREAM(s) static_cast<cudaStream_t>(s)
 
-// SM count x resident blocks (at most kEwBlocks / kSMs = 4 per SM): one full wave, no partial last wave
-template <typename K>
-static int wave_grid(K kernel) {
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
-  if (occ > kEwBlocks / kSMs) occ = kEwBlocks / kSMs;
-  return kSMs * occ;
-}
-
 // 16-bit threshold: P(drop) = thresh / 65536 (p is quantised to 1/65536; the kept values are scaled by the exact
 // reciprocal of the quantised keep probability so the mask stays unbiased)
 static uint32_t drop_threshold(float p) {
@@ -451,10 +522,25 @@ extern "C" int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale
     return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: strides must be multiples of 8");
   if (dropout_p < 0.f || dropout_p >= 1.f) return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: dropout_p in [0,1)");
   count_launch();
-  bn_act_apply_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
-      static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, static_cast<const __nv_bfloat16*>(res), res_cstride,
-      static_cast<__nv_bfloat16*>(out), out_cstride, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed,
-      step_counter);
+  const long long items = npix * (C / 8);
+  if (res) {
+    constexpr int smem = PrefetchRing<2, kBnActDepth>::kBytes;
+    ew_allow_smem(bn_act_apply_kernel<true>, smem);
+    static const int wave = ew_wave_blocks(bn_act_apply_kernel<true>, smem);
+    bn_act_apply_kernel<true><<<ew_clamp_grid(wave, items, kThreads * 4), kThreads, smem,
+                                STREAM(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, static_cast<const __nv_bfloat16*>(res),
+        res_cstride, static_cast<__nv_bfloat16*>(out), out_cstride, npix, C, relu, drop_threshold(dropout_p),
+        drop_scale_of(dropout_p), seed, step_counter);
+  } else {
+    constexpr int smem = PrefetchRing<1, kBnActDepth>::kBytes;
+    ew_allow_smem(bn_act_apply_kernel<false>, smem);
+    static const int wave = ew_wave_blocks(bn_act_apply_kernel<false>, smem);
+    bn_act_apply_kernel<false><<<ew_clamp_grid(wave, items, kThreads * 4), kThreads, smem,
+                                 STREAM(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, nullptr, 0, static_cast<__nv_bfloat16*>(out),
+        out_cstride, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed, step_counter);
+  }
   return check_launch("bn_act_apply_kernel");
 }
 
@@ -466,8 +552,10 @@ extern "C" int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void*
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: unsupported C");
   count_launch();
-  static const int grid = wave_grid(bn_act_bwd_kernel<false>);
-  bn_act_bwd_kernel<false><<<grid, kThreads, 0, STREAM(stream)>>>(
+  constexpr int smem = PrefetchRing<2, kBnActDepth>::kBytes;
+  ew_allow_smem(bn_act_bwd_kernel<false>, smem);
+  static const int wave = ew_wave_blocks(bn_act_bwd_kernel<false>, smem);
+  bn_act_bwd_kernel<false><<<wave, kThreads, smem, STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
       mean, invstd, nullptr, nullptr, 0, partial, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed,
       step_counter);
@@ -482,8 +570,10 @@ extern "C" int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* 
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: unsupported C");
   count_launch();
-  static const int grid = wave_grid(bn_act_bwd_kernel<true>);
-  bn_act_bwd_kernel<true><<<grid, kThreads, 0, STREAM(stream)>>>(
+  constexpr int smem = PrefetchRing<2, kBnActDepth>::kBytes;
+  ew_allow_smem(bn_act_bwd_kernel<true>, smem);
+  static const int wave = ew_wave_blocks(bn_act_bwd_kernel<true>, smem);
+  bn_act_bwd_kernel<true><<<wave, kThreads, smem, STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
       mean, invstd, coef, static_cast<__nv_bfloat16*>(dz), dz_cstride, dbias_partial, npix, C, relu,
       drop_threshold(dropout_p), drop_scale_of(dropout_p), seed, step_counter);
@@ -534,7 +624,10 @@ extern "C" int b2s_upsample_zero2x(const void* src, int src_cstride, void* dst, 
   return check_launch("upsample_zero2x_kernel");
 }
 
-extern "C" int b2s_se_chunks(long long HW) { return static_cast<int>((HW + kSePixPerBlock - 1) / kSePixPerBlock); }
+extern "C" int b2s_se_chunks(long long HW) {
+  const int ppb = se_pix_per_block(HW);
+  return static_cast<int>((HW + ppb - 1) / ppb);
+}
 
 // partial [N][b2s_se_chunks(HW)][C]: sums of x over H*W (y == NULL) or of x*y (the gate gradient) per sample, channel
 extern "C" int b2s_se_pool(const void* x, int x_cstride, const void* y, int y_cstride, float* partial, int N,
