@@ -7,42 +7,52 @@
 namespace b2s {
 
 // ---- counter-based dropout mask: depends only on (seed, logical NHWC element index) so backward re-derives it ----
-// One 64-bit hash per group of four consecutive channels supplies four 16-bit uniforms: keep iff u16 >= p * 65536.
+// Eight 16-bit uniforms per group of eight consecutive channels: keep iff u16 >= p * 65536. The first 32 bits are a
+// full-avalanche hash of (seed, group index); the other three words are cheap bijective multiply-xorshift steps of
+// it (the kernels that draw the mask are instruction-issue bound, so the mask has to cost few instructions).
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
-// keep mask (bit k = keep element k) of the 8 consecutive elements starting at idx8 (a multiple of 8)
-__device__ __forceinline__ uint32_t drop_keep8(unsigned long long idx8, uint32_t seed, uint32_t thresh16) {
-  const uint32_t lo = static_cast<uint32_t>(idx8 >> 2), hi = static_cast<uint32_t>(idx8 >> 34);
-  const uint32_t base = mix32(hi + seed);
-  uint32_t mask = 0;
+struct DropMask {
+  uint32_t base0;     // mix32(seed): the per-launch key of indices below 2^35 (the usual case)
+  uint32_t seed, thresh16;
+  float keep_scale;   // 1 / (1 - p), p quantised to 1/65536
+  __device__ __forceinline__ DropMask(uint32_t seed_, uint32_t thresh16_, float keep_scale_)
+      : base0(mix32(seed_)), seed(seed_), thresh16(thresh16_), keep_scale(keep_scale_) {}
+  // f[k] = keep_scale if element idx8 + k is kept, else 0 (idx8: a multiple of 8)
+  __device__ __forceinline__ void factors(unsigned long long idx8, float (&f)[8]) const {
+    const uint32_t lo = static_cast<uint32_t>(idx8 >> 3), hi = static_cast<uint32_t>(idx8 >> 35);
+    const uint32_t base = hi ? mix32(hi + seed) : base0;
+    uint32_t h[4];
+    h[0] = mix32(lo ^ base);
+    h[1] = h[0] * 0x9e3779b1U; h[1] ^= h[1] >> 15;
+    h[2] = h[1] * 0x85ebca77U; h[2] ^= h[2] >> 13;
+    h[3] = h[2] * 0xc2b2ae3dU; h[3] ^= h[3] >> 16;
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const uint32_t h0 = mix32((lo + g) ^ base);
-    const uint32_t h1 = mix32(h0 + 0x9e3779b9U);
-    mask |= ((h0 & 0xFFFFu) >= thresh16 ? 1u : 0u) << (4 * g + 0);
-    mask |= ((h0 >> 16) >= thresh16 ? 1u : 0u) << (4 * g + 1);
-    mask |= ((h1 & 0xFFFFu) >= thresh16 ? 1u : 0u) << (4 * g + 2);
-    mask |= ((h1 >> 16) >= thresh16 ? 1u : 0u) << (4 * g + 3);
+    for (int j = 0; j < 4; ++j) {
+      f[2 * j] = (h[j] & 0xFFFFu) >= thresh16 ? keep_scale : 0.f;
+      f[2 * j + 1] = (h[j] >> 16) >= thresh16 ? keep_scale : 0.f;
+    }
   }
-  return mask;
-}
+};
 
-// relu == 1: out = dropout(relu(z * scale + shift)) + res      (models/vnet.py:51-59)
-// relu == 2: out = relu(z * scale + shift + res)                (ResidualBlock, models/mod.py:84);  relu == 0: no ReLU
 constexpr int kBnActDepth = 6;   // work items each thread keeps in flight (PrefetchRing, ew_common.cuh)
 
-template <bool HAS_RES>
+// RELU == 1: out = dropout(relu(z * scale + shift)) + res      (models/vnet.py:51-59)
+// RELU == 2: out = relu(z * scale + shift + res)                (ResidualBlock, models/mod.py:84);  RELU == 0: no ReLU
+template <int RELU, bool DROP, bool HAS_RES>
 __global__ void __launch_bounds__(kThreads)
 bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* __restrict__ scale,
                     const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_cs,
-                    __nv_bfloat16* __restrict__ out, int out_cs, long long npix, int C, int relu, uint32_t drop_thresh,
+                    __nv_bfloat16* __restrict__ out, int out_cs, long long npix, int C, uint32_t drop_thresh,
                     float drop_scale, uint32_t seed, const long long* __restrict__ step_counter) {
+  pdl_entry();
   extern __shared__ uint4 ring_smem[];
   constexpr int NV = HAS_RES ? 2 : 1, DEPTH = kBnActDepth;
   const PrefetchRing<NV, DEPTH> ring(ring_smem);   // vector 0: z, 1: res
-  if (step_counter) seed ^= mix32(static_cast<uint32_t>(*step_counter) + 0x632be5abU);
+  if (DROP && step_counter) seed ^= mix32(static_cast<uint32_t>(*step_counter) + 0x632be5abU);
+  const DropMask mask(seed, drop_thresh, drop_scale);
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
   const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
@@ -67,7 +77,7 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* 
   int stage = 0;
   for (long long i = tid; i < total; i += stride) {
     cp_async_wait<DEPTH - 1>();
-    float v[8], rr[8];
+    float v[8], rr[8], f[8];
     unpack8(ring.get(stage, 0), v);
     if (HAS_RES) unpack8(ring.get(stage, 1), rr);
     if (inext < total) fetch(stage, inext);     // the item is in registers: refill its slots
@@ -75,34 +85,36 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* 
     inext += stride;
     stage = stage + 1 == DEPTH ? 0 : stage + 1;
     const long long pix = i >> gshift;
-    const uint32_t keep = drop_thresh ? drop_keep8(static_cast<unsigned long long>(pix) * C + cg * 8, seed, drop_thresh) : 0xFFu;
+    if (DROP) mask.factors(static_cast<unsigned long long>(pix) * C + cg * 8, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float a = fmaf(v[k], sc[k], sh[k]);
-      if (relu == 1) a = fmaxf(a, 0.f);
-      if (drop_thresh) a = (keep >> k) & 1u ? a * drop_scale : 0.f;
+      if (RELU == 1) a = fmaxf(a, 0.f);
+      if (DROP) a *= f[k];
       if (HAS_RES) a += rr[k];
-      if (relu == 2) a = fmaxf(a, 0.f);
+      if (RELU == 2) a = fmaxf(a, 0.f);
       v[k] = a;
     }
     stg16(out + pix * out_cs + cg * 8, pack8(v));
   }
 }
 
-// Backward of a = dropout(relu(bn(z))): dy = da * keep/(1-p) * (bn(z) > 0).
+// Backward of a = dropout(relu(bn(z))): dy = da * keep/(1-p) * (bn(z) > 0)   (RELU: the ReLU sits before the dropout).
 // APPLY = false: partial [grid][2][C] = sum dy, sum dy * xhat;   APPLY = true: dz = c0 (dy - c1 - xhat c2), partial
 // [grid][C] = sum dz (gradient of the conv bias). Rows beyond the grid are zero-filled (kEwBlocks rows in total).
-template <bool APPLY>
+template <bool APPLY, bool RELU, bool DROP>
 __global__ void __launch_bounds__(kThreads)
 bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bfloat16* __restrict__ z, int z_cs,
                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dz,
-                  int dz_cs, float* __restrict__ partial, long long npix, int C, int relu, uint32_t drop_thresh,
+                  int dz_cs, float* __restrict__ partial, long long npix, int C, uint32_t drop_thresh,
                   float drop_scale, uint32_t seed, const long long* __restrict__ step_counter) {
+  pdl_entry();
   extern __shared__ uint4 ring_smem[];      // prefetch ring; reused for the block reduction after the loop
   constexpr int DEPTH = kBnActDepth;
   const PrefetchRing<2, DEPTH> ring(ring_smem);    // vector 0: z, 1: da
-  if (step_counter) seed ^= mix32(static_cast<uint32_t>(*step_counter) + 0x632be5abU);
+  if (DROP && step_counter) seed ^= mix32(static_cast<uint32_t>(*step_counter) + 0x632be5abU);
+  const DropMask mask(seed, drop_thresh, drop_scale);
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
   const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
@@ -112,7 +124,8 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = cg * 8 + k;
-    sc[k] = scale[c]; sh[k] = shift[c]; mu[k] = mean[c]; is[k] = invstd[c];
+    mu[k] = mean[c]; is[k] = invstd[c];
+    if (RELU) { sc[k] = scale[c]; sh[k] = shift[c]; }
     if (APPLY) { c0[k] = coef[c]; c1[k] = coef[C + c]; c2[k] = coef[2 * C + c]; }
   }
   float acc[16];
@@ -134,7 +147,7 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
   int stage = 0;
   for (long long i = tid; i < total; i += stride) {
     cp_async_wait<DEPTH - 1>();
-    float zv[8], g[8], outv[8];
+    float zv[8], g[8], outv[8], f[8];
     unpack8(ring.get(stage, 0), zv);
     unpack8(ring.get(stage, 1), g);
     if (inext < total) fetch(stage, inext);     // the item is in registers: refill its slots
@@ -142,12 +155,12 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
     inext += stride;
     stage = stage + 1 == DEPTH ? 0 : stage + 1;
     const long long pix = i >> gshift;
-    const uint32_t keep = drop_thresh ? drop_keep8(static_cast<unsigned long long>(pix) * C + cg * 8, seed, drop_thresh) : 0xFFu;
+    if (DROP) mask.factors(static_cast<unsigned long long>(pix) * C + cg * 8, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float d = g[k];
-      if (drop_thresh) d = (keep >> k) & 1u ? d * drop_scale : 0.f;
-      if (relu == 1 && !(fmaf(zv[k], sc[k], sh[k]) > 0.f)) d = 0.f;
+      if (DROP) d *= f[k];
+      if (RELU && !(fmaf(zv[k], sc[k], sh[k]) > 0.f)) d = 0.f;
       const float xh = (zv[k] - mu[k]) * is[k];
       if (!APPLY) {
         acc[k] += d;
@@ -184,6 +197,7 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
 // partial [kEwBlocks][C] = per-block sums over pixels of x (bias gradients of convs that are not followed by BN)
 __global__ void __launch_bounds__(kThreads)
 channel_sums_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, float* __restrict__ partial, long long npix, int C) {
+  pdl_entry();
   __shared__ float red[kThreads * 8];
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
@@ -227,6 +241,7 @@ channel_sums_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, float* __rest
 __global__ void __launch_bounds__(kThreads)
 upsample_zero2x_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_bfloat16* __restrict__ dst, int dst_cs,
                        int N, int Hs, int Ws, int C) {
+  pdl_entry();
   const int groups = C / 8;
   const int Hd = 2 * Hs, Wd = 2 * Ws;
   const long long total = static_cast<long long>(N) * Hd * Wd * groups;
@@ -248,6 +263,7 @@ upsample_zero2x_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_b
 __global__ void __launch_bounds__(kThreads)
 relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat16* __restrict__ y, int y_cs,
                 __nv_bfloat16* __restrict__ dx, int dx_cs, long long npix, int C) {
+  pdl_entry();
   const int groups = C / 8;
   const long long total = npix * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
@@ -268,6 +284,7 @@ relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bflo
 __global__ void __launch_bounds__(kThreads)
 maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat16* __restrict__ dpool, int dp_cs,
                       __nv_bfloat16* __restrict__ dx, int dx_cs, int N, int H, int W, int C) {
+  pdl_entry();
   const int groups = C / 8;
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(N) * Ho * Wo * groups;
@@ -304,7 +321,7 @@ maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_
 // Pixels of one sample reduced by one block: 256 at the deep levels (few pixels per sample), more at high resolution
 // so that a block streams >= 0.5 MB instead of paying a launch + block reduction per 32 KB.
 __host__ __device__ constexpr int se_pix_per_block(long long HW) {
-  return HW >= (1ll << 18) ? 4096 : HW >= (1ll << 14) ? 1024 : 256;
+  return HW >= (1ll << 18) ? 4096 : HW >= (1ll << 16) ? 1024 : 256;   // >= 64 blocks per sample from 128^2 upwards
 }
 
 // partial[n][chunk][C] = sum over the chunk's pixels of x (DOT: of x * y)
@@ -312,6 +329,7 @@ template <bool DOT>
 __global__ void __launch_bounds__(kThreads)
 se_pool_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat16* __restrict__ y, int y_cs,
                float* __restrict__ partial, long long HW, int C, int chunks) {
+  pdl_entry();
   __shared__ float red[kThreads * 8];
   const int groups = C / 8;                 // power of two <= 256 (host-checked)
   const int cg = threadIdx.x % groups;
@@ -325,7 +343,7 @@ se_pool_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat1
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  constexpr int U = 4;   // pixels in flight per thread
+  constexpr int U = DOT ? 4 : 8;   // pixels in flight per thread (16 bytes per stream each)
   for (long long pb = p0 + pl; pb < p1; pb += static_cast<long long>(ppi) * U) {
     uint4 xr[U], yr[U];
 #pragma unroll
@@ -368,6 +386,7 @@ se_fc_fwd_kernel(const float* __restrict__ partial, int chunks, float inv_hw, co
                  const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                  float* __restrict__ mean_out, float* __restrict__ hidden_out, float* __restrict__ gate_out, int C,
                  int Cr) {
+  pdl_entry();
   extern __shared__ float sm[];   // mean [C], hidden [Cr]
   float* mean = sm;
   float* hid = sm + C;
@@ -400,6 +419,7 @@ __global__ void __launch_bounds__(kThreads)
 se_scale_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const float* __restrict__ gate,
                 const float* __restrict__ add, float add_scale, __nv_bfloat16* __restrict__ y, int y_cs, long long HW,
                 int C, long long npix) {
+  pdl_entry();
   // forward: y = x * gate;  backward (add != nullptr): dx = dy * gate + add[n][c] * add_scale, with x := dy
   const int groups = C / 8;
   const bool pow2 = (groups & (groups - 1)) == 0;
@@ -446,6 +466,7 @@ __global__ void __launch_bounds__(kThreads)
 se_fc_bwd_kernel(const float* __restrict__ partial, int chunks, const float* __restrict__ gate,
                  const float* __restrict__ hidden, const float* __restrict__ w1, const float* __restrict__ w2,
                  float* __restrict__ ds_out, float* __restrict__ dh_out, float* __restrict__ dmean_out, int C, int Cr) {
+  pdl_entry();
   extern __shared__ float sm[];   // ds [C], dh [Cr]
   float* ds = sm;
   float* dh = sm + C;
@@ -479,6 +500,7 @@ se_fc_bwd_kernel(const float* __restrict__ partial, int chunks, const float* __r
 __global__ void __launch_bounds__(kThreads)
 outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                  float* __restrict__ out_bias, int N, int R, int K) {
+  pdl_entry();
   const long long total = static_cast<long long>(R) * K;
   for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kThreads) {
@@ -513,6 +535,38 @@ static float drop_scale_of(float p) {
   return t ? static_cast<float>(65536.0 / (65536.0 - t)) : 1.f;
 }
 
+// one launch of a templated streaming kernel with its prefetch ring: opt into the shared memory, one resident wave
+template <typename K, typename... Args>
+static void launch_ring(K kernel, int smem, long long items, int per_block, cudaStream_t stream, Args... args) {
+  ew_allow_smem(kernel, smem);
+  // occupancy of each template instance, looked up once per host thread (instances of one signature share this function)
+  thread_local const void* seen[32];
+  thread_local int waves[32];
+  thread_local int nseen = 0;
+  int wave = 0;
+  for (int i = 0; i < nseen; ++i)
+    if (seen[i] == reinterpret_cast<const void*>(kernel)) wave = waves[i];
+  if (!wave) {
+    wave = ew_wave_blocks(kernel, smem);
+    if (nseen < 32) { seen[nseen] = reinterpret_cast<const void*>(kernel); waves[nseen] = wave; ++nseen; }
+  }
+  const int grid = items < 0 ? wave : ew_clamp_grid(wave, items, per_block);
+  launch_k(kernel, dim3(grid), dim3(kThreads), smem, stream, args...);
+}
+
+template <int RELU, bool DROP>
+static void launch_bn_act_apply(bool has_res, long long items, cudaStream_t st, const __nv_bfloat16* z, int z_cs,
+                                const float* scale, const float* shift, const __nv_bfloat16* res, int res_cs,
+                                __nv_bfloat16* out, int out_cs, long long npix, int C, uint32_t thresh, float dscale,
+                                uint32_t seed, const long long* step_counter) {
+  if (has_res)
+    launch_ring(bn_act_apply_kernel<RELU, DROP, true>, PrefetchRing<2, kBnActDepth>::kBytes, items, kThreads * 4, st, z,
+                z_cs, scale, shift, res, res_cs, out, out_cs, npix, C, thresh, dscale, seed, step_counter);
+  else
+    launch_ring(bn_act_apply_kernel<RELU, DROP, false>, PrefetchRing<1, kBnActDepth>::kBytes, items, kThreads * 4, st, z,
+                z_cs, scale, shift, res, res_cs, out, out_cs, npix, C, thresh, dscale, seed, step_counter);
+}
+
 extern "C" int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale, const float* shift, const void* res,
                                 int res_cstride, void* out, int out_cstride, long long npix, int C, int relu,
                                 float dropout_p, unsigned seed, const long long* step_counter, void* stream) {
@@ -521,27 +575,35 @@ extern "C" int b2s_bn_act_apply(const void* z, int z_cstride, const float* scale
   if (z_cstride % 8 || out_cstride % 8 || (res && res_cstride % 8))
     return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: strides must be multiples of 8");
   if (dropout_p < 0.f || dropout_p >= 1.f) return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: dropout_p in [0,1)");
+  if (relu < 0 || relu > 2) return set_error(B2S_ERR_ARG, "b2s_bn_act_apply: relu mode must be 0, 1 or 2");
   count_launch();
+  const uint32_t thresh = drop_threshold(dropout_p);
+  const float dscale = drop_scale_of(dropout_p);
+  const auto* zp = static_cast<const __nv_bfloat16*>(z);
+  const auto* rp = static_cast<const __nv_bfloat16*>(res);
+  auto* op = static_cast<__nv_bfloat16*>(out);
   const long long items = npix * (C / 8);
-  if (res) {
-    constexpr int smem = PrefetchRing<2, kBnActDepth>::kBytes;
-    ew_allow_smem(bn_act_apply_kernel<true>, smem);
-    static const int wave = ew_wave_blocks(bn_act_apply_kernel<true>, smem);
-    bn_act_apply_kernel<true><<<ew_clamp_grid(wave, items, kThreads * 4), kThreads, smem,
-                                STREAM(stream)>>>(
-        static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, static_cast<const __nv_bfloat16*>(res),
-        res_cstride, static_cast<__nv_bfloat16*>(out), out_cstride, npix, C, relu, drop_threshold(dropout_p),
-        drop_scale_of(dropout_p), seed, step_counter);
-  } else {
-    constexpr int smem = PrefetchRing<1, kBnActDepth>::kBytes;
-    ew_allow_smem(bn_act_apply_kernel<false>, smem);
-    static const int wave = ew_wave_blocks(bn_act_apply_kernel<false>, smem);
-    bn_act_apply_kernel<false><<<ew_clamp_grid(wave, items, kThreads * 4), kThreads, smem,
-                                 STREAM(stream)>>>(
-        static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, nullptr, 0, static_cast<__nv_bfloat16*>(out),
-        out_cstride, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed, step_counter);
-  }
+  cudaStream_t st = STREAM(stream);
+#define B2S_APPLY(R, D) launch_bn_act_apply<R, D>(res != nullptr, items, st, zp, z_cstride, scale, shift, rp, res_cstride, \
+                                                  op, out_cstride, npix, C, thresh, dscale, seed, step_counter)
+  if (thresh) { if (relu == 1) B2S_APPLY(1, true); else if (relu == 2) B2S_APPLY(2, true); else B2S_APPLY(0, true); }
+  else        { if (relu == 1) B2S_APPLY(1, false); else if (relu == 2) B2S_APPLY(2, false); else B2S_APPLY(0, false); }
+#undef B2S_APPLY
   return check_launch("bn_act_apply_kernel");
+}
+
+template <bool APPLY>
+static void launch_bn_act_bwd(bool relu, bool drop, cudaStream_t st, const __nv_bfloat16* da, int da_cs,
+                              const __nv_bfloat16* z, int z_cs, const float* scale, const float* shift, const float* mean,
+                              const float* invstd, const float* coef, __nv_bfloat16* dz, int dz_cs, float* partial,
+                              long long npix, int C, uint32_t thresh, float dscale, uint32_t seed,
+                              const long long* step_counter) {
+  constexpr int smem = PrefetchRing<2, kBnActDepth>::kBytes;
+#define B2S_BWD(R, D) launch_ring(bn_act_bwd_kernel<APPLY, R, D>, smem, -1, 1, st, da, da_cs, z, z_cs, scale, shift, mean, \
+                                  invstd, coef, dz, dz_cs, partial, npix, C, thresh, dscale, seed, step_counter)
+  if (relu) { if (drop) B2S_BWD(true, true); else B2S_BWD(true, false); }
+  else      { if (drop) B2S_BWD(false, true); else B2S_BWD(false, false); }
+#undef B2S_BWD
 }
 
 extern "C" int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void* z, int z_cstride, const float* scale,
@@ -552,13 +614,10 @@ extern "C" int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void*
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: unsupported C");
   count_launch();
-  constexpr int smem = PrefetchRing<2, kBnActDepth>::kBytes;
-  ew_allow_smem(bn_act_bwd_kernel<false>, smem);
-  static const int wave = ew_wave_blocks(bn_act_bwd_kernel<false>, smem);
-  bn_act_bwd_kernel<false><<<wave, kThreads, smem, STREAM(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
-      mean, invstd, nullptr, nullptr, 0, partial, npix, C, relu, drop_threshold(dropout_p), drop_scale_of(dropout_p), seed,
-      step_counter);
+  const uint32_t thresh = drop_threshold(dropout_p);
+  launch_bn_act_bwd<false>(relu == 1, thresh != 0, STREAM(stream), static_cast<const __nv_bfloat16*>(da), da_cstride,
+                           static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, mean, invstd, nullptr, nullptr, 0,
+                           partial, npix, C, thresh, drop_scale_of(dropout_p), seed, step_counter);
   return check_launch("bn_act_bwd_kernel<reduce>");
 }
 
@@ -570,13 +629,11 @@ extern "C" int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* 
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: unsupported C");
   count_launch();
-  constexpr int smem = PrefetchRing<2, kBnActDepth>::kBytes;
-  ew_allow_smem(bn_act_bwd_kernel<true>, smem);
-  static const int wave = ew_wave_blocks(bn_act_bwd_kernel<true>, smem);
-  bn_act_bwd_kernel<true><<<wave, kThreads, smem, STREAM(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), da_cstride, static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift,
-      mean, invstd, coef, static_cast<__nv_bfloat16*>(dz), dz_cstride, dbias_partial, npix, C, relu,
-      drop_threshold(dropout_p), drop_scale_of(dropout_p), seed, step_counter);
+  const uint32_t thresh = drop_threshold(dropout_p);
+  launch_bn_act_bwd<true>(relu == 1, thresh != 0, STREAM(stream), static_cast<const __nv_bfloat16*>(da), da_cstride,
+                          static_cast<const __nv_bfloat16*>(z), z_cstride, scale, shift, mean, invstd, coef,
+                          static_cast<__nv_bfloat16*>(dz), dz_cstride, dbias_partial, npix, C, thresh,
+                          drop_scale_of(dropout_p), seed, step_counter);
   return check_launch("bn_act_bwd_kernel<apply>");
 }
 
@@ -585,9 +642,7 @@ extern "C" int b2s_relu_bwd(const void* dy, int dy_cstride, const void* y, int y
   if (!dy || !y || !dx) return set_error(B2S_ERR_ARG, "b2s_relu_bwd: null pointer");
   if (C % 8 || dy_cstride % 8 || y_cstride % 8 || dx_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_relu_bwd: need multiples of 8");
   count_launch();
-  relu_bwd_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), dy_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride,
-      static_cast<__nv_bfloat16*>(dx), dx_cstride, npix, C);
+  launch_k(relu_bwd_kernel, dim3(ew_grid_for(npix * (C / 8), kThreads * 4)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(dy), dy_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride, static_cast<__nv_bfloat16*>(dx), dx_cstride, npix, C);
   return check_launch("relu_bwd_kernel");
 }
 
@@ -598,9 +653,7 @@ extern "C" int b2s_maxpool2x2_bwd(const void* x, int x_cstride, const void* dpoo
     return set_error(B2S_ERR_ARG, "b2s_maxpool2x2_bwd: need C % 8 == 0, even H and W");
   const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   count_launch();
-  maxpool2x2_bwd_kernel<<<ew_grid_for(items, kThreads * 2), kThreads, 0, STREAM(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(dpool), dpool_cstride,
-      static_cast<__nv_bfloat16*>(dx), dx_cstride, N, H, W, C);
+  launch_k(maxpool2x2_bwd_kernel, dim3(ew_grid_for(items, kThreads * 2)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(dpool), dpool_cstride, static_cast<__nv_bfloat16*>(dx), dx_cstride, N, H, W, C);
   return check_launch("maxpool2x2_bwd_kernel");
 }
 
@@ -608,8 +661,7 @@ extern "C" int b2s_channel_sums(const void* x, int x_cstride, float* partial, lo
   if (!x || !partial) return set_error(B2S_ERR_ARG, "b2s_channel_sums: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_channel_sums: unsupported C");
   count_launch();
-  channel_sums_kernel<<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_cstride,
-                                                                 partial, npix, C);
+  launch_k(channel_sums_kernel, dim3(kEwBlocks), dim3(kThreads), 0, STREAM(stream), static_cast<const __nv_bfloat16*>(x), x_cstride, partial, npix, C);
   return check_launch("channel_sums_kernel");
 }
 
@@ -619,8 +671,7 @@ extern "C" int b2s_upsample_zero2x(const void* src, int src_cstride, void* dst, 
   if (C % 8 || src_cstride % 8 || dst_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_upsample_zero2x: need multiples of 8");
   const long long items = static_cast<long long>(N) * 4 * Hs * Ws * (C / 8);
   count_launch();
-  upsample_zero2x_kernel<<<ew_grid_for(items, kThreads * 4), kThreads, 0, STREAM(stream)>>>(
-      static_cast<const __nv_bfloat16*>(src), src_cstride, static_cast<__nv_bfloat16*>(dst), dst_cstride, N, Hs, Ws, C);
+  launch_k(upsample_zero2x_kernel, dim3(ew_grid_for(items, kThreads * 4)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(src), src_cstride, static_cast<__nv_bfloat16*>(dst), dst_cstride, N, Hs, Ws, C);
   return check_launch("upsample_zero2x_kernel");
 }
 
@@ -639,12 +690,9 @@ extern "C" int b2s_se_pool(const void* x, int x_cstride, const void* y, int y_cs
   dim3 grid(chunks, N);
   count_launch();
   if (y)
-    se_pool_kernel<true><<<grid, kThreads, 0, STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_cstride,
-                                                                static_cast<const __nv_bfloat16*>(y), y_cstride, partial,
-                                                                HW, C, chunks);
+    launch_k(se_pool_kernel<true>, dim3(grid), dim3(kThreads), 0, STREAM(stream), static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride, partial, HW, C, chunks);
   else
-    se_pool_kernel<false><<<grid, kThreads, 0, STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_cstride, nullptr,
-                                                                 0, partial, HW, C, chunks);
+    launch_k(se_pool_kernel<false>, dim3(grid), dim3(kThreads), 0, STREAM(stream), static_cast<const __nv_bfloat16*>(x), x_cstride, nullptr, 0, partial, HW, C, chunks);
   return check_launch("se_pool_kernel");
 }
 
@@ -655,8 +703,7 @@ extern "C" int b2s_se_fc_fwd(const float* partial, int chunks, long long HW, con
     return set_error(B2S_ERR_ARG, "b2s_se_fc_fwd: null pointer");
   if (C > 4096 || Cr < 1 || Cr > C) return set_error(B2S_ERR_ARG, "b2s_se_fc_fwd: unsupported channel counts");
   count_launch();
-  se_fc_fwd_kernel<<<N, kThreads, (C + Cr) * sizeof(float), STREAM(stream)>>>(partial, chunks, 1.f / static_cast<float>(HW),
-                                                                             w1, b1, w2, b2, mean, hidden, gate, C, Cr);
+  launch_k(se_fc_fwd_kernel, dim3(N), dim3(kThreads), (C + Cr) * sizeof(float), STREAM(stream), partial, chunks, 1.f / static_cast<float>(HW), w1, b1, w2, b2, mean, hidden, gate, C, Cr);
   return check_launch("se_fc_fwd_kernel");
 }
 
@@ -666,9 +713,7 @@ extern "C" int b2s_se_scale(const void* x, int x_cstride, const float* gate, con
   if (C % 8 || x_cstride % 8 || y_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_se_scale: need multiples of 8");
   const long long npix = static_cast<long long>(N) * HW;
   count_launch();
-  se_scale_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), x_cstride, gate, add, add_scale, static_cast<__nv_bfloat16*>(y),
-      y_cstride, HW, C, npix);
+  launch_k(se_scale_kernel, dim3(ew_grid_for(npix * (C / 8), kThreads * 4)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(x), x_cstride, gate, add, add_scale, static_cast<__nv_bfloat16*>(y), y_cstride, HW, C, npix);
   return check_launch("se_scale_kernel");
 }
 
@@ -679,16 +724,13 @@ extern "C" int b2s_se_fc_bwd(const float* partial, int chunks, const float* gate
     return set_error(B2S_ERR_ARG, "b2s_se_fc_bwd: null pointer");
   if (C > 4096 || Cr < 1 || Cr > C) return set_error(B2S_ERR_ARG, "b2s_se_fc_bwd: unsupported channel counts");
   count_launch();
-  se_fc_bwd_kernel<<<N, kThreads, (C + Cr) * sizeof(float), STREAM(stream)>>>(partial, chunks, gate, hidden, w1, w2, ds, dh,
-                                                                             dmean, C, Cr);
+  launch_k(se_fc_bwd_kernel, dim3(N), dim3(kThreads), (C + Cr) * sizeof(float), STREAM(stream), partial, chunks, gate, hidden, w1, w2, ds, dh, dmean, C, Cr);
   int rc = check_launch("se_fc_bwd_kernel");
   if (rc) return rc;
   // dW2 [C][Cr] = sum_n ds (x) hidden, db2 = sum_n ds;  dW1 [Cr][C] = sum_n dh (x) mean, db1 = sum_n dh
   count_launch();
-  outer_sum_kernel<<<ew_grid_for(static_cast<long long>(C) * Cr, kThreads), kThreads, 0, STREAM(stream)>>>(ds, hidden, dw2, db2, N,
-                                                                                                         C, Cr);
+  launch_k(outer_sum_kernel, dim3(ew_grid_for(static_cast<long long>(C) * Cr, kThreads)), dim3(kThreads), 0, STREAM(stream), ds, hidden, dw2, db2, N, C, Cr);
   count_launch();
-  outer_sum_kernel<<<ew_grid_for(static_cast<long long>(C) * Cr, kThreads), kThreads, 0, STREAM(stream)>>>(dh, mean, dw1, db1, N,
-                                                                                                         Cr, C);
+  launch_k(outer_sum_kernel, dim3(ew_grid_for(static_cast<long long>(C) * Cr, kThreads)), dim3(kThreads), 0, STREAM(stream), dh, mean, dw1, db1, N, Cr, C);
   return check_launch("outer_sum_kernel");
 }
