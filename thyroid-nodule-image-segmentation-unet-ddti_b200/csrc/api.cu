@@ -1,6 +1,5 @@
 // Error slot, launch counter and version of libb2s (the C ABI declared in include/b2s.h).
 #include <atomic>
-#include <stdlib.h>
 #include <string.h>
 #include "b2s_internal.h"
 
@@ -27,14 +26,6 @@ int check_launch(const char* what) {
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("B2S_PDL");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
 
 }  // namespace b2s
 

@@ -104,9 +104,6 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // barriers, TMEM and descriptors are set up: from here on the kernel touches memory its predecessor may still
-  // be writing (programmatic dependent launch, ptx.cuh)
-  pdl_entry();
 
   if (warp == 0) {
     if (HALO && lane == 0) {
@@ -404,7 +401,7 @@ static int launch_conv2_t(int grid, const CUtensorMap& tmA, const CUtensorMap& t
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv2_tc_kernel)");
     attr_set = true;
   }
-  launch_k(kfn, dim3(grid), dim3(kConv2Threads), L::kDynBytes, stream, tmA, tmB, tmOut, p);
+  kfn<<<grid, kConv2Threads, L::kDynBytes, stream>>>(tmA, tmB, tmOut, p);
   return check_launch("conv2_tc_kernel");
 }
 

@@ -88,9 +88,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // barriers, TMEM and descriptors are set up: from here on the kernel touches memory its predecessor may still
-  // be writing (programmatic dependent launch, ptx.cuh)
-  pdl_entry();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -359,9 +356,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_ptr_smem;
-  // barriers, TMEM and descriptors are set up: from here on the kernel touches memory its predecessor may still
-  // be writing (programmatic dependent launch, ptx.cuh)
-  pdl_entry();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -492,7 +486,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
     attr_set = true;
   }
-  launch_k(kfn, dim3(conv_grid(p.tiles_m, p.tiles_nn)), dim3(kConvThreads), L::kDynBytes, stream, tmA, tmB, tmOut, p);
+  kfn<<<conv_grid(p.tiles_m, p.tiles_nn), kConvThreads, L::kDynBytes, stream>>>(tmA, tmB, tmOut, p);
   return check_launch("conv_tc_kernel");
 }
 
@@ -717,7 +711,7 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Wg
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(wgrad_tc_kernel)");
     attr_set = true;
   }
-  launch_k(kfn, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream, tmA, tmB, p);
+  kfn<<<grid, kNumThreads, L::kDynBytes, stream>>>(tmA, tmB, p);
   return check_launch("wgrad_tc_kernel");
 }
 

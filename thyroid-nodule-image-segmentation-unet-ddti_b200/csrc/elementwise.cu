@@ -17,7 +17,6 @@ constexpr int kRedBatch = 8;
 
 __global__ void __launch_bounds__(32 * kRedY)
 reduce_rows_kernel(const float* __restrict__ in, int rows, int K, int rows_per_slice, float* __restrict__ out) {
-  pdl_entry();
   // grid (ceil(K/32), slices); block (32, kRedY): lane = column (coalesced), threadIdx.y strides over the rows
   __shared__ double red[kRedY][33];
   const int k = blockIdx.x * 32 + threadIdx.x;
@@ -86,7 +85,7 @@ int reduce_to_small(const float* in, int rows, int K, float* scratch, const floa
   const int used = (rows + rps - 1) / rps;
   dim3 grid((K + 31) / 32, used), block(32, kRedY);
   count_launch();
-  launch_k(reduce_rows_kernel, dim3(grid), dim3(block), 0, stream, in, rows, K, rps, scratch);
+  reduce_rows_kernel<<<grid, block, 0, stream>>>(in, rows, K, rps, scratch);
   int rc = check_launch("reduce_rows_kernel");
   *out_ptr = scratch; *out_rows = used;
   return rc;
@@ -99,7 +98,6 @@ __global__ void __launch_bounds__(kThreads)
 conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       __nv_bfloat16* __restrict__ r, float* __restrict__ stats_partial, int N, int H, int W, int Cout,
                       int flags, const float* __restrict__ post_scale, const float* __restrict__ post_shift) {
-  pdl_entry();
   __shared__ float red[kThreads * 16];
   const int groups = Cout / 8;              // threads per pixel
   const int ppi = kThreads / groups;        // pixels per block iteration
@@ -169,7 +167,6 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 __global__ void __launch_bounds__(kThreads)
 conv3x3_c1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                         float* __restrict__ partial, int N, int H, int W, int Cout) {
-  pdl_entry();
   __shared__ float red[kThreads * 8];
   const int groups = Cout / 8;
   const int ppi = kThreads / groups;
@@ -239,7 +236,6 @@ __global__ void __launch_bounds__(kThreads, 2)
 conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        __nv_bfloat16* __restrict__ r, float* __restrict__ stats_partial, int N, int H, int W, int Cout,
                        int flags, const float* __restrict__ post_scale, const float* __restrict__ post_shift) {
-  pdl_entry();
   // weights live in shared memory ([tap][Cout], read as two broadcast float4 per tap): keeping all 72 of a thread's
   // weights in registers cost 191 registers and one resident block per SM
   __shared__ float red[kThreads * 16];
@@ -327,7 +323,6 @@ conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w,
 __global__ void __launch_bounds__(kThreads)
 conv3x3_c1_wgrad4_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                          float* __restrict__ partial, int N, int H, int W, int Cout) {
-  pdl_entry();
   __shared__ float red[kThreads * 8];
   const int groups = Cout / 8;
   const int qpi = kThreads / groups;
@@ -388,7 +383,6 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                                    float* scale, float* shift, float* mean_out, float* invstd_out) {
-  pdl_entry();
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s, q;
   block_sum_pairs(partial, rows, C, c, s, q);
@@ -414,7 +408,6 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
 
 __global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
                                       float eps, float* scale, float* shift, int C) {
-  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = 1.f / sqrtf(rv[c] + eps);
@@ -434,7 +427,6 @@ __global__ void __launch_bounds__(kThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __restrict__ scale,
                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int y_cs,
                 __nv_bfloat16* __restrict__ pooled, int N, int H, int W, int C) {
-  pdl_entry();
   extern __shared__ uint4 ring_smem[];
   constexpr int Q = bn_apply_nv<POOL>(), DEPTH = bn_apply_depth<POOL>();
   const PrefetchRing<Q, DEPTH> ring(ring_smem);
@@ -509,7 +501,6 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __re
 __global__ void __launch_bounds__(kThreads)
 maxpool2x2_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, __nv_bfloat16* __restrict__ pooled, int N, int H, int W,
                   int C) {
-  pdl_entry();
   const int groups = C / 8;
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(N) * Ho * Wo * groups;
@@ -547,7 +538,6 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
               const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
               const float* __restrict__ coef, __nv_bfloat16* __restrict__ dz, int dz_cs, float* __restrict__ partial,
               int N, int H, int W, int C) {
-  pdl_entry();
   extern __shared__ uint4 ring_smem[];      // prefetch ring; reused for the block reduction after the loop
   constexpr int Q = POOL ? 4 : 1;           // pixels per work item (one 2x2 pooling window, or one pixel)
   constexpr int NV = bn_bwd_nv<POOL>(), DEPTH = bn_bwd_depth<POOL, APPLY>();
@@ -673,7 +663,6 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        float* dgamma, float* dbeta, float* coef) {
-  pdl_entry();
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s, q;
   block_sum_pairs(partial, rows, C, c, s, q);
@@ -693,7 +682,6 @@ __global__ void __launch_bounds__(kThreads)
 head_fwd_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __restrict__ scale,
                 const float* __restrict__ shift, const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ logits, unsigned char* __restrict__ mask, int N, long long HW, int C, int O) {
-  pdl_entry();
   extern __shared__ float wf[];  // [O][C] folded weights, then [O] folded bias
   for (int i = threadIdx.x; i < O * C; i += kThreads) {
     const int c = i % C;
@@ -746,7 +734,6 @@ head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restri
                 const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ w,
                 __nv_bfloat16* __restrict__ dy, int dy_cs, float* __restrict__ partial, int N, long long HW, int C,
                 int O) {
-  pdl_entry();
   __shared__ float red[kThreads * 9];
   const int groups = C / 8;
   const int cg = threadIdx.x % groups;
@@ -823,7 +810,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(kThreads)
 seg_loss_partial_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long long per_sample,
                         int chunks, float* __restrict__ partial) {
-  pdl_entry();
   __shared__ float red[4][kThreads / 32];
   const int b = blockIdx.y, ch = blockIdx.x;
   const long long base = static_cast<long long>(b) * per_sample;
@@ -870,7 +856,6 @@ __global__ void seg_loss_finalize_kernel(const float* __restrict__ partial, int 
                                          float* __restrict__ sums, float* __restrict__ out, float dice_smooth,
                                          float w_bce, float w_dice, float w_ft, float ft_alpha, float ft_beta,
                                          float ft_gamma, float ft_smooth) {
-  pdl_entry();
   // single block; thread b < B reduces its sample
   __shared__ double sh[4][kThreads];
   double acc[4] = {0, 0, 0, 0};
@@ -919,7 +904,6 @@ seg_loss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ 
                     long long bce_count, int dice_batch, const float* __restrict__ grad_out,
                     float* __restrict__ dlogits, float dice_smooth, float w_bce, float w_dice, float w_ft,
                     float ft_alpha, float ft_beta, float ft_gamma, float ft_smooth) {
-  pdl_entry();
   const int b = blockIdx.y;
   const float go = grad_out ? *grad_out : 1.f;
   const float I = sums[b * 4 + 0], U = sums[b * 4 + 1] + sums[b * 4 + 2];
@@ -967,7 +951,6 @@ seg_loss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ 
 __global__ void __launch_bounds__(kThreads)
 seg_metrics_partial_kernel(const float* __restrict__ logits, const float* __restrict__ targets, long long n,
                            unsigned int* __restrict__ partial) {
-  pdl_entry();
   __shared__ unsigned int red[6][kThreads / 32];
   unsigned int c[6] = {0, 0, 0, 0, 0, 0};
   const long long i0 = static_cast<long long>(blockIdx.x) * kLossChunk;
@@ -998,7 +981,6 @@ seg_metrics_partial_kernel(const float* __restrict__ logits, const float* __rest
 
 __global__ void seg_metrics_accumulate_kernel(const unsigned int* __restrict__ partial, int blocks, long long n,
                                               long long* __restrict__ counters) {
-  pdl_entry();
   __shared__ long long red[6][kThreads];
   long long c[6] = {0, 0, 0, 0, 0, 0};
   for (int b = threadIdx.x; b < blocks; b += kThreads)
@@ -1021,7 +1003,6 @@ __global__ void seg_metrics_accumulate_kernel(const unsigned int* __restrict__ p
 __global__ void __launch_bounds__(kThreads)
 pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                         __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int taps) {
-  pdl_entry();
   // one block per (32 co x 32 ci) tile: coalesced fp32 reads, both transposed bf16 layouts written in 64-B runs
   __shared__ float tile[32][32 * 9 + 1];
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -1047,7 +1028,6 @@ pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__
 
 __global__ void pack_convt_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                          __nv_bfloat16* __restrict__ wd, int Cin, int Cout) {
-  pdl_entry();
   // w [Cin][Cout][4]; wf [(ab)*Cout+co][Cin]; wd [(ab)*Cin+ci][Cout]
   const long long total = static_cast<long long>(Cin) * Cout * 4;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -1080,7 +1060,6 @@ struct PackTable {
 
 __global__ void __launch_bounds__(kThreads)
 pack_all_kernel(const __grid_constant__ PackTable tab) {
-  pdl_entry();
   __shared__ float tile[32][32 * 9 + 1];
   int ti = 0;
   while (ti + 1 < tab.n && static_cast<int>(blockIdx.x) >= tab.e[ti + 1].tile_begin) ++ti;
@@ -1132,7 +1111,6 @@ pack_all_kernel(const __grid_constant__ PackTable tab) {
 __global__ void __launch_bounds__(kThreads)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int Cin, int Cout, float* __restrict__ dw,
                     int layout, int sgroups) {
-  pdl_entry();
   __shared__ float tile[9][8][129];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int cpb = 8 / sgroups;                       // input channels per block
@@ -1189,7 +1167,6 @@ __global__ void __launch_bounds__(kThreads)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
              float grad_scale) {
-  pdl_entry();
   const float step_size = lr / bc1;
   for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * kThreads) {
@@ -1209,7 +1186,6 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 __global__ void __launch_bounds__(kThreads)
 adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  long long n, const float* __restrict__ hyper) {
-  pdl_entry();
   const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5],
               bc2_sqrt = hyper[6], grad_scale = hyper[7];
   const float step_size = lr / bc1;
@@ -1228,7 +1204,6 @@ adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 __global__ void __launch_bounds__(kThreads)
 copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_bfloat16* __restrict__ dst, int dst_cs,
                      long long npix, int C) {
-  pdl_entry();
   const int groups = C / 8;
   const bool pow2 = (groups & (groups - 1)) == 0;
   const int gshift = __ffs(groups) - 1;
@@ -1278,7 +1253,7 @@ extern "C" int b2s_reduce_rows(const float* in, int rows, int K, float* scratch,
   if (rc) return rc;
   dim3 grid((K + 31) / 32, 1), block(32, kRedY);
   count_launch();
-  launch_k(reduce_rows_kernel, dim3(grid), dim3(block), 0, STREAM(stream), src, r, K, r, out);
+  reduce_rows_kernel<<<grid, block, 0, STREAM(stream)>>>(src, r, K, r, out);
   return check_launch("reduce_rows_kernel");
 }
 
@@ -1297,7 +1272,9 @@ static int c1_fwd_impl(const float* x, const float* w, const float* bias, const 
   const int grid = b2s_c1_rows(N, H, W);
   count_launch();
   auto kfn = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? conv3x3_c1_fwd4_kernel : conv3x3_c1_fwd_kernel;
-  launch_k(kfn, dim3(grid), dim3(kThreads), 0, STREAM(stream), x, w, bias, static_cast<__nv_bfloat16*>(r), (flags & B2S_FLAG_STATS) ? stats_partial : nullptr, N, H, W, Cout, flags, post_scale, post_shift);
+  kfn<<<grid, kThreads, 0, STREAM(stream)>>>(x, w, bias, static_cast<__nv_bfloat16*>(r),
+                                             (flags & B2S_FLAG_STATS) ? stats_partial : nullptr, N, H, W, Cout, flags,
+                                             post_scale, post_shift);
   return check_launch("conv3x3_c1_fwd_kernel");
 }
 
@@ -1321,7 +1298,7 @@ extern "C" int b2s_conv3x3_c1_wgrad(const float* x, const void* dz, float* parti
   const int grid = b2s_c1_rows(N, H, W);
   count_launch();
   auto kfn = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? conv3x3_c1_wgrad4_kernel : conv3x3_c1_wgrad_kernel;
-  launch_k(kfn, dim3(grid), dim3(kThreads), 0, STREAM(stream), x, static_cast<const __nv_bfloat16*>(dz), partial, N, H, W, Cout);
+  kfn<<<grid, kThreads, 0, STREAM(stream)>>>(x, static_cast<const __nv_bfloat16*>(dz), partial, N, H, W, Cout);
   return check_launch("conv3x3_c1_wgrad_kernel");
 }
 
@@ -1337,7 +1314,9 @@ extern "C" int b2s_bn_finalize(const float* partial, int rows, int C, double cou
   int rc = reduce_to_small(partial, rows, 2 * C, scratch, &src, &r, STREAM(stream));
   if (rc) return rc;
   count_launch();
-  launch_k(bn_finalize_kernel, dim3((C + 31) / 32), dim3(dim3(32, kRedY)), 0, STREAM(stream), src, r, C, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean, invstd);
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, STREAM(stream)>>>(src, r, C, count, gamma, beta, running_mean,
+                                                                  running_var, num_batches_tracked, momentum, eps,
+                                                                  scale, shift, mean, invstd);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -1346,7 +1325,8 @@ extern "C" int b2s_bn_eval_affine(const float* gamma, const float* beta, const f
                                   void* stream) {
   if (!running_mean || !running_var || !scale || !shift) return set_error(B2S_ERR_ARG, "b2s_bn_eval_affine: null");
   count_launch();
-  launch_k(bn_eval_affine_kernel, dim3((C + 127) / 128), dim3(128), 0, STREAM(stream), gamma, beta, running_mean, running_var, eps, scale, shift, C);
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, STREAM(stream)>>>(gamma, beta, running_mean, running_var, eps, scale,
+                                                                     shift, C);
   return check_launch("bn_eval_affine_kernel");
 }
 
@@ -1365,13 +1345,16 @@ extern "C" int b2s_bn_apply(const void* r, int r_cstride, const float* scale, co
     ew_allow_smem(bn_apply_kernel<true>, smem);
     const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
     static const int wave = ew_wave_blocks(bn_apply_kernel<true>, smem);
-    launch_k(bn_apply_kernel<true>, dim3(ew_clamp_grid(wave, items, kThreads * 2)), dim3(kThreads), smem, STREAM(stream), rp, r_cstride, scale, shift, yp, y_cstride, static_cast<__nv_bfloat16*>(pooled), N, H, W, C);
+    bn_apply_kernel<true><<<ew_clamp_grid(wave, items, kThreads * 2), kThreads, smem,
+                            STREAM(stream)>>>(rp, r_cstride, scale, shift, yp, y_cstride,
+                                              static_cast<__nv_bfloat16*>(pooled), N, H, W, C);
   } else {
     constexpr int smem = PrefetchRing<bn_apply_nv<false>(), bn_apply_depth<false>()>::kBytes;
     ew_allow_smem(bn_apply_kernel<false>, smem);
     const long long items = static_cast<long long>(N) * H * W * (C / 8);
     static const int wave = ew_wave_blocks(bn_apply_kernel<false>, smem);
-    launch_k(bn_apply_kernel<false>, dim3(ew_clamp_grid(wave, items, kThreads * 4)), dim3(kThreads), smem, STREAM(stream), rp, r_cstride, scale, shift, yp, y_cstride, nullptr, N, H, W, C);
+    bn_apply_kernel<false><<<ew_clamp_grid(wave, items, kThreads * 4), kThreads, smem,
+                             STREAM(stream)>>>(rp, r_cstride, scale, shift, yp, y_cstride, nullptr, N, H, W, C);
   }
   return check_launch("bn_apply_kernel");
 }
@@ -1381,7 +1364,8 @@ extern "C" int b2s_maxpool2x2(const void* x, int x_cstride, void* pooled, int N,
   if (C % 8 || x_cstride % 8 || H % 2 || W % 2) return set_error(B2S_ERR_ARG, "b2s_maxpool2x2: need C % 8 == 0, even H and W");
   const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   count_launch();
-  launch_k(maxpool2x2_kernel, dim3(grid_for(items, kThreads * 2)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<__nv_bfloat16*>(pooled), N, H, W, C);
+  maxpool2x2_kernel<<<grid_for(items, kThreads * 2), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<__nv_bfloat16*>(pooled), N, H, W, C);
   return check_launch("maxpool2x2_kernel");
 }
 
@@ -1401,11 +1385,16 @@ extern "C" int b2s_bn_bwd_reduce(const void* dy, int dy_cstride, const void* dpo
   if (dpool) {
     ew_allow_smem(bn_bwd_kernel<true, false>, smem_pool);
     static const int wave = ew_wave_blocks(bn_bwd_kernel<true, false>, smem_pool);
-    launch_k(bn_bwd_kernel<true, false>, dim3(wave), dim3(kThreads), smem_pool, STREAM(stream),  dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, nullptr, nullptr, 0, partial, N, H, W, C);
+    bn_bwd_kernel<true, false><<<wave, kThreads, smem_pool,
+                                 STREAM(stream)>>>(
+        dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, nullptr,
+        nullptr, 0, partial, N, H, W, C);
   } else {
     ew_allow_smem(bn_bwd_kernel<false, false>, smem_flat);
     static const int wave = ew_wave_blocks(bn_bwd_kernel<false, false>, smem_flat);
-    launch_k(bn_bwd_kernel<false, false>, dim3(wave), dim3(kThreads), smem_flat, STREAM(stream),  dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, nullptr, nullptr, 0, partial, N, H, W, C);
+    bn_bwd_kernel<false, false><<<wave, kThreads, smem_flat,
+                                  STREAM(stream)>>>(
+        dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, nullptr, nullptr, 0, partial, N, H, W, C);
   }
   return check_launch("bn_bwd_kernel<reduce>");
 }
@@ -1418,7 +1407,8 @@ extern "C" int b2s_bn_bwd_finalize(const float* partial, int rows, int C, double
   int rc = reduce_to_small(partial, rows, 2 * C, scratch, &src, &r, STREAM(stream));
   if (rc) return rc;
   count_launch();
-  launch_k(bn_bwd_finalize_kernel, dim3((C + 31) / 32), dim3(dim3(32, kRedY)), 0, STREAM(stream), src, r, C, count, gamma, invstd, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, STREAM(stream)>>>(src, r, C, count, gamma, invstd, dgamma, dbeta,
+                                                                      coef);
   return check_launch("bn_bwd_finalize_kernel");
 }
 
@@ -1440,11 +1430,17 @@ extern "C" int b2s_bn_bwd_apply(const void* dy, int dy_cstride, const void* dpoo
   if (dpool) {
     ew_allow_smem(bn_bwd_kernel<true, true>, smem_pool);
     static const int wave = ew_wave_blocks(bn_bwd_kernel<true, true>, smem_pool);
-    launch_k(bn_bwd_kernel<true, true>, dim3(wave), dim3(kThreads), smem_pool, STREAM(stream),  dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, coef, dzp, dz_cstride, dbias_partial, N, H, W, C);
+    bn_bwd_kernel<true, true><<<wave, kThreads, smem_pool,
+                                STREAM(stream)>>>(
+        dyp, dy_cstride, static_cast<const __nv_bfloat16*>(dpool), rp, r_cstride, scale, shift, mean, invstd, coef, dzp,
+        dz_cstride, dbias_partial, N, H, W, C);
   } else {
     ew_allow_smem(bn_bwd_kernel<false, true>, smem_flat);
     static const int wave = ew_wave_blocks(bn_bwd_kernel<false, true>, smem_flat);
-    launch_k(bn_bwd_kernel<false, true>, dim3(wave), dim3(kThreads), smem_flat, STREAM(stream),  dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, coef, dzp, dz_cstride, dbias_partial, N, H, W, C);
+    bn_bwd_kernel<false, true><<<wave, kThreads, smem_flat,
+                                 STREAM(stream)>>>(
+        dyp, dy_cstride, nullptr, rp, r_cstride, scale, shift, mean, invstd, coef, dzp, dz_cstride, dbias_partial, N, H,
+        W, C);
   }
   return check_launch("bn_bwd_kernel<apply>");
 }
@@ -1459,7 +1455,8 @@ extern "C" int b2s_head_fwd(const void* r, int r_cstride, const float* scale, co
   const long long npix = static_cast<long long>(N) * HW;
   const int ppi = kThreads / (C / 8);
   count_launch();
-  launch_k(head_fwd_kernel, dim3(grid_for(npix, ppi * 16)), dim3(kThreads), (O * C + O) * sizeof(float), STREAM(stream),  static_cast<const __nv_bfloat16*>(r), r_cstride, scale, shift, w, b, logits, mask, N, HW, C, O);
+  head_fwd_kernel<<<grid_for(npix, ppi * 16), kThreads, (O * C + O) * sizeof(float), STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(r), r_cstride, scale, shift, w, b, logits, mask, N, HW, C, O);
   return check_launch("head_fwd_kernel");
 }
 
@@ -1471,7 +1468,9 @@ extern "C" int b2s_head_bwd(const float* dlogits, const void* r, int r_cstride, 
   if (O < 1 || O > 64) return set_error(B2S_ERR_ARG, "b2s_head_bwd: unsupported out_channels");
   if (static_cast<long long>(N) * HW >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_head_bwd: N*H*W >= 2^31");
   count_launch();
-  launch_k(head_bwd_kernel, dim3(kEwBlocks), dim3(kThreads), 0, STREAM(stream), dlogits, static_cast<const __nv_bfloat16*>(r), r_cstride, scale, shift, w, static_cast<__nv_bfloat16*>(dy), dy_cstride, partial, N, HW, C, O);
+  head_bwd_kernel<<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(dlogits, static_cast<const __nv_bfloat16*>(r), r_cstride,
+                                                             scale, shift, w, static_cast<__nv_bfloat16*>(dy),
+                                                             dy_cstride, partial, N, HW, C, O);
   return check_launch("head_bwd_kernel");
 }
 
@@ -1486,11 +1485,14 @@ extern "C" int b2s_seg_loss_fwd(const float* logits, const float* targets, int B
   if (B <= 0 || per_sample <= 0 || B > 65535) return set_error(B2S_ERR_ARG, "b2s_seg_loss_fwd: bad batch");
   const int chunks = b2s_loss_chunks(per_sample);
   count_launch();
-  launch_k(seg_loss_partial_kernel, dim3(dim3(chunks, B)), dim3(kThreads), 0, STREAM(stream), logits, targets, per_sample, chunks, partial);
+  seg_loss_partial_kernel<<<dim3(chunks, B), kThreads, 0, STREAM(stream)>>>(logits, targets, per_sample, chunks,
+                                                                           partial);
   int rc = check_launch("seg_loss_partial_kernel");
   if (rc) return rc;
   count_launch();
-  launch_k(seg_loss_finalize_kernel, dim3(1), dim3(kThreads), 0, STREAM(stream), partial, B, chunks, per_sample, sums, out, dice_smooth, w_bce, w_dice, w_ft, ft_alpha, ft_beta, ft_gamma, ft_smooth);
+  seg_loss_finalize_kernel<<<1, kThreads, 0, STREAM(stream)>>>(partial, B, chunks, per_sample, sums, out, dice_smooth,
+                                                              w_bce, w_dice, w_ft, ft_alpha, ft_beta, ft_gamma,
+                                                              ft_smooth);
   return check_launch("seg_loss_finalize_kernel");
 }
 
@@ -1504,7 +1506,10 @@ extern "C" int b2s_seg_loss_bwd(const float* logits, const float* targets, const
   int gx = static_cast<int>((per_sample + kThreads * 4 - 1) / (kThreads * 4));
   if (gx > 1024) gx = 1024;
   count_launch();
-  launch_k(seg_loss_bwd_kernel, dim3(dim3(gx, B)), dim3(kThreads), 0, STREAM(stream), logits, targets, sums, ft_tot, B, per_sample, bce_count, dice_batch, grad_out, dlogits, dice_smooth, w_bce, w_dice, w_ft, ft_alpha, ft_beta, ft_gamma, ft_smooth);
+  seg_loss_bwd_kernel<<<dim3(gx, B), kThreads, 0, STREAM(stream)>>>(logits, targets, sums, ft_tot, B, per_sample,
+                                                                   bce_count, dice_batch, grad_out, dlogits,
+                                                                   dice_smooth, w_bce, w_dice, w_ft, ft_alpha, ft_beta,
+                                                                   ft_gamma, ft_smooth);
   return check_launch("seg_loss_bwd_kernel");
 }
 
@@ -1516,11 +1521,11 @@ extern "C" int b2s_seg_metrics(const float* logits, const float* targets, long l
   if (n <= 0) return set_error(B2S_ERR_ARG, "b2s_seg_metrics: empty input");
   const int blocks = b2s_metrics_blocks(n);
   count_launch();
-  launch_k(seg_metrics_partial_kernel, dim3(blocks), dim3(kThreads), 0, STREAM(stream), logits, targets, n, partial);
+  seg_metrics_partial_kernel<<<blocks, kThreads, 0, STREAM(stream)>>>(logits, targets, n, partial);
   int rc = check_launch("seg_metrics_partial_kernel");
   if (rc) return rc;
   count_launch();
-  launch_k(seg_metrics_accumulate_kernel, dim3(1), dim3(kThreads), 0, STREAM(stream), partial, blocks, n, counters);
+  seg_metrics_accumulate_kernel<<<1, kThreads, 0, STREAM(stream)>>>(partial, blocks, n, counters);
   return check_launch("seg_metrics_accumulate_kernel");
 }
 
@@ -1530,7 +1535,9 @@ extern "C" int b2s_pack_conv_weight(const float* w, void* w_fwd, void* w_dgrad, 
   if (ksize != 1 && ksize != 3) return set_error(B2S_ERR_ARG, "b2s_pack_conv_weight: ksize must be 1 or 3");
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
   count_launch();
-  launch_k(pack_conv_weight_kernel, dim3(grid), dim3(kThreads), 0, STREAM(stream), w, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad), Cout, Cin, ksize * ksize);
+  pack_conv_weight_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(w, static_cast<__nv_bfloat16*>(w_fwd),
+                                                           static_cast<__nv_bfloat16*>(w_dgrad), Cout, Cin,
+                                                           ksize * ksize);
   return check_launch("pack_conv_weight_kernel");
 }
 
@@ -1538,7 +1545,8 @@ extern "C" int b2s_pack_convt_weight(const float* w, void* w_fwd, void* w_dgrad,
   if (!w || (!w_fwd && !w_dgrad)) return set_error(B2S_ERR_ARG, "b2s_pack_convt_weight: null pointer");
   const long long total = static_cast<long long>(Cin) * Cout * 4;
   count_launch();
-  launch_k(pack_convt_weight_kernel, dim3(grid_for(total, kThreads * 4)), dim3(kThreads), 0, STREAM(stream),  w, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad), Cin, Cout);
+  pack_convt_weight_kernel<<<grid_for(total, kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad), Cin, Cout);
   return check_launch("pack_convt_weight_kernel");
 }
 
@@ -1560,7 +1568,7 @@ extern "C" int b2s_pack_weights_all(int n, const void* const* w, void* const* wf
   }
   tab.n = n;
   count_launch();
-  launch_k(pack_all_kernel, dim3(blocks), dim3(kThreads), 0, STREAM(stream), tab);
+  pack_all_kernel<<<blocks, kThreads, 0, STREAM(stream)>>>(tab);
   return check_launch("pack_all_kernel");
 }
 
@@ -1573,7 +1581,7 @@ extern "C" int b2s_wgrad_reduce(const float* ws, int splits, int taps, int Cin, 
   const int cpb = 8 / sgroups;
   dim3 grid((Cin + cpb - 1) / cpb, (Cout + 127) / 128);
   count_launch();
-  launch_k(wgrad_reduce_kernel, dim3(grid), dim3(kThreads), 0, STREAM(stream), ws, splits, taps, Cin, Cout, dw, layout, sgroups);
+  wgrad_reduce_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(ws, splits, taps, Cin, Cout, dw, layout, sgroups);
   return check_launch("wgrad_reduce_kernel");
 }
 
@@ -1584,7 +1592,9 @@ extern "C" int b2s_adamw_step(float* p, const float* g, float* m, float* v, long
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   count_launch();
-  launch_k(adamw_kernel, dim3(grid_for(n, kThreads * 8)), dim3(kThreads), 0, STREAM(stream),  p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale);
+  adamw_kernel<<<grid_for(n, kThreads * 8), kThreads, 0, STREAM(stream)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
+      grad_scale);
   return check_launch("adamw_kernel");
 }
 
@@ -1592,7 +1602,7 @@ extern "C" int b2s_adamw_step_dev(float* p, const float* g, float* m, float* v, 
                                   void* stream) {
   if (!p || !g || !m || !v || !hyper) return set_error(B2S_ERR_ARG, "b2s_adamw_step_dev: null pointer");
   count_launch();
-  launch_k(adamw_dev_kernel, dim3(grid_for(n, kThreads * 8)), dim3(kThreads), 0, STREAM(stream), p, g, m, v, n, hyper);
+  adamw_dev_kernel<<<grid_for(n, kThreads * 8), kThreads, 0, STREAM(stream)>>>(p, g, m, v, n, hyper);
   return check_launch("adamw_dev_kernel");
 }
 
@@ -1601,6 +1611,7 @@ extern "C" int b2s_copy_channels(const void* src, int src_cstride, void* dst, in
   if (!src || !dst) return set_error(B2S_ERR_ARG, "b2s_copy_channels: null pointer");
   if (C % 8 || src_cstride % 8 || dst_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_copy_channels: need multiples of 8");
   count_launch();
-  launch_k(copy_channels_kernel, dim3(grid_for(npix * (C / 8), kThreads * 4)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(src), src_cstride, static_cast<__nv_bfloat16*>(dst), dst_cstride, npix, C);
+  copy_channels_kernel<<<grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), src_cstride, static_cast<__nv_bfloat16*>(dst), dst_cstride, npix, C);
   return check_launch("copy_channels_kernel");
 }

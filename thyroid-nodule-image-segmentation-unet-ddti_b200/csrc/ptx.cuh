@@ -18,16 +18,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
-// Every libb2s kernel is launched with the programmatic-stream-serialization attribute (launch_k, b2s_internal.h):
-// the next kernel in the stream may be scheduled, and run its prologue, while this one drains. A kernel therefore
-// calls pdl_wait() -- all threads, before its first global-memory access -- which returns once every prerequisite
-// grid has completed and flushed; pdl_launch_dependents() lets the successor be scheduled as soon as every CTA of
-// this grid is resident. Both are no-ops for a launch without the attribute.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_entry() { pdl_wait(); pdl_launch_dependents(); }
-
 __device__ __forceinline__ uint32_t lane_id() {
   uint32_t l;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));

@@ -47,7 +47,6 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ z, int z_cs, const float* 
                     const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_cs,
                     __nv_bfloat16* __restrict__ out, int out_cs, long long npix, int C, uint32_t drop_thresh,
                     float drop_scale, uint32_t seed, const long long* __restrict__ step_counter) {
-  pdl_entry();
   extern __shared__ uint4 ring_smem[];
   constexpr int NV = HAS_RES ? 2 : 1, DEPTH = kBnActDepth;
   const PrefetchRing<NV, DEPTH> ring(ring_smem);   // vector 0: z, 1: res
@@ -109,7 +108,6 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
                   const float* __restrict__ invstd, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dz,
                   int dz_cs, float* __restrict__ partial, long long npix, int C, uint32_t drop_thresh,
                   float drop_scale, uint32_t seed, const long long* __restrict__ step_counter) {
-  pdl_entry();
   extern __shared__ uint4 ring_smem[];      // prefetch ring; reused for the block reduction after the loop
   constexpr int DEPTH = kBnActDepth;
   const PrefetchRing<2, DEPTH> ring(ring_smem);    // vector 0: z, 1: da
@@ -197,7 +195,6 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
 // partial [kEwBlocks][C] = per-block sums over pixels of x (bias gradients of convs that are not followed by BN)
 __global__ void __launch_bounds__(kThreads)
 channel_sums_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, float* __restrict__ partial, long long npix, int C) {
-  pdl_entry();
   __shared__ float red[kThreads * 8];
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
@@ -241,7 +238,6 @@ channel_sums_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, float* __rest
 __global__ void __launch_bounds__(kThreads)
 upsample_zero2x_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_bfloat16* __restrict__ dst, int dst_cs,
                        int N, int Hs, int Ws, int C) {
-  pdl_entry();
   const int groups = C / 8;
   const int Hd = 2 * Hs, Wd = 2 * Ws;
   const long long total = static_cast<long long>(N) * Hd * Wd * groups;
@@ -263,7 +259,6 @@ upsample_zero2x_kernel(const __nv_bfloat16* __restrict__ src, int src_cs, __nv_b
 __global__ void __launch_bounds__(kThreads)
 relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat16* __restrict__ y, int y_cs,
                 __nv_bfloat16* __restrict__ dx, int dx_cs, long long npix, int C) {
-  pdl_entry();
   const int groups = C / 8;
   const long long total = npix * groups;
   for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
@@ -284,7 +279,6 @@ relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bflo
 __global__ void __launch_bounds__(kThreads)
 maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat16* __restrict__ dpool, int dp_cs,
                       __nv_bfloat16* __restrict__ dx, int dx_cs, int N, int H, int W, int C) {
-  pdl_entry();
   const int groups = C / 8;
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(N) * Ho * Wo * groups;
@@ -329,7 +323,6 @@ template <bool DOT>
 __global__ void __launch_bounds__(kThreads)
 se_pool_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat16* __restrict__ y, int y_cs,
                float* __restrict__ partial, long long HW, int C, int chunks) {
-  pdl_entry();
   __shared__ float red[kThreads * 8];
   const int groups = C / 8;                 // power of two <= 256 (host-checked)
   const int cg = threadIdx.x % groups;
@@ -386,7 +379,6 @@ se_fc_fwd_kernel(const float* __restrict__ partial, int chunks, float inv_hw, co
                  const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                  float* __restrict__ mean_out, float* __restrict__ hidden_out, float* __restrict__ gate_out, int C,
                  int Cr) {
-  pdl_entry();
   extern __shared__ float sm[];   // mean [C], hidden [Cr]
   float* mean = sm;
   float* hid = sm + C;
@@ -419,7 +411,6 @@ __global__ void __launch_bounds__(kThreads)
 se_scale_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const float* __restrict__ gate,
                 const float* __restrict__ add, float add_scale, __nv_bfloat16* __restrict__ y, int y_cs, long long HW,
                 int C, long long npix) {
-  pdl_entry();
   // forward: y = x * gate;  backward (add != nullptr): dx = dy * gate + add[n][c] * add_scale, with x := dy
   const int groups = C / 8;
   const bool pow2 = (groups & (groups - 1)) == 0;
@@ -466,7 +457,6 @@ __global__ void __launch_bounds__(kThreads)
 se_fc_bwd_kernel(const float* __restrict__ partial, int chunks, const float* __restrict__ gate,
                  const float* __restrict__ hidden, const float* __restrict__ w1, const float* __restrict__ w2,
                  float* __restrict__ ds_out, float* __restrict__ dh_out, float* __restrict__ dmean_out, int C, int Cr) {
-  pdl_entry();
   extern __shared__ float sm[];   // ds [C], dh [Cr]
   float* ds = sm;
   float* dh = sm + C;
@@ -500,7 +490,6 @@ se_fc_bwd_kernel(const float* __restrict__ partial, int chunks, const float* __r
 __global__ void __launch_bounds__(kThreads)
 outer_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                  float* __restrict__ out_bias, int N, int R, int K) {
-  pdl_entry();
   const long long total = static_cast<long long>(R) * K;
   for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kThreads) {
@@ -551,7 +540,7 @@ static void launch_ring(K kernel, int smem, long long items, int per_block, cuda
     if (nseen < 32) { seen[nseen] = reinterpret_cast<const void*>(kernel); waves[nseen] = wave; ++nseen; }
   }
   const int grid = items < 0 ? wave : ew_clamp_grid(wave, items, per_block);
-  launch_k(kernel, dim3(grid), dim3(kThreads), smem, stream, args...);
+  kernel<<<grid, kThreads, smem, stream>>>(args...);
 }
 
 template <int RELU, bool DROP>
@@ -642,7 +631,9 @@ extern "C" int b2s_relu_bwd(const void* dy, int dy_cstride, const void* y, int y
   if (!dy || !y || !dx) return set_error(B2S_ERR_ARG, "b2s_relu_bwd: null pointer");
   if (C % 8 || dy_cstride % 8 || y_cstride % 8 || dx_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_relu_bwd: need multiples of 8");
   count_launch();
-  launch_k(relu_bwd_kernel, dim3(ew_grid_for(npix * (C / 8), kThreads * 4)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(dy), dy_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride, static_cast<__nv_bfloat16*>(dx), dx_cstride, npix, C);
+  relu_bwd_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), dy_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride,
+      static_cast<__nv_bfloat16*>(dx), dx_cstride, npix, C);
   return check_launch("relu_bwd_kernel");
 }
 
@@ -653,7 +644,9 @@ extern "C" int b2s_maxpool2x2_bwd(const void* x, int x_cstride, const void* dpoo
     return set_error(B2S_ERR_ARG, "b2s_maxpool2x2_bwd: need C % 8 == 0, even H and W");
   const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   count_launch();
-  launch_k(maxpool2x2_bwd_kernel, dim3(ew_grid_for(items, kThreads * 2)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(dpool), dpool_cstride, static_cast<__nv_bfloat16*>(dx), dx_cstride, N, H, W, C);
+  maxpool2x2_bwd_kernel<<<ew_grid_for(items, kThreads * 2), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(dpool), dpool_cstride,
+      static_cast<__nv_bfloat16*>(dx), dx_cstride, N, H, W, C);
   return check_launch("maxpool2x2_bwd_kernel");
 }
 
@@ -661,7 +654,8 @@ extern "C" int b2s_channel_sums(const void* x, int x_cstride, float* partial, lo
   if (!x || !partial) return set_error(B2S_ERR_ARG, "b2s_channel_sums: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_channel_sums: unsupported C");
   count_launch();
-  launch_k(channel_sums_kernel, dim3(kEwBlocks), dim3(kThreads), 0, STREAM(stream), static_cast<const __nv_bfloat16*>(x), x_cstride, partial, npix, C);
+  channel_sums_kernel<<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_cstride, partial, npix, C);
   return check_launch("channel_sums_kernel");
 }
 
@@ -671,7 +665,9 @@ extern "C" int b2s_upsample_zero2x(const void* src, int src_cstride, void* dst, 
   if (C % 8 || src_cstride % 8 || dst_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_upsample_zero2x: need multiples of 8");
   const long long items = static_cast<long long>(N) * 4 * Hs * Ws * (C / 8);
   count_launch();
-  launch_k(upsample_zero2x_kernel, dim3(ew_grid_for(items, kThreads * 4)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(src), src_cstride, static_cast<__nv_bfloat16*>(dst), dst_cstride, N, Hs, Ws, C);
+  upsample_zero2x_kernel<<<ew_grid_for(items, kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), src_cstride, static_cast<__nv_bfloat16*>(dst), dst_cstride, N, Hs, Ws,
+      C);
   return check_launch("upsample_zero2x_kernel");
 }
 
@@ -690,9 +686,12 @@ extern "C" int b2s_se_pool(const void* x, int x_cstride, const void* y, int y_cs
   dim3 grid(chunks, N);
   count_launch();
   if (y)
-    launch_k(se_pool_kernel<true>, dim3(grid), dim3(kThreads), 0, STREAM(stream), static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride, partial, HW, C, chunks);
+    se_pool_kernel<true><<<grid, kThreads, 0, STREAM(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride, partial,
+        HW, C, chunks);
   else
-    launch_k(se_pool_kernel<false>, dim3(grid), dim3(kThreads), 0, STREAM(stream), static_cast<const __nv_bfloat16*>(x), x_cstride, nullptr, 0, partial, HW, C, chunks);
+    se_pool_kernel<false><<<grid, kThreads, 0, STREAM(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), x_cstride, nullptr, 0, partial, HW, C, chunks);
   return check_launch("se_pool_kernel");
 }
 
@@ -703,7 +702,8 @@ extern "C" int b2s_se_fc_fwd(const float* partial, int chunks, long long HW, con
     return set_error(B2S_ERR_ARG, "b2s_se_fc_fwd: null pointer");
   if (C > 4096 || Cr < 1 || Cr > C) return set_error(B2S_ERR_ARG, "b2s_se_fc_fwd: unsupported channel counts");
   count_launch();
-  launch_k(se_fc_fwd_kernel, dim3(N), dim3(kThreads), (C + Cr) * sizeof(float), STREAM(stream), partial, chunks, 1.f / static_cast<float>(HW), w1, b1, w2, b2, mean, hidden, gate, C, Cr);
+  se_fc_fwd_kernel<<<N, kThreads, (C + Cr) * sizeof(float), STREAM(stream)>>>(
+      partial, chunks, 1.f / static_cast<float>(HW), w1, b1, w2, b2, mean, hidden, gate, C, Cr);
   return check_launch("se_fc_fwd_kernel");
 }
 
@@ -713,7 +713,9 @@ extern "C" int b2s_se_scale(const void* x, int x_cstride, const float* gate, con
   if (C % 8 || x_cstride % 8 || y_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_se_scale: need multiples of 8");
   const long long npix = static_cast<long long>(N) * HW;
   count_launch();
-  launch_k(se_scale_kernel, dim3(ew_grid_for(npix * (C / 8), kThreads * 4)), dim3(kThreads), 0, STREAM(stream),  static_cast<const __nv_bfloat16*>(x), x_cstride, gate, add, add_scale, static_cast<__nv_bfloat16*>(y), y_cstride, HW, C, npix);
+  se_scale_kernel<<<ew_grid_for(npix * (C / 8), kThreads * 4), kThreads, 0, STREAM(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_cstride, gate, add, add_scale, static_cast<__nv_bfloat16*>(y),
+      y_cstride, HW, C, npix);
   return check_launch("se_scale_kernel");
 }
 
@@ -724,13 +726,16 @@ extern "C" int b2s_se_fc_bwd(const float* partial, int chunks, const float* gate
     return set_error(B2S_ERR_ARG, "b2s_se_fc_bwd: null pointer");
   if (C > 4096 || Cr < 1 || Cr > C) return set_error(B2S_ERR_ARG, "b2s_se_fc_bwd: unsupported channel counts");
   count_launch();
-  launch_k(se_fc_bwd_kernel, dim3(N), dim3(kThreads), (C + Cr) * sizeof(float), STREAM(stream), partial, chunks, gate, hidden, w1, w2, ds, dh, dmean, C, Cr);
+  se_fc_bwd_kernel<<<N, kThreads, (C + Cr) * sizeof(float), STREAM(stream)>>>(
+      partial, chunks, gate, hidden, w1, w2, ds, dh, dmean, C, Cr);
   int rc = check_launch("se_fc_bwd_kernel");
   if (rc) return rc;
   // dW2 [C][Cr] = sum_n ds (x) hidden, db2 = sum_n ds;  dW1 [Cr][C] = sum_n dh (x) mean, db1 = sum_n dh
   count_launch();
-  launch_k(outer_sum_kernel, dim3(ew_grid_for(static_cast<long long>(C) * Cr, kThreads)), dim3(kThreads), 0, STREAM(stream), ds, hidden, dw2, db2, N, C, Cr);
+  outer_sum_kernel<<<ew_grid_for(static_cast<long long>(C) * Cr, kThreads), kThreads, 0, STREAM(stream)>>>(
+      ds, hidden, dw2, db2, N, C, Cr);
   count_launch();
-  launch_k(outer_sum_kernel, dim3(ew_grid_for(static_cast<long long>(C) * Cr, kThreads)), dim3(kThreads), 0, STREAM(stream), dh, mean, dw1, db1, N, Cr, C);
+  outer_sum_kernel<<<ew_grid_for(static_cast<long long>(C) * Cr, kThreads), kThreads, 0, STREAM(stream)>>>(
+      dh, mean, dw1, db1, N, Cr, C);
   return check_launch("outer_sum_kernel");
 }

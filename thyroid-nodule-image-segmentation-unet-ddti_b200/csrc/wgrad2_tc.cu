@@ -88,9 +88,6 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // barriers, TMEM and descriptors are set up: from here on the kernel touches memory its predecessor may still
-  // be writing (programmatic dependent launch, ptx.cuh)
-  pdl_entry();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -206,7 +203,7 @@ static int launch_wg2(int grid, const CUtensorMap& tmX, const CUtensorMap& tmDz,
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(wgrad_halo_kernel)");
     attr_set = true;
   }
-  launch_k(kfn, dim3(grid), dim3(kWg2Threads), L::kDynBytes, stream, tmX, tmDz, p);
+  kfn<<<grid, kWg2Threads, L::kDynBytes, stream>>>(tmX, tmDz, p);
   return check_launch("wgrad_halo_kernel");
 }
 
