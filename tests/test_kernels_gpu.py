@@ -579,13 +579,15 @@ def test_seg_loss_fwd_bwd(ops, B, HW, soft):
     report("sums", sums.view(B, 4), ref["sums"], rel=1e-5, abs_frac=1e-6)
 
 
-def test_adamw_matches_oracle(ops):
-    n = 10007
+@pytest.mark.parametrize("n,offset", [(10007, 0), (10007, 1), (1200003, 0)])
+def test_adamw_matches_oracle(ops, n, offset):
+    """offset 1: buffers that are not 16-byte aligned (one-by-one path); 1.2 M: every thread loops, plus a 3-element tail"""
     p, g = rnd((n,), 131), rnd((n,), 132)
-    pd, m, v = p.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    view = lambda t: torch.cat([torch.zeros(offset), t]).to(DEV)[offset:]
+    pd, m, v = view(p), view(torch.zeros(n)), view(torch.zeros(n))
     pr, mr, vr = p.double(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
     for s in range(1, 4):
-        ops.adamw_step(pd, (g * s).to(DEV), m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, s, 1.0)
+        ops.adamw_step(pd, view(g * s), m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, s, 1.0)
         O.adamw_step(pr, (g * s).double(), mr, vr, 1e-3, step=s)
     torch.cuda.synchronize()
     report("adamw", pd, pr, rel=1e-6, abs_frac=1e-7)

@@ -1163,21 +1163,50 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int Cin,
   }
 }
 
+// One AdamW update (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments).
+__device__ __forceinline__ void adamw_update(float& p, float g, float& m, float& v, float lr, float beta1, float beta2,
+                                             float eps, float wd, float step_size, float bc2_sqrt, float grad_scale) {
+  const float gi = g * grad_scale;
+  float pi = p * (1.f - lr * wd);
+  const float mi = beta1 * m + (1.f - beta1) * gi;
+  const float vi = beta2 * v + (1.f - beta2) * gi * gi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi -= step_size * (mi / denom);
+  p = pi; m = mi; v = vi;
+}
+
+// Four parameters per thread and trip (four 16-byte loads in flight per thread); the last n % 4 elements -- or all of
+// them when a buffer is not 16-byte aligned (vec == false) -- go one by one.
+__device__ __forceinline__ void adamw_span(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                           float* __restrict__ v, long long n, bool vec, float lr, float beta1,
+                                           float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+                                           float grad_scale) {
+  const float step_size = lr / bc1;
+  const long long n4 = vec ? n >> 2 : 0;
+  const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = tid; i < n4; i += stride) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    adamw_update(pp.x, gg.x, mm.x, vv.x, lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, grad_scale);
+    adamw_update(pp.y, gg.y, mm.y, vv.y, lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, grad_scale);
+    adamw_update(pp.z, gg.z, mm.z, vv.z, lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, grad_scale);
+    adamw_update(pp.w, gg.w, mm.w, vv.w, lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, grad_scale);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  for (long long i = (n4 << 2) + tid; i < n; i += stride)
+    adamw_update(p[i], g[i], m[i], v[i], lr, beta1, beta2, eps, wd, step_size, bc2_sqrt, grad_scale);
+}
+
 __global__ void __launch_bounds__(kThreads)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+             long long n, bool vec, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
              float grad_scale) {
-  const float step_size = lr / bc1;
-  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
-    const float gi = g[i] * grad_scale;
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= step_size * (mi / denom);
-    p[i] = pi; m[i] = mi; v[i] = vi;
-  }
+  adamw_span(p, g, m, v, n, vec, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
 }
 
 // Same update with the hyper-parameters read from device memory, so that a CUDA graph of the whole training step can
@@ -1185,20 +1214,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 // grad_scale}.
 __global__ void __launch_bounds__(kThreads)
 adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 long long n, const float* __restrict__ hyper) {
-  const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5],
-              bc2_sqrt = hyper[6], grad_scale = hyper[7];
-  const float step_size = lr / bc1;
-  for (long long i = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
-    const float gi = g[i] * grad_scale;
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= step_size * (mi / denom);
-    p[i] = pi; m[i] = mi; v[i] = vi;
-  }
+                 long long n, bool vec, const float* __restrict__ hyper) {
+  adamw_span(p, g, m, v, n, vec, hyper[0], hyper[1], hyper[2], hyper[3], hyper[4], hyper[5], hyper[6], hyper[7]);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -1585,6 +1602,11 @@ extern "C" int b2s_wgrad_reduce(const float* ws, int splits, int taps, int Cin, 
   return check_launch("wgrad_reduce_kernel");
 }
 
+static bool adamw_aligned(const float* p, const float* g, const float* m, const float* v) {
+  return ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+           reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+}
+
 extern "C" int b2s_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
   if (!p || !g || !m || !v) return set_error(B2S_ERR_ARG, "b2s_adamw_step: null pointer");
@@ -1593,7 +1615,7 @@ extern "C" int b2s_adamw_step(float* p, const float* g, float* m, float* v, long
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   count_launch();
   adamw_kernel<<<grid_for(n, kThreads * 8), kThreads, 0, STREAM(stream)>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
+      p, g, m, v, n, adamw_aligned(p, g, m, v), lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
       grad_scale);
   return check_launch("adamw_kernel");
 }
@@ -1602,7 +1624,8 @@ extern "C" int b2s_adamw_step_dev(float* p, const float* g, float* m, float* v, 
                                   void* stream) {
   if (!p || !g || !m || !v || !hyper) return set_error(B2S_ERR_ARG, "b2s_adamw_step_dev: null pointer");
   count_launch();
-  adamw_dev_kernel<<<grid_for(n, kThreads * 8), kThreads, 0, STREAM(stream)>>>(p, g, m, v, n, hyper);
+  adamw_dev_kernel<<<grid_for(n, kThreads * 8), kThreads, 0, STREAM(stream)>>>(p, g, m, v, n,
+                                                                              adamw_aligned(p, g, m, v), hyper);
   return check_launch("adamw_dev_kernel");
 }
 
