@@ -23,6 +23,9 @@ WANT = {
  "smsp__cycles_active.avg": "smsp_cycles_active",
  "gpc__cycles_elapsed.max": "gpc_cycles",
  "sm__cycles_elapsed.avg.per_second": "sm_hz",
+ "sm__inst_issued.avg.pct_of_peak_sustained_active": "issue_slots_busy_pct",
+ "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
+ "smsp__inst_executed.sum": "warp_instructions",
 }
 def main():
     rep = sys.argv[1]
