@@ -175,7 +175,7 @@ int b2s_copy_channels(const void* src, int src_cstride, void* dst, int dst_cstri
 /* ---- V-Net variant (models/vnet.py) ------------------------------------------------------------------------- */
 
 /* nn.Conv2d(C,2C,3,stride=2,padding=1) forward (models/vnet.py:97): x [N,H,W,Cin] -> y [N,H/2,W/2,Cout] (+bias);
- * the A tiles are TMA boxes with elementStrides = 2. Its input and weight gradients are b2s_conv_fwd (rotated
+ * the A tiles are dense TMA boxes over one pixel-parity class of x. Its input and weight gradients are b2s_conv_fwd (rotated
  * weights) and b2s_conv3x3_wgrad applied to the zero-inserted output gradient from b2s_upsample_zero2x. */
 int b2s_conv3x3_s2_fwd(const void* x, int x_cstride, const void* w_packed, const float* bias, void* y, int y_cstride,
                        int N, int H, int W, int Cin, int Cout, int tile_n, void* stream);
@@ -185,7 +185,7 @@ int b2s_conv3x3_s2_fwd(const void* x, int x_cstride, const void* w_packed, const
  * zero-insertion path then. */
 int b2s_conv3x3_s2_dgrad(const void* dz, int dz_cstride, const void* w_dgrad_packed, void* dx, int dx_cstride, int N,
                          int H, int W, int Cin, int Cout, int tile_n, void* stream);
-/* its weight gradient: x boxes loaded with elementStrides = 2; workspace / splits from
+/* its weight gradient: x read as parity-class boxes (no zero insertion); workspace / splits from
  * b2s_conv_wgrad_workspace(N, H/2, W/2, Cin, Cout, 3, tile_n | 4096, splits, &s). */
 int b2s_conv3x3_s2_wgrad(const void* x, int x_cstride, const void* dz, int dz_cstride, float* ws, int N, int H, int W,
                          int Cin, int Cout, int tile_n, int splits, void* stream);

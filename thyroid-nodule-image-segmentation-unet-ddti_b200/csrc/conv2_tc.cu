@@ -162,9 +162,11 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (p.a_mode == A_CONV3) {
                 const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;
                 tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0[mt] + dw, h0[mt] + dh, n0[mt]);
-              } else if (p.a_mode == A_CONV3_S2) {   // stride 2: the map steps two input pixels per box element
-                const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;
-                tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, 2 * w0[mt] + dw, 2 * h0[mt] + dh, n0[mt]);
+              } else if (p.a_mode == A_CONV3_S2) {   // stride 2: one parity class of the input per tap (make_act_map5_parity)
+                const int dh = tap / 3 - 1, dw = tap - (tap / 3) * 3 - 1;   // input pixel = 2 * output pixel + (dh, dw)
+                const int ph = dh & 1, pw = dw & 1;
+                tma_load_5d(&tmA, &full_bar[stage], a_dst, pw * p.a_cstride + kc * kBlockK, w0[mt] + ((dw - pw) >> 1), ph,
+                            h0[mt] + ((dh - ph) >> 1), n0[mt]);
               } else if (p.a_mode == A_TAPLIST) {    // explicit tap offsets (stride-2 conv input gradient, one parity class)
                 tma_load_4d(&tmA, &full_bar[stage], a_dst, kc * kBlockK, w0[mt] + p.tap_dw[tap], h0[mt] + p.tap_dh[tap],
                             n0[mt]);

@@ -26,6 +26,7 @@ struct ConvTcParams {
   int flags;                       // B2S_FLAG_*
   int tap_dh[4], tap_dw[4], tap_w[4];  // A_TAPLIST: pixel offsets of tap t and its row block in the packed weights
   int sub_a, sub_b;                // OUT_SUB_5D: sub-lattice (row, column parity) of the 2x up-sampled output
+  int a_cstride;                   // A_CONV3_S2: pixel stride (elements) of the input, the offset of the odd-column parity
   const float* bias;               // [cout_sub] or nullptr
   const float* post_scale;         // eval-mode BatchNorm folded into the epilogue: y = act(acc + bias) * post_scale +
   const float* post_shift;         // post_shift per output channel (both nullptr in training)
@@ -97,15 +98,18 @@ static inline int make_act_map4(CUtensorMap* m, const void* base, int C, int W, 
   uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
   return make_tmap(m, base, 4, dims, str, box);
 }
-// Same, traversing every second pixel in W and H (stride-2 convolution input): a box of (bw, bh) OUTPUT pixels is
-// encoded as boxDim = 2 * (bw, bh) with elementStrides = 2 (TMA loads ceil(boxDim / elementStride) elements).
-static inline int make_act_map4_s2(CUtensorMap* m, const void* base, int C, int W, int H, int N, int cstride, int bw,
-                                   int bh, int bn) {
-  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-  uint64_t str[3] = {(uint64_t)cstride * 2, (uint64_t)W * cstride * 2, (uint64_t)H * W * cstride * 2};
-  uint32_t box[4] = {64, (uint32_t)(2 * bw), (uint32_t)(2 * bh), (uint32_t)bn};
-  uint32_t es[4] = {1, 2, 2, 1};
-  return make_tmap(m, base, 4, dims, str, box, es);
+// Stride-2 sampling without element strides (a box with elementStrides = 2 makes TMA fetch the skipped pixels as
+// well: 182 TFLOP/s for the 64 -> 128 conv at 512^2). The NHWC tensor is viewed as (pc, w2, ph, h2, n) with
+// w = 2*w2 + pw, h = 2*h2 + ph and pc = pw * cstride + c: a pixel pair is one row of cstride + C elements, so the
+// parity pw is an offset in the innermost coordinate. One parity class of an image is then a dense box
+// {64, bw, 1, bh, bn}; w2 = -1 / h2 = -1 (the conv's zero padding) are out of bounds of their own dimensions.
+static inline int make_act_map5_parity(CUtensorMap* m, const void* base, int C, int W, int H, int N, int cstride, int bw,
+                                       int bh, int bn) {
+  uint64_t dims[5] = {(uint64_t)cstride + C, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)N};
+  uint64_t str[4] = {2ull * cstride * 2, (uint64_t)W * cstride * 2, 2ull * W * cstride * 2,
+                     (uint64_t)H * W * cstride * 2};
+  uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bn};
+  return make_tmap(m, base, 5, dims, str, box);
 }
 // 2x-upsampled NHWC tensor [N, 2Hi, 2Wi, C] viewed as (C, b, j, a, i*N) so that one (a,b) sub-lattice is a box.
 static inline int make_up_map5(CUtensorMap* m, const void* base, int C, int Wi, int Hi, int N, int cstride, int bw,

@@ -293,6 +293,7 @@ struct WgradParams {
   int m_tiles;                    // ceil(total_rb / (2 * mt))
   int splits, chunks_total, chunks_per_split;
   int mode;
+  int x_cstride;                  // WG_CONV3_S2: pixel stride (elements) of x, the offset of the odd-column parity
   float* ws;                      // [splits][num_taps*cin][cout] fp32
 };
 
@@ -383,9 +384,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int j = 0; j < NRB; ++j) {
           int dh = 0, dw = 0;
           if (p.mode == WG_CONV3 || p.mode == WG_CONV3_S2) { dh = tap_j[j] / 3 - 1; dw = tap_j[j] % 3 - 1; }
-          if (p.mode == WG_CONV3_S2)   // the x map steps two input pixels per box element (stride-2 conv)
-            tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 8192, cib_j[j] * 64, 2 * w0 + dw, 2 * h0 + dh, n0);
-          else
+          if (p.mode == WG_CONV3_S2) {   // stride-2 conv: one parity class of x per tap (make_act_map5_parity)
+            const int ph = dh & 1, pw = dw & 1;
+            tma_load_5d(&tmA, &full_bar[stage], a_dst + j * 8192, pw * p.x_cstride + cib_j[j] * 64, w0 + ((dw - pw) >> 1),
+                        ph, h0 + ((dh - ph) >> 1), n0);
+          } else
             tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 8192, cib_j[j] * 64, w0 + dw, h0 + dh, n0);
         }
         if (p.mode != WG_CONVT) {
@@ -588,7 +591,8 @@ extern "C" int b2s_conv3x3_s2_fwd(const void* x, int x_cstride, const void* w_pa
   p.flags = 0; p.bias = bias; p.stats = nullptr;
   CUtensorMap tmA, tmB, tmOut;
   int rc;
-  if ((rc = make_act_map4_s2(&tmA, x, Cin, W, H, N, x_cstride, pl.bw, pl.bh, pl.bn))) return rc;
+  p.a_cstride = x_cstride;
+  if ((rc = make_act_map5_parity(&tmA, x, Cin, W, H, N, x_cstride, pl.bw, pl.bh, pl.bn))) return rc;
   if ((rc = make_weight_map(&tmB, w_packed, Cin, 9 * Cout, pl.block_n))) return rc;
   if ((rc = make_act_map4(&tmOut, y, Cout, Wo, Ho, N, y_cstride, pl.bw, pl.bh, pl.bn))) return rc;
   return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
@@ -824,10 +828,10 @@ extern "C" int b2s_conv3x3_s2_wgrad(const void* x, int x_cstride, const void* dz
   int block_n;
   if (wgrad_plan(N, Ho, Wo, Cin, Cout, 9, tile_n, splits, &p, &block_n))
     return set_error(B2S_ERR_ARG, "b2s_conv3x3_s2_wgrad: bad tile_n");
-  p.mode = WG_CONV3_S2; p.ws = ws;
+  p.mode = WG_CONV3_S2; p.ws = ws; p.x_cstride = x_cstride;
   CUtensorMap tmA, tmB;
   int rc;
-  if ((rc = make_act_map4_s2(&tmA, x, Cin, W, H, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
+  if ((rc = make_act_map5_parity(&tmA, x, Cin, W, H, N, x_cstride, p.pw, p.ph, p.pn))) return rc;
   if ((rc = make_act_map4(&tmB, dz, Cout, Wo, Ho, N, dz_cstride, p.pw, p.ph, p.pn))) return rc;
   return dispatch_wgrad(block_n, tmA, tmB, p, stream);
 }

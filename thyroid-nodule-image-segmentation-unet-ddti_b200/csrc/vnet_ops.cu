@@ -193,9 +193,13 @@ bn_act_bwd_kernel(const __nv_bfloat16* __restrict__ da, int da_cs, const __nv_bf
 }
 
 // partial [kEwBlocks][C] = per-block sums over pixels of x (bias gradients of convs that are not followed by BN)
+constexpr int kChannelSumsDepth = 8;
+
 __global__ void __launch_bounds__(kThreads)
 channel_sums_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, float* __restrict__ partial, long long npix, int C) {
-  __shared__ float red[kThreads * 8];
+  extern __shared__ uint4 ring_smem[];      // prefetch ring; reused for the block reduction after the loop
+  constexpr int DEPTH = kChannelSumsDepth;
+  const PrefetchRing<1, DEPTH> ring(ring_smem);
   const int groups = C / 8;
   const int gshift = __ffs(groups) - 1;
   const long long tid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
@@ -205,22 +209,28 @@ channel_sums_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, float* __rest
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   const long long total = npix * groups;
-  constexpr int U = 4;   // independent 16-byte loads in flight per thread
-  for (long long i0 = tid; i0 < total; i0 += stride * U) {
-    uint4 raw[U];
+  long long inext = tid;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      raw[u] = i < total ? ldg16(x + (i >> gshift) * x_cs + cg * 8) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float v[8];
-      unpack8(raw[u], v);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += v[k];
-    }
+  for (int s = 0; s < DEPTH; ++s) {
+    if (inext < total) ring.fetch(s, 0, x + (inext >> gshift) * x_cs + cg * 8);
+    cp_async_commit();
+    inext += stride;
   }
+  int stage = 0;
+  for (long long i = tid; i < total; i += stride) {
+    cp_async_wait<DEPTH - 1>();
+    float v[8];
+    unpack8(ring.get(stage, 0), v);
+    if (inext < total) ring.fetch(stage, 0, x + (inext >> gshift) * x_cs + cg * 8);
+    cp_async_commit();
+    inext += stride;
+    stage = stage + 1 == DEPTH ? 0 : stage + 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+  }
+  float* red = reinterpret_cast<float*>(ring_smem);
+  cp_async_wait<0>();
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
   __syncthreads();
@@ -315,15 +325,21 @@ maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_
 // Pixels of one sample reduced by one block: 256 at the deep levels (few pixels per sample), more at high resolution
 // so that a block streams >= 0.5 MB instead of paying a launch + block reduction per 32 KB.
 __host__ __device__ constexpr int se_pix_per_block(long long HW) {
-  return HW >= (1ll << 18) ? 4096 : HW >= (1ll << 16) ? 1024 : 256;   // >= 64 blocks per sample from 128^2 upwards
+  return HW >= (1ll << 18) ? 4096 : HW >= (1ll << 16) ? 1024 : HW >= (1ll << 12) ? 256 : 64;   // >= 16 blocks per sample
 }
 
-// partial[n][chunk][C] = sum over the chunk's pixels of x (DOT: of x * y)
+// partial[n][chunk][C] = sum over the chunk's pixels of x (DOT: of x * y). The loads go through the per-thread
+// prefetch ring: with plain register loads ptxas interleaved each load with its adds (35 registers, one or two loads in
+// flight per thread: 3.4 TB/s at 512^2 and 0.5 TB/s at 32^2, where only 64 blocks exist).
+constexpr int kSePoolDepth = 8;
+
 template <bool DOT>
 __global__ void __launch_bounds__(kThreads)
 se_pool_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat16* __restrict__ y, int y_cs,
                float* __restrict__ partial, long long HW, int C, int chunks) {
-  __shared__ float red[kThreads * 8];
+  extern __shared__ uint4 ring_smem[];      // prefetch ring; reused for the block reduction after the loop
+  constexpr int NV = DOT ? 2 : 1, DEPTH = kSePoolDepth;
+  const PrefetchRing<NV, DEPTH> ring(ring_smem);
   const int groups = C / 8;                 // power of two <= 256 (host-checked)
   const int cg = threadIdx.x % groups;
   const int pl = threadIdx.x / groups;
@@ -336,31 +352,33 @@ se_pool_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat1
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  constexpr int U = DOT ? 4 : 8;   // pixels in flight per thread (16 bytes per stream each)
-  for (long long pb = p0 + pl; pb < p1; pb += static_cast<long long>(ppi) * U) {
-    uint4 xr[U], yr[U];
+  auto fetch = [&](int stage, long long p) {
+    ring.fetch(stage, 0, x + (base + p) * x_cs + cg * 8);
+    if (DOT) ring.fetch(stage, 1, y + (base + p) * y_cs + cg * 8);
+  };
+  long long pnext = p0 + pl;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long p = pb + static_cast<long long>(u) * ppi;
-      const bool on = p < p1;
-      xr[u] = on ? ldg16(x + (base + p) * x_cs + cg * 8) : make_uint4(0, 0, 0, 0);
-      if (DOT) yr[u] = on ? ldg16(y + (base + p) * y_cs + cg * 8) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float v[8];
-      unpack8(xr[u], v);
-      if (DOT) {
-        float w8[8];
-        unpack8(yr[u], w8);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(v[k], w8[k], acc[k]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k];
-      }
-    }
+  for (int s = 0; s < DEPTH; ++s) {
+    if (pnext < p1) fetch(s, pnext);
+    cp_async_commit();
+    pnext += ppi;
   }
+  int stage = 0;
+  for (long long pcur = p0 + pl; pcur < p1; pcur += ppi) {
+    cp_async_wait<DEPTH - 1>();
+    float v[8], w8[8];
+    unpack8(ring.get(stage, 0), v);
+    if (DOT) unpack8(ring.get(stage, 1), w8);
+    if (pnext < p1) fetch(stage, pnext);     // the pixel is in registers: refill its slot
+    cp_async_commit();
+    pnext += ppi;
+    stage = stage + 1 == DEPTH ? 0 : stage + 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = DOT ? fmaf(v[k], w8[k], acc[k]) : acc[k] + v[k];
+  }
+  float* red = reinterpret_cast<float*>(ring_smem);
+  cp_async_wait<0>();
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
   __syncthreads();
@@ -654,8 +672,9 @@ extern "C" int b2s_channel_sums(const void* x, int x_cstride, float* partial, lo
   if (!x || !partial) return set_error(B2S_ERR_ARG, "b2s_channel_sums: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_channel_sums: unsupported C");
   count_launch();
-  channel_sums_kernel<<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), x_cstride, partial, npix, C);
+  constexpr int smem = PrefetchRing<1, kChannelSumsDepth>::kBytes;
+  channel_sums_kernel<<<kEwBlocks, kThreads, smem, STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_cstride,
+                                                                    partial, npix, C);
   return check_launch("channel_sums_kernel");
 }
 
@@ -685,13 +704,17 @@ extern "C" int b2s_se_pool(const void* x, int x_cstride, const void* y, int y_cs
   const int chunks = b2s_se_chunks(HW);
   dim3 grid(chunks, N);
   count_launch();
-  if (y)
-    se_pool_kernel<true><<<grid, kThreads, 0, STREAM(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride, partial,
-        HW, C, chunks);
-  else
-    se_pool_kernel<false><<<grid, kThreads, 0, STREAM(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), x_cstride, nullptr, 0, partial, HW, C, chunks);
+  constexpr int smem_dot = PrefetchRing<2, kSePoolDepth>::kBytes, smem_sum = PrefetchRing<1, kSePoolDepth>::kBytes;
+  if (y) {
+    ew_allow_smem(se_pool_kernel<true>, smem_dot);
+    se_pool_kernel<true><<<grid, kThreads, smem_dot, STREAM(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), x_cstride, static_cast<const __nv_bfloat16*>(y), y_cstride, partial, HW, C,
+        chunks);
+  } else {
+    ew_allow_smem(se_pool_kernel<false>, smem_sum);
+    se_pool_kernel<false><<<grid, kThreads, smem_sum, STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_cstride,
+                                                                        nullptr, 0, partial, HW, C, chunks);
+  }
   return check_launch("se_pool_kernel");
 }
 

@@ -229,7 +229,7 @@ class Conv1x1(torch.autograd.Function):
 
 class ConvS2(torch.autograd.Function):
     """nn.Conv2d(C, 2C, 3, stride=2, padding=1) (models/vnet.py:97). Forward and weight gradient read x through TMA
-    boxes with elementStrides = 2; the input gradient is four parity-class convolutions over dz."""
+    boxes over one pixel-parity class per tap; the input gradient is four parity-class convolutions over dz."""
 
     @staticmethod
     def forward(ctx, x, w, b):
@@ -252,7 +252,7 @@ class ConvS2(torch.autograd.Function):
         db = torch.empty(Cout, **f32)
         ops.channel_sums(dy, db)
         dw = torch.empty((Cout, Cin, 3, 3), **f32)
-        ops.conv3x3_s2_wgrad(xa, dy, dw)                 # x boxes with elementStrides = 2: no zero insertion
+        ops.conv3x3_s2_wgrad(xa, dy, dw)                 # x read as parity-class boxes: no zero insertion
         dx = None
         if ctx.needs_input_grad[0]:
             _, wd = packed_conv(w, True)
