@@ -170,7 +170,7 @@ def run_b200(args):
     from b200seg import _lib, ops
     from b200seg.models.model import UNet
     from b200seg.train import TrainStep
-    from oracle import unet_oracle as O   # synthetic-data generator only (shared with the tests)
+    from b200seg.synth import synth_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,7 +188,7 @@ def run_b200(args):
     torch.manual_seed(42)
     sd = UNet().state_dict()
     ts = TrainStep(sd, dev, lr=1e-5)
-    x_cpu, t_cpu = O.synth_batch(B, S, S, seed=1234 + rank)
+    x_cpu, t_cpu = synth_batch(B, S, S, seed=1234 + rank)
     x_pin, t_pin = x_cpu.pin_memory(), t_cpu.pin_memory()
     x_dev, t_dev = x_pin.to(dev, non_blocking=True), t_pin.to(dev, non_blocking=True)
     x_in, t_in = torch.empty_like(x_dev), torch.empty_like(t_dev)

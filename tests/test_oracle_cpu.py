@@ -167,3 +167,14 @@ def test_metrics_oracle_matches_reference_functions():
         got = MO.metrics((torch.sigmoid(c["logits"]) > 0.5).numpy(), c["targets"].numpy())
         for k in ("acc", "precision", "recall", "f1", "iou"):
             assert abs(got[k] - c[k]) < 1e-12, (name, k)
+
+
+def test_workload_generator_matches_the_oracles_copy():
+    """bench.py and the tools draw their synthetic frames from the package (b200seg.synth), the parity tests from the
+    oracle: both must be the same function of (shape, seed)"""
+    import b200seg  # noqa: F401
+    from b200seg.synth import synth_batch
+    for (B, H, W, seed) in [(2, 32, 32, 1234), (3, 48, 80, 7)]:
+        xa, ta = synth_batch(B, H, W, seed=seed)
+        xb, tb = O.synth_batch(B, H, W, seed=seed)
+        assert torch.equal(xa, xb) and torch.equal(ta, tb)

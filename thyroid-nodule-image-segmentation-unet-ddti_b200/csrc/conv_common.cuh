@@ -55,12 +55,12 @@ static inline EncodeTiledFn get_encode_fn() {
 // bf16 tensor map, SWIZZLE_128B, inner box = 64 elements. dims/strides innermost first; strides in BYTES for
 // dims 1..rank-1.
 static inline int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                     const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+                     const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(B2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = elem_strides ? elem_strides[i] : 1; }
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_b[i];
   if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(B2S_ERR_ARG, "tensor base not 16-B aligned");
   for (int i = 0; i + 1 < rank; ++i)

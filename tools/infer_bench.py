@@ -13,7 +13,7 @@ import torch
 import b200seg  # noqa
 from b200seg import _lib
 from b200seg.models.model import UNet
-from oracle import unet_oracle as O   # synthetic data generator only
+from b200seg.synth import synth_batch
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
@@ -28,7 +28,7 @@ with torch.no_grad():   # non-degenerate running statistics
     for m in net.modules():
         if isinstance(m, torch.nn.BatchNorm2d):
             m.running_mean.uniform_(0.0, 0.2); m.running_var.uniform_(0.5, 1.5)
-x_cpu, _ = O.synth_batch(args.chunk, args.size, args.size, seed=1234)
+x_cpu, _ = synth_batch(args.chunk, args.size, args.size, seed=1234)
 x_pin = x_cpu.pin_memory()
 x_dev = x_pin.to(dev)
 x_in = torch.empty_like(x_dev)

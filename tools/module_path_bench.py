@@ -7,13 +7,13 @@ import torch
 import b200seg  # noqa
 from b200seg.models.model import UNet
 from b200seg.models.loss import BCEDiceLoss
-from oracle import unet_oracle as O
+from b200seg.synth import synth_batch
 dev = "cuda"
 torch.manual_seed(42)
 net = UNet().to(dev).train()
 opt = torch.optim.AdamW(net.parameters(), lr=1e-5, fused=True)
 crit = BCEDiceLoss()
-x, t = O.synth_batch(64, 256, 256, seed=1234)
+x, t = synth_batch(64, 256, 256, seed=1234)
 x, t = x.to(dev), t.to(dev)
 def step():
     opt.zero_grad(set_to_none=True)

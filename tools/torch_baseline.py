@@ -16,7 +16,7 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import b200seg  # noqa: E402,F401
 from b200seg.models.model import UNet  # noqa: E402
-from oracle import unet_oracle as O  # noqa: E402
+from b200seg.synth import synth_batch
 
 
 def stock_forward(m, x):
@@ -40,7 +40,7 @@ def dice(logits, t):
 def run(variant, B, S, steps, warmup=3):
     torch.manual_seed(42)
     m = UNet().cuda().train()
-    x, t = O.synth_batch(B, S, S)
+    x, t = synth_batch(B, S, S)
     x, t = x.cuda(), t.cuda()
     if variant == "bf16_channels_last":
         m = m.to(memory_format=torch.channels_last)

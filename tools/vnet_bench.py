@@ -16,7 +16,7 @@ import b200seg  # noqa
 from b200seg import _lib
 from b200seg.models.vnet import ImprovedVNet
 from b200seg.models.loss import BCEDiceLoss
-from oracle import unet_oracle as O   # synthetic data generator only
+from b200seg.synth import synth_batch
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
@@ -36,7 +36,7 @@ net = ImprovedVNet(dropout_rate=args.dropout).to(dev).train()
 model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
 opt = torch.optim.AdamW(net.parameters(), lr=1e-5, fused=True, capturable=args.graph)
 crit = BCEDiceLoss()
-x, t = O.synth_batch(args.batch, args.size, args.size, seed=1234 + rank)
+x, t = synth_batch(args.batch, args.size, args.size, seed=1234 + rank)
 x, t = x.to(dev), t.to(dev)
 
 def step():
