@@ -391,36 +391,74 @@ se_pool_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const __nv_bfloat1
   }
 }
 
-// one block per sample: mean = pooled / HW; hidden = relu(W1 mean + b1); gate = sigmoid(W2 hidden + b2)
+// ---- the two tiny FC layers of the SE block ---------------------------------------------------------------------
+// One block per sample walking W1 and W2 (2 MB at C = 1024) through a single SM took 73 us per call; the three phases
+// are separate launches spread over the whole chip instead: chunk sums -> mean (or the gate gradient), then one warp
+// per output row (coalesced over the contraction index, shuffle reduction) for W v, and lanes over the output index
+// with the contraction split across the warps of a block for W^T v.
+
+// out[n][c] = (sum_k partial[n][k][c]) * mult, where mult = scale (gate == nullptr) or g (1 - g) with g = gate[n][c]
 __global__ void __launch_bounds__(kThreads)
-se_fc_fwd_kernel(const float* __restrict__ partial, int chunks, float inv_hw, const float* __restrict__ w1,
-                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                 float* __restrict__ mean_out, float* __restrict__ hidden_out, float* __restrict__ gate_out, int C,
-                 int Cr) {
-  extern __shared__ float sm[];   // mean [C], hidden [Cr]
-  float* mean = sm;
-  float* hid = sm + C;
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += kThreads) {
+se_chunk_sum_kernel(const float* __restrict__ partial, int chunks, int C, float scale, const float* __restrict__ gate,
+                    float* __restrict__ out) {
+  const int c = blockIdx.x * kThreads + threadIdx.x, n = blockIdx.y;
+  if (c >= C) return;
+  const float* src = partial + static_cast<size_t>(n) * chunks * C + c;
+  float s = 0.f;
+  int k = 0;
+  for (; k + 8 <= chunks; k += 8) {     // eight independent loads, added in chunk order
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(src + static_cast<size_t>(k + j) * C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; k < chunks; ++k) s += __ldg(src + static_cast<size_t>(k) * C);
+  float mult = scale;
+  if (gate) { const float g = gate[static_cast<size_t>(n) * C + c]; mult = g * (1.f - g); }
+  out[static_cast<size_t>(n) * C + c] = s * mult;
+}
+
+// out[n][r] = act(sum_k W[r][k] in[n][k] + bias[r]); W [R][K] row-major. One warp per (n, r). ACT 1: ReLU, 2: sigmoid.
+template <int ACT>
+__global__ void __launch_bounds__(kThreads)
+se_matvec_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ in,
+                 float* __restrict__ out, int R, int K) {
+  const int r = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5), n = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float* wr = W + static_cast<size_t>(r) * K;
+  const float* v = in + static_cast<size_t>(n) * K;
+  float a = 0.f;
+  for (int k = lane; k < K; k += 32) a = fmaf(__ldg(wr + k), __ldg(v + k), a);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+  if (lane == 0) {
+    a += bias[r];
+    out[static_cast<size_t>(n) * R + r] = ACT == 1 ? fmaxf(a, 0.f) : 1.f / (1.f + expf(-a));
+  }
+}
+
+// out[n][j] = mask(sum_k W[k][j] in[n][k]); W [K][J] row-major (the transposed product). Block = 32 output columns x 8
+// slices of k; mask_src != nullptr: zero where mask_src[n][j] <= 0 (gradient through the hidden layer's ReLU).
+__global__ void __launch_bounds__(kThreads)
+se_matvec_t_kernel(const float* __restrict__ W, const float* __restrict__ in, const float* __restrict__ mask_src,
+                   float* __restrict__ out, int K, int J) {
+  __shared__ float red[kThreads / 32][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane, n = blockIdx.y;
+  const float* v = in + static_cast<size_t>(n) * K;
+  float a = 0.f;
+  if (j < J)
+    for (int k = slice; k < K; k += kThreads / 32) a = fmaf(__ldg(W + static_cast<size_t>(k) * J + j), __ldg(v + k), a);
+  red[slice][lane] = a;
+  __syncthreads();
+  if (slice == 0 && j < J) {
     float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += partial[(static_cast<size_t>(n) * chunks + k) * C + c];
-    s *= inv_hw;
-    mean[c] = s;
-    mean_out[static_cast<size_t>(n) * C + c] = s;
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < Cr; j += kThreads) {
-    float a = b1[j];
-    for (int c = 0; c < C; ++c) a = fmaf(w1[static_cast<size_t>(j) * C + c], mean[c], a);
-    a = fmaxf(a, 0.f);
-    hid[j] = a;
-    hidden_out[static_cast<size_t>(n) * Cr + j] = a;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kThreads) {
-    float a = b2[c];
-    for (int j = 0; j < Cr; ++j) a = fmaf(w2[static_cast<size_t>(c) * Cr + j], hid[j], a);
-    gate_out[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-a));
+#pragma unroll
+    for (int t = 0; t < kThreads / 32; ++t) s += red[t][lane];
+    if (mask_src && !(mask_src[static_cast<size_t>(n) * J + j] > 0.f)) s = 0.f;
+    out[static_cast<size_t>(n) * J + j] = s;
   }
 }
 
@@ -467,39 +505,6 @@ se_scale_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, const float* __re
       }
       stg16(y + pixs[u] * y_cs + cgs[u] * 8, pack8(v));
     }
-  }
-}
-
-// one block per sample: dgate = sum partial; ds = dgate g (1-g); dh = (h>0) W2^T ds; dmean = W1^T dh
-__global__ void __launch_bounds__(kThreads)
-se_fc_bwd_kernel(const float* __restrict__ partial, int chunks, const float* __restrict__ gate,
-                 const float* __restrict__ hidden, const float* __restrict__ w1, const float* __restrict__ w2,
-                 float* __restrict__ ds_out, float* __restrict__ dh_out, float* __restrict__ dmean_out, int C, int Cr) {
-  extern __shared__ float sm[];   // ds [C], dh [Cr]
-  float* ds = sm;
-  float* dh = sm + C;
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += kThreads) {
-    float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += partial[(static_cast<size_t>(n) * chunks + k) * C + c];
-    const float g = gate[static_cast<size_t>(n) * C + c];
-    s *= g * (1.f - g);
-    ds[c] = s;
-    ds_out[static_cast<size_t>(n) * C + c] = s;
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < Cr; j += kThreads) {
-    float a = 0.f;
-    for (int c = 0; c < C; ++c) a = fmaf(w2[static_cast<size_t>(c) * Cr + j], ds[c], a);
-    a = hidden[static_cast<size_t>(n) * Cr + j] > 0.f ? a : 0.f;
-    dh[j] = a;
-    dh_out[static_cast<size_t>(n) * Cr + j] = a;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kThreads) {
-    float a = 0.f;
-    for (int j = 0; j < Cr; ++j) a = fmaf(w1[static_cast<size_t>(j) * C + c], dh[j], a);
-    dmean_out[static_cast<size_t>(n) * C + c] = a;
   }
 }
 
@@ -724,10 +729,16 @@ extern "C" int b2s_se_fc_fwd(const float* partial, int chunks, long long HW, con
   if (!partial || !w1 || !b1 || !w2 || !b2 || !mean || !hidden || !gate)
     return set_error(B2S_ERR_ARG, "b2s_se_fc_fwd: null pointer");
   if (C > 4096 || Cr < 1 || Cr > C) return set_error(B2S_ERR_ARG, "b2s_se_fc_fwd: unsupported channel counts");
+  // mean = pooled / HW; hidden = relu(W1 mean + b1); gate = sigmoid(W2 hidden + b2)      (models/vnet.py:20-25)
+  cudaStream_t st = STREAM(stream);
   count_launch();
-  se_fc_fwd_kernel<<<N, kThreads, (C + Cr) * sizeof(float), STREAM(stream)>>>(
-      partial, chunks, 1.f / static_cast<float>(HW), w1, b1, w2, b2, mean, hidden, gate, C, Cr);
-  return check_launch("se_fc_fwd_kernel");
+  se_chunk_sum_kernel<<<dim3((C + kThreads - 1) / kThreads, N), kThreads, 0, st>>>(
+      partial, chunks, C, 1.f / static_cast<float>(HW), nullptr, mean);
+  count_launch();
+  se_matvec_kernel<1><<<dim3((Cr + 7) / 8, N), kThreads, 0, st>>>(w1, b1, mean, hidden, Cr, C);
+  count_launch();
+  se_matvec_kernel<2><<<dim3((C + 7) / 8, N), kThreads, 0, st>>>(w2, b2, hidden, gate, C, Cr);
+  return check_launch("se_fc_fwd kernels");
 }
 
 extern "C" int b2s_se_scale(const void* x, int x_cstride, const float* gate, const float* add, float add_scale, void* y,
@@ -748,10 +759,15 @@ extern "C" int b2s_se_fc_bwd(const float* partial, int chunks, const float* gate
   if (!partial || !gate || !hidden || !mean || !w1 || !w2 || !ds || !dh || !dmean || !dw1 || !db1 || !dw2 || !db2)
     return set_error(B2S_ERR_ARG, "b2s_se_fc_bwd: null pointer");
   if (C > 4096 || Cr < 1 || Cr > C) return set_error(B2S_ERR_ARG, "b2s_se_fc_bwd: unsupported channel counts");
+  // ds = dgate g (1 - g) with dgate = the pooled dy * x;  dh = (h > 0) W2^T ds;  dmean = W1^T dh
+  cudaStream_t st = STREAM(stream);
   count_launch();
-  se_fc_bwd_kernel<<<N, kThreads, (C + Cr) * sizeof(float), STREAM(stream)>>>(
-      partial, chunks, gate, hidden, w1, w2, ds, dh, dmean, C, Cr);
-  int rc = check_launch("se_fc_bwd_kernel");
+  se_chunk_sum_kernel<<<dim3((C + kThreads - 1) / kThreads, N), kThreads, 0, st>>>(partial, chunks, C, 1.f, gate, ds);
+  count_launch();
+  se_matvec_t_kernel<<<dim3((Cr + 31) / 32, N), kThreads, 0, st>>>(w2, ds, hidden, dh, C, Cr);
+  count_launch();
+  se_matvec_t_kernel<<<dim3((C + 31) / 32, N), kThreads, 0, st>>>(w1, dh, nullptr, dmean, Cr, C);
+  int rc = check_launch("se_fc_bwd kernels");
   if (rc) return rc;
   // dW2 [C][Cr] = sum_n ds (x) hidden, db2 = sum_n ds;  dW1 [Cr][C] = sum_n dh (x) mean, db1 = sum_n dh
   count_launch();

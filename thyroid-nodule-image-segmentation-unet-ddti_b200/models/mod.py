@@ -105,7 +105,7 @@ class UNet(nn.Module, _PackMixin):
         x = self._run_block(self.bottleneck, x)
         for up, dec, skip in zip(self.upconvs, self.decoders, reversed(skips)):
             x = VF.ConvT2x2.apply(x, up.weight, up.bias)
-            x = VF.Cat.apply(skip, x)
+            x = VF.Cat.apply((True, False), skip, x)    # the skip also feeds the max-pool; the up-conv output only this
             x = self._run_block(dec, x)
         return VF.Head.apply(x, self.final_conv.weight, self.final_conv.bias)
 
@@ -173,6 +173,6 @@ class ResUNet(nn.Module, _PackMixin):
         x = self.bottleneck.forward_nhwc(x)
         for up, dec, skip in zip(self.upconvs, self.decoders, reversed(skips)):
             x = VF.ConvT2x2.apply(x, up.weight, up.bias)
-            x = VF.Cat.apply(skip, x)
+            x = VF.Cat.apply((True, False), skip, x)    # the skip also feeds the max-pool; the up-conv output only this
             x = dec.forward_nhwc(x)
         return VF.Head.apply(x, self.final_conv.weight, self.final_conv.bias)

@@ -184,10 +184,11 @@ class ImprovedVNet(nn.Module):
                 if i < 4:
                     dc = self.down_convs[b][i]
                     e = VF.ConvS2.apply(e, dc.weight, dc.bias)
-        d = VF.Cat.apply(*[feats[b][4] for b in range(nb)])
+        d = VF.Cat.apply((False,) * nb, *[feats[b][4] for b in range(nb)])     # bottleneck features: one consumer each
         for lvl, up, blk in ((3, self.up6, 0), (2, self.up7, 1), (1, self.up8, 2), (0, self.up9, 3)):
             d = VF.ConvT2x2.apply(d, up.weight, up.bias)
-            d = VF.Cat.apply(d, *[feats[b][lvl] for b in range(nb)])
+            # the up-conv output is consumed here only; the skips also feed their branch's down conv
+            d = VF.Cat.apply((False,) + (True,) * nb, d, *[feats[b][lvl] for b in range(nb)])
             d = self.dec_blocks[blk].forward_nhwc(d)
         return self.dec_se_final.forward_nhwc(d)
 

@@ -344,11 +344,16 @@ class MaxPool2x2(torch.autograd.Function):
 
 
 class Cat(torch.autograd.Function):
-    """torch.cat along channels (models/vnet.py:127-150) with the strided channel-slice copy kernel; backward hands
-    out channel-slice views of the incoming gradient (no copy)."""
+    """torch.cat along channels (models/vnet.py:127-150) with the strided channel-slice copy kernel.
+
+    Cat.apply(dense, *xs): dense[i] says how input i receives its gradient. False: as a channel-slice view of the
+    incoming gradient (no copy; every libb2s node reads slices in place). True: copied into a dense tensor with the
+    slice-copy kernel -- for inputs with further consumers (the skip tensors), because autograd summing a strided view
+    into a dense gradient goes through torch's non-vectorised elementwise kernel (310 us per add at 512^2, 4.7 % of the
+    V-Net step) instead of the 16-byte one. dense=None: all True."""
 
     @staticmethod
-    def forward(ctx, *xs):
+    def forward(ctx, dense, *xs):
         acts = [as_act(t) for t in xs]
         a0 = acts[0]
         Ct = sum(a.C for a in acts)
@@ -358,13 +363,22 @@ class Cat(torch.autograd.Function):
             ops.copy_channels(a, Act(out, o, a.C))
             o += a.C
         ctx.sizes = [a.C for a in acts]
+        ctx.dense = tuple(dense) if dense is not None else (True,) * len(xs)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        grads, o = [], 0
-        for c in ctx.sizes:
-            grads.append(dout[..., o:o + c])
+        da = as_act(dout)
+        grads, o = [None], 0
+        for i, c in enumerate(ctx.sizes):
+            if not ctx.needs_input_grad[i + 1]:
+                grads.append(None)
+            elif ctx.dense[i]:
+                g = new_act(da.N, da.H, da.W, c, dout.device)
+                ops.copy_channels(da.slice(o, c), Act(g))
+                grads.append(g)
+            else:
+                grads.append(dout[..., o:o + c])
             o += c
         return tuple(grads)
 
