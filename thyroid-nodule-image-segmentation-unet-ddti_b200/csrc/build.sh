@@ -13,5 +13,5 @@ for f in api conv_tc conv2_tc wgrad2_tc elementwise vnet_ops; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$out/libb2s.so" "$here/obj/api.o" "$here/obj/conv_tc.o" "$here/obj/conv2_tc.o" "$here/obj/wgrad2_tc.o" "$here/obj/elementwise.o" "$here/obj/vnet_ops.o" -cudart static
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/libb2s.so" "$here/obj/api.o" "$here/obj/conv_tc.o" "$here/obj/conv2_tc.o" "$here/obj/wgrad2_tc.o" "$here/obj/elementwise.o" "$here/obj/vnet_ops.o" -cudart static
 echo "built $out/libb2s.so"
