@@ -232,7 +232,6 @@ __device__ __forceinline__ void c1_load_window(const float* __restrict__ xi, int
   }
 }
 
-template <bool F2>   // F2: the 288 FMAs of a work item as 144 packed FFMA2 (bit-identical results)
 __global__ void __launch_bounds__(kThreads, 2)
 conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        __nv_bfloat16* __restrict__ r, float* __restrict__ stats_partial, int N, int H, int W, int Cout,
@@ -272,48 +271,31 @@ conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w,
       const float* xi = x + (p - wq - static_cast<unsigned>(hq) * W);  // image base
       float xv[3][6];
       c1_load_window(xi, hq, wq, H, W, xv);
+      // the 288 FMAs of the work item as 144 packed FFMA2 (one issue slot per channel pair; bit-identical to scalar
+      // FMAs: 244 -> 221 us at batch 64 @256^2, the kernel is instruction-issue bound)
       float acc[4][8];
-      if constexpr (F2) {
-        f32x2 acc2[4][4];
+      f32x2 acc2[4][4];
 #pragma unroll
-        for (int px = 0; px < 4; ++px)
+      for (int px = 0; px < 4; ++px)
 #pragma unroll
-          for (int kp = 0; kp < 4; ++kp) acc2[px][kp] = f2_pack(br[2 * kp], br[2 * kp + 1]);
+        for (int kp = 0; kp < 4; ++kp) acc2[px][kp] = f2_pack(br[2 * kp], br[2 * kp + 1]);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(&wsm[t * Cout + cg * 8]);      // channels 0..3
-          const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(&wsm[t * Cout + cg * 8 + 4]);  // channels 4..7
-          const f32x2 wp[4] = {w0.x, w0.y, w1.x, w1.y};
+      for (int t = 0; t < 9; ++t) {
+        const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(&wsm[t * Cout + cg * 8]);      // channels 0..3
+        const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(&wsm[t * Cout + cg * 8 + 4]);  // channels 4..7
+        const f32x2 wp[4] = {w0.x, w0.y, w1.x, w1.y};
 #pragma unroll
-          for (int px = 0; px < 4; ++px) {
-            const float v = xv[t / 3][px + t % 3];
-            const f32x2 vv = f2_pack(v, v);
+        for (int px = 0; px < 4; ++px) {
+          const float v = xv[t / 3][px + t % 3];
+          const f32x2 vv = f2_pack(v, v);
 #pragma unroll
-            for (int kp = 0; kp < 4; ++kp) acc2[px][kp] = f2_fma(vv, wp[kp], acc2[px][kp]);
-          }
-        }
-#pragma unroll
-        for (int px = 0; px < 4; ++px)
-#pragma unroll
-          for (int kp = 0; kp < 4; ++kp) f2_unpack(acc2[px][kp], acc[px][2 * kp], acc[px][2 * kp + 1]);
-      } else {
-#pragma unroll
-        for (int px = 0; px < 4; ++px)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[px][k] = br[k];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float4 w0 = *reinterpret_cast<const float4*>(&wsm[t * Cout + cg * 8]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&wsm[t * Cout + cg * 8 + 4]);
-          const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int px = 0; px < 4; ++px) {
-            const float v = xv[t / 3][px + t % 3];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[px][k] = fmaf(v, wk[k], acc[px][k]);
-          }
+          for (int kp = 0; kp < 4; ++kp) acc2[px][kp] = f2_fma(vv, wp[kp], acc2[px][kp]);
         }
       }
+#pragma unroll
+      for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int kp = 0; kp < 4; ++kp) f2_unpack(acc2[px][kp], acc[px][2 * kp], acc[px][2 * kp + 1]);
 #pragma unroll
       for (int px = 0; px < 4; ++px) {
 #pragma unroll
@@ -346,7 +328,6 @@ conv3x3_c1_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w,
   }
 }
 
-template <bool F2>
 __global__ void __launch_bounds__(kThreads)
 conv3x3_c1_wgrad4_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                          float* __restrict__ partial, int N, int H, int W, int Cout) {
@@ -355,15 +336,11 @@ conv3x3_c1_wgrad4_kernel(const float* __restrict__ x, const __nv_bfloat16* __res
   const int qpi = kThreads / groups;
   const int cg = threadIdx.x % groups;
   const int ql = threadIdx.x / groups;
-  float acc[9][8];
-  f32x2 acc2[9][4];    // F2: the same sums as packed pairs (k, k + 1)
+  f32x2 acc2[9][4];    // [tap][channel pair]: the weight-gradient sums as packed fp32 pairs
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int kp = 0; kp < 4; ++kp) acc2[t][kp] = 0ull;
-  }
   const unsigned nquads = static_cast<unsigned>(N) * H * W / 4;
   for (unsigned q0 = blockIdx.x * qpi; q0 < nquads; q0 += gridDim.x * qpi) {
     const unsigned qd = q0 + ql;
@@ -382,32 +359,22 @@ conv3x3_c1_wgrad4_kernel(const float* __restrict__ x, const __nv_bfloat16* __res
       for (int px = 0; px < 4; ++px) {
         float g[8];
         unpack8(graw[px], g);
-        if constexpr (F2) {
-          const f32x2 g2[4] = {f2_pack(g[0], g[1]), f2_pack(g[2], g[3]), f2_pack(g[4], g[5]), f2_pack(g[6], g[7])};
+        const f32x2 g2[4] = {f2_pack(g[0], g[1]), f2_pack(g[2], g[3]), f2_pack(g[4], g[5]), f2_pack(g[6], g[7])};
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const float v = xv[t / 3][px + t % 3];
-            const f32x2 vv = f2_pack(v, v);
+        for (int t = 0; t < 9; ++t) {
+          const float v = xv[t / 3][px + t % 3];
+          const f32x2 vv = f2_pack(v, v);
 #pragma unroll
-            for (int kp = 0; kp < 4; ++kp) acc2[t][kp] = f2_fma(vv, g2[kp], acc2[t][kp]);
-          }
-        } else {
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const float v = xv[t / 3][px + t % 3];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(v, g[k], acc[t][k]);
-          }
+          for (int kp = 0; kp < 4; ++kp) acc2[t][kp] = f2_fma(vv, g2[kp], acc2[t][kp]);   // FFMA2: 190 -> 162 us
         }
       }
     }
   }
-  if constexpr (F2) {
+  float acc[9][8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int kp = 0; kp < 4; ++kp) f2_unpack(acc2[t][kp], acc[t][2 * kp], acc[t][2 * kp + 1]);
-  }
+    for (int kp = 0; kp < 4; ++kp) f2_unpack(acc2[t][kp], acc[t][2 * kp], acc[t][2 * kp + 1]);
   float* row = partial + static_cast<size_t>(blockIdx.x) * Cout * 9;
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
@@ -1327,12 +1294,6 @@ extern "C" int b2s_c1_rows(int N, int H, int W) {
   return grid_for(npix, 32 * 16);
 }
 
-// A/B switch of the packed-FMA variants of the Cin = 1 kernels (B2S_C1_FFMA2=0: scalar FMAs)
-static bool c1_use_ffma2() {
-  static const bool on = [] { const char* e = getenv("B2S_C1_FFMA2"); return !(e && e[0] == '0'); }();
-  return on;
-}
-
 static int c1_fwd_impl(const float* x, const float* w, const float* bias, const float* post_scale,
                        const float* post_shift, void* r, float* stats_partial, int N, int H, int W, int Cout, int flags,
                        void* stream) {
@@ -1343,8 +1304,7 @@ static int c1_fwd_impl(const float* x, const float* w, const float* bias, const 
   const int grid = b2s_c1_rows(N, H, W);
   count_launch();
   auto kfn = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
-                 ? (c1_use_ffma2() ? conv3x3_c1_fwd4_kernel<true> : conv3x3_c1_fwd4_kernel<false>)
-                 : conv3x3_c1_fwd_kernel;
+                 ? conv3x3_c1_fwd4_kernel : conv3x3_c1_fwd_kernel;
   kfn<<<grid, kThreads, 0, STREAM(stream)>>>(x, w, bias, static_cast<__nv_bfloat16*>(r),
                                              (flags & B2S_FLAG_STATS) ? stats_partial : nullptr, N, H, W, Cout, flags,
                                              post_scale, post_shift);
@@ -1371,8 +1331,7 @@ extern "C" int b2s_conv3x3_c1_wgrad(const float* x, const void* dz, float* parti
   const int grid = b2s_c1_rows(N, H, W);
   count_launch();
   auto kfn = (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
-                 ? (c1_use_ffma2() ? conv3x3_c1_wgrad4_kernel<true> : conv3x3_c1_wgrad4_kernel<false>)
-                 : conv3x3_c1_wgrad_kernel;
+                 ? conv3x3_c1_wgrad4_kernel : conv3x3_c1_wgrad_kernel;
   kfn<<<grid, kThreads, 0, STREAM(stream)>>>(x, static_cast<const __nv_bfloat16*>(dz), partial, N, H, W, Cout);
   return check_launch("conv3x3_c1_wgrad_kernel");
 }

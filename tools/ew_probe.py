@@ -11,7 +11,7 @@ from b200seg import ops, _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--size", type=int, default=512)
-ap.add_argument("--c1", action="store_true", help="time the Cin = 1 first-conv kernels instead (B2S_C1_FFMA2=0/1 for the A/B)")
+ap.add_argument("--c1", action="store_true", help="time the Cin = 1 first-conv kernels instead")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -30,7 +30,6 @@ def timed(fn, reps=5):
 
 
 if args.c1:
-    import os
     for (N, S) in ((64, 256), (16, 512)):
         x = torch.rand((N, 1, S, S), device=dev)
         w, b = torch.randn((64, 1, 3, 3), device=dev) * 0.3, torch.randn(64, device=dev) * 0.1
@@ -41,7 +40,7 @@ if args.c1:
         dw = torch.empty((64, 1, 3, 3), dtype=torch.float32, device=dev)
         tf = timed(lambda: ops.conv3x3_c1_fwd(x, w, b, r, relu=True, stats=stats))
         tw = timed(lambda: L.b2s_conv3x3_c1_wgrad(ops._p(x), r.ptr, ops._p(partial), N, S, S, 64, ops._stream()))
-        print(json.dumps({"ffma2": os.environ.get("B2S_C1_FFMA2", "1"), "shape": [N, 1, S, S], "c1_fwd_us": round(tf * 1e3, 1),
+        print(json.dumps({"shape": [N, 1, S, S], "c1_fwd_us": round(tf * 1e3, 1),
                           "c1_wgrad_us": round(tw * 1e3, 1), "checksum": float(r.buf.float().sum())}), flush=True)
     sys.exit(0)
 
