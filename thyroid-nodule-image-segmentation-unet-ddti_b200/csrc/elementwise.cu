@@ -693,6 +693,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ro
 // head: folded BN + 1x1 conv (+ threshold); backward
 // ------------------------------------------------------------------------------------------------
 // 8 lanes cooperate on one pixel (C == 64): lane j holds channels 8j..8j+7.
+template <bool O1>   // O1: one output channel (the reference's UNet(out_channels=1)): weights in registers, logits[p]
 __global__ void __launch_bounds__(kThreads)
 head_fwd_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __restrict__ scale,
                 const float* __restrict__ shift, const float* __restrict__ w, const float* __restrict__ b,
@@ -714,6 +715,12 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __re
   const long long npix = static_cast<long long>(N) * HW;
   const long long ppi = kThreads / groups;
   constexpr int U = 4;       // pixels per lane group and loop trip: four independent 16-byte loads in flight
+  float wr[8], fb = 0.f;
+  if constexpr (O1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[k] = wf[cg * 8 + k];
+    fb = wf[C];
+  }
   for (long long p0 = static_cast<long long>(blockIdx.x) * ppi * U; p0 < npix;
        p0 += static_cast<long long>(gridDim.x) * ppi * U) {
     uint4 raw[U];
@@ -727,23 +734,36 @@ head_fwd_kernel(const __nv_bfloat16* __restrict__ r, int r_cs, const float* __re
       const long long p = p0 + u * ppi + threadIdx.x / groups;
       float v[8];
       unpack8(raw[u], v);
-      for (int o = 0; o < O; ++o) {
+      if constexpr (O1) {      // same FMA chain and lane reduction as the general path; no shared-memory reads, no division
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc = fmaf(v[k], wf[o * C + cg * 8 + k], acc);
+        for (int k = 0; k < 8; ++k) acc = fmaf(v[k], wr[k], acc);
         for (int off = groups >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         if (cg == 0 && p < npix) {
-          const float logit = acc + wf[O * C + o];
-          const long long n = static_cast<unsigned>(p) / static_cast<unsigned>(HW), hw = p - n * HW;
-          const long long oi = (n * O + o) * HW + hw;
-          logits[oi] = logit;
-          if (mask) mask[oi] = (1.f / (1.f + expf(-logit))) > 0.5f ? 1 : 0;
+          const float logit = acc + fb;
+          logits[p] = logit;
+          if (mask) mask[p] = (1.f / (1.f + expf(-logit))) > 0.5f ? 1 : 0;
+        }
+      } else {
+        for (int o = 0; o < O; ++o) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc = fmaf(v[k], wf[o * C + cg * 8 + k], acc);
+          for (int off = groups >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          if (cg == 0 && p < npix) {
+            const float logit = acc + wf[O * C + o];
+            const long long n = static_cast<unsigned>(p) / static_cast<unsigned>(HW), hw = p - n * HW;
+            const long long oi = (n * O + o) * HW + hw;
+            logits[oi] = logit;
+            if (mask) mask[oi] = (1.f / (1.f + expf(-logit))) > 0.5f ? 1 : 0;
+          }
         }
       }
     }
   }
 }
 
+template <bool O1>   // O1: one output channel: weights in registers, dlogits[p], two pixels in flight per thread
 __global__ void __launch_bounds__(kThreads)
 head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ r, int r_cs,
                 const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ w,
@@ -767,27 +787,60 @@ head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restri
     float acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.f;
-    for (long long p0 = static_cast<long long>(blockIdx.x) * ppi; p0 < npix;
-         p0 += static_cast<long long>(gridDim.x) * ppi) {
-      const long long p = p0 + threadIdx.x / groups;
-      if (p < npix) {
-        const long long n = static_cast<unsigned>(p) / static_cast<unsigned>(HW), hw = p - n * HW;
-        const float g = dlogits[(n * O + o) * HW + hw];
-        float v[8];
-        unpack8(ldg16(r + p * r_cs + cg * 8), v);
+    if constexpr (O1) {
+      float wr[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(g, bf16_round(fmaf(v[k], sc[k], sh[k])), acc[k]);
-        if (cg == 0) acc[8] += g;
-        if (o == O - 1) {
-          float d[8];
+      for (int k = 0; k < 8; ++k) wr[k] = w[cg * 8 + k];
+      constexpr int U = 2;
+      const long long step = static_cast<long long>(gridDim.x) * ppi;
+      for (long long p0 = static_cast<long long>(blockIdx.x) * ppi + threadIdx.x / groups; p0 < npix; p0 += step * U) {
+        uint4 raw[U];
+        float g[U];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) d[k] = 0.f;
-          for (int oo = 0; oo < O; ++oo) {
-            const float go = dlogits[(n * O + oo) * HW + hw];
+        for (int u = 0; u < U; ++u) {
+          const long long p = p0 + u * step;
+          const bool on = p < npix;
+          raw[u] = on ? ldg16(r + p * r_cs + cg * 8) : make_uint4(0, 0, 0, 0);
+          g[u] = on ? __ldg(dlogits + p) : 0.f;
+        }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) d[k] = fmaf(go, w[oo * C + cg * 8 + k], d[k]);
+        for (int u = 0; u < U; ++u) {
+          const long long p = p0 + u * step;
+          if (p >= npix) break;
+          float v[8], d[8];
+          unpack8(raw[u], v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            acc[k] = fmaf(g[u], bf16_round(fmaf(v[k], sc[k], sh[k])), acc[k]);
+            d[k] = g[u] * wr[k];
           }
+          if (cg == 0) acc[8] += g[u];
           stg16(dy + p * dy_cs + cg * 8, pack8(d));
+        }
+      }
+    } else {
+      for (long long p0 = static_cast<long long>(blockIdx.x) * ppi; p0 < npix;
+           p0 += static_cast<long long>(gridDim.x) * ppi) {
+        const long long p = p0 + threadIdx.x / groups;
+        if (p < npix) {
+          const long long n = static_cast<unsigned>(p) / static_cast<unsigned>(HW), hw = p - n * HW;
+          const float g = dlogits[(n * O + o) * HW + hw];
+          float v[8];
+          unpack8(ldg16(r + p * r_cs + cg * 8), v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(g, bf16_round(fmaf(v[k], sc[k], sh[k])), acc[k]);
+          if (cg == 0) acc[8] += g;
+          if (o == O - 1) {
+            float d[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) d[k] = 0.f;
+            for (int oo = 0; oo < O; ++oo) {
+              const float go = dlogits[(n * O + oo) * HW + hw];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) d[k] = fmaf(go, w[oo * C + cg * 8 + k], d[k]);
+            }
+            stg16(dy + p * dy_cs + cg * 8, pack8(d));
+          }
         }
       }
     }
@@ -1489,7 +1542,8 @@ extern "C" int b2s_head_fwd(const void* r, int r_cstride, const float* scale, co
   const long long npix = static_cast<long long>(N) * HW;
   const int ppi = kThreads / (C / 8);
   count_launch();
-  head_fwd_kernel<<<grid_for(npix, ppi * 16), kThreads, (O * C + O) * sizeof(float), STREAM(stream)>>>(
+  auto kfn = O == 1 ? head_fwd_kernel<true> : head_fwd_kernel<false>;
+  kfn<<<grid_for(npix, ppi * 16), kThreads, (O * C + O) * sizeof(float), STREAM(stream)>>>(
       static_cast<const __nv_bfloat16*>(r), r_cstride, scale, shift, w, b, logits, mask, N, HW, C, O);
   return check_launch("head_fwd_kernel");
 }
@@ -1502,9 +1556,9 @@ extern "C" int b2s_head_bwd(const float* dlogits, const void* r, int r_cstride, 
   if (O < 1 || O > 64) return set_error(B2S_ERR_ARG, "b2s_head_bwd: unsupported out_channels");
   if (static_cast<long long>(N) * HW >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_head_bwd: N*H*W >= 2^31");
   count_launch();
-  head_bwd_kernel<<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(dlogits, static_cast<const __nv_bfloat16*>(r), r_cstride,
-                                                             scale, shift, w, static_cast<__nv_bfloat16*>(dy),
-                                                             dy_cstride, partial, N, HW, C, O);
+  auto kfn = O == 1 ? head_bwd_kernel<true> : head_bwd_kernel<false>;
+  kfn<<<kEwBlocks, kThreads, 0, STREAM(stream)>>>(dlogits, static_cast<const __nv_bfloat16*>(r), r_cstride, scale, shift, w,
+                                                  static_cast<__nv_bfloat16*>(dy), dy_cstride, partial, N, HW, C, O);
   return check_launch("head_bwd_kernel");
 }
 
