@@ -1172,61 +1172,66 @@ pack_all_kernel(const __grid_constant__ PackTable tab) {
   }
 }
 
-// ws [splits][taps][Cin][Cout] -> layout 0: dw[co][ci][t]; layout 1: dw[ci][co][t].
+// ws [splits][TAPS][Cin][Cout] -> layout 0: dw[co][ci][t]; layout 1: dw[ci][co][t].
 // Block = 8 warps x (32 lanes = 128 co as float4). The warps are split into (8/sgroups) input channels x sgroups
 // split groups, so that shallow layers (tiny K, many K-splits) and deep layers (huge K, 1-2 splits) both stream with
-// `taps` independent float4 loads in flight per thread.
+// TAPS independent float4 loads in flight per thread. TAPS and sgroups are compile-time / powers of two: the index
+// arithmetic of the transposing write-out was two runtime divisions per element and made the kernel instruction-bound
+// (1024 -> 1024, one split: 47 us for 75 MB).
+template <int TAPS>
 __global__ void __launch_bounds__(kThreads)
-wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int Cin, int Cout, float* __restrict__ dw,
-                    int layout, int sgroups) {
-  __shared__ float tile[9][8][129];
+wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int Cin, int Cout, float* __restrict__ dw, int layout,
+                    int sgroups) {
+  __shared__ float tile[TAPS][8][129];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int cpb = 8 / sgroups;                       // input channels per block
-  const int cil = ty / sgroups, sg = ty - cil * sgroups;
+  const int sshift = __ffs(sgroups) - 1;             // sgroups in {1, 2, 4, 8}
+  const int cpb = 8 >> sshift;                       // input channels per block
+  const int cil = ty >> sshift, sg = ty & (sgroups - 1);
   const int ci0 = blockIdx.x * cpb, co0 = blockIdx.y * 128;
   const int ci = ci0 + cil, co = co0 + tx * 4;
   const size_t tap_stride = static_cast<size_t>(Cin) * Cout;
-  const size_t split_stride = static_cast<size_t>(taps) * tap_stride;
-  float4 acc[9];
+  const size_t split_stride = static_cast<size_t>(TAPS) * tap_stride;
+  float4 acc[TAPS];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < TAPS; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ci < Cin && co < Cout) {
     const float* base = ws + static_cast<size_t>(ci) * Cout + co;
     for (int sp = sg; sp < splits; sp += sgroups) {
+      float4 v[TAPS];
 #pragma unroll
-      for (int t = 0; t < 9; ++t)
-        if (t < taps) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(base + sp * split_stride + t * tap_stride));
-          acc[t].x += v.x; acc[t].y += v.y; acc[t].z += v.z; acc[t].w += v.w;
-        }
+      for (int t = 0; t < TAPS; ++t) v[t] = __ldg(reinterpret_cast<const float4*>(base + sp * split_stride + t * tap_stride));
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) { acc[t].x += v[t].x; acc[t].y += v[t].y; acc[t].z += v[t].z; acc[t].w += v[t].w; }
     }
   }
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
+  for (int t = 0; t < TAPS; ++t) {
     tile[t][ty][tx * 4 + 0] = acc[t].x; tile[t][ty][tx * 4 + 1] = acc[t].y;
     tile[t][ty][tx * 4 + 2] = acc[t].z; tile[t][ty][tx * 4 + 3] = acc[t].w;
   }
   __syncthreads();
   const int nci = min(cpb, Cin - ci0), nco = min(128, Cout - co0);
+  const int cshift = 3 - sshift;                     // log2(cpb)
+  // e enumerates (outer, c, t) with t fastest: outer = output channel (layout 0) or nothing (layout 1, see below)
   if (layout == 0) {
-    // dw[co][ci0 .. ci0+nci)[t]: nci*taps contiguous floats per output channel; thread <-> (col, i)
-    const int run = nci * taps;
-    for (int e = threadIdx.x; e < nco * run; e += kThreads) {
-      const int col = e / run, i = e - col * run;
-      const int c = i / taps, t = i - c * taps;
+    // dw[co][ci0 .. ci0+nci)[t]: nci*TAPS contiguous floats per output channel; thread <-> (col, c, t)
+    for (int e = threadIdx.x; e < (nco * TAPS) << cshift; e += kThreads) {
+      const int ct = e / TAPS, t = e - ct * TAPS;     // division by a constant
+      const int col = ct >> cshift, c = ct & (cpb - 1);
+      if (c >= nci) continue;
       float v = 0.f;
-      for (int g = 0; g < sgroups; ++g) v += tile[t][c * sgroups + g][col];
-      dw[(static_cast<size_t>(co0 + col) * Cin + ci0) * taps + i] = v;
+      for (int g = 0; g < sgroups; ++g) v += tile[t][(c << sshift) + g][col];
+      dw[(static_cast<size_t>(co0 + col) * Cin + ci0 + c) * TAPS + t] = v;
     }
   } else {
-    // dw[ci][co0 .. co0+nco)[t]: nco*taps contiguous floats per input channel
-    const int run = nco * taps;
-    for (int e = threadIdx.x; e < nci * run; e += kThreads) {
-      const int c = e / run, i = e - c * run;
-      const int col = i / taps, t = i - col * taps;
+    // dw[ci][co0 .. co0+nco)[t]: nco*TAPS contiguous floats per input channel; thread <-> (c, col, t)
+    for (int e = threadIdx.x; e < nci * 128 * TAPS; e += kThreads) {
+      const int cc = e / TAPS, t = e - cc * TAPS;
+      const int c = cc >> 7, col = cc & 127;
+      if (col >= nco) continue;
       float v = 0.f;
-      for (int g = 0; g < sgroups; ++g) v += tile[t][c * sgroups + g][col];
-      dw[(static_cast<size_t>(ci0 + c) * Cout + co0) * taps + i] = v;
+      for (int g = 0; g < sgroups; ++g) v += tile[t][(c << sshift) + g][col];
+      dw[(static_cast<size_t>(ci0 + c) * Cout + co0 + col) * TAPS + t] = v;
     }
   }
 }
@@ -1669,7 +1674,12 @@ extern "C" int b2s_wgrad_reduce(const float* ws, int splits, int taps, int Cin, 
   const int cpb = 8 / sgroups;
   dim3 grid((Cin + cpb - 1) / cpb, (Cout + 127) / 128);
   count_launch();
-  wgrad_reduce_kernel<<<grid, kThreads, 0, STREAM(stream)>>>(ws, splits, taps, Cin, Cout, dw, layout, sgroups);
+  switch (taps) {
+    case 9: wgrad_reduce_kernel<9><<<grid, kThreads, 0, STREAM(stream)>>>(ws, splits, Cin, Cout, dw, layout, sgroups); break;
+    case 4: wgrad_reduce_kernel<4><<<grid, kThreads, 0, STREAM(stream)>>>(ws, splits, Cin, Cout, dw, layout, sgroups); break;
+    case 1: wgrad_reduce_kernel<1><<<grid, kThreads, 0, STREAM(stream)>>>(ws, splits, Cin, Cout, dw, layout, sgroups); break;
+    default: return set_error(B2S_ERR_ARG, "b2s_wgrad_reduce: taps must be 9 (3x3), 4 (transposed 2x2) or 1 (1x1)");
+  }
   return check_launch("wgrad_reduce_kernel");
 }
 
