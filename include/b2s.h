@@ -67,7 +67,7 @@ int b2s_conv3x3_wgrad(const void* x, int x_cstride, const void* dz, int dz_cstri
                       int Cin, int Cout, int tile_n, int splits, void* stream);
 int b2s_convt2x2_wgrad(const void* x, int x_cstride, const void* dy, int dy_cstride, float* ws, int N, int Hi, int Wi,
                        int Cin, int Cout, int tile_n, int splits, void* stream);
-/* layout 0: dw[co][ci][tap] (Conv2d OIHW); layout 1: dw[ci][co][tap] (ConvTranspose2d IOHW). */
+/* layout 0: dw[co][ci][tap] (Conv2d OIHW); layout 1: dw[ci][co][tap] (ConvTranspose2d IOHW). taps: 9, 4 or 1. */
 int b2s_wgrad_reduce(const float* ws, int splits, int taps, int Cin, int Cout, float* dw, int layout, void* stream);
 
 /* ---- weight packing (fp32 parameters -> bf16 GEMM operands) ---------------------------------------------------- */
