@@ -174,5 +174,15 @@ def test_host_side_planners_over_many_shapes():
                         assert nb4 == s.value * 4 * cin * C * 4 and s.value >= 1
                     forced_splits = L.b2s_conv_wgrad_workspace(N, H, W, cin, C, 3, LEGACY, 3, ctypes.byref(s))
                     assert forced_splits > 0 and 1 <= s.value <= 3
-    assert L.b2s_se_chunks(512 * 512) >= 1 and L.b2s_metrics_blocks(1) == 1 and L.b2s_loss_chunks(65536) >= 1
+    assert L.b2s_metrics_blocks(1) == 1 and L.b2s_loss_chunks(65536) >= 1
+    # SE pooling chunks: every pixel covered, between 4 and 64 blocks per sample at the V-Net levels (enough blocks at
+    # 32^2, no more than 64 partial rows for the FC kernels to sum at 512^2), never decreasing with the image size
+    prev = 0
+    for side in (1, 2, 7, 8, 16, 32, 64, 100, 128, 256, 512, 1024):
+        hw = side * side
+        c = L.b2s_se_chunks(hw)
+        assert c >= 1 and c * 4096 >= hw and c >= prev, (side, c)
+        if 32 <= side <= 512 and side & (side - 1) == 0:
+            assert 4 <= c <= 64, (side, c)
+        prev = c
     assert L.b2s_c1_rows(64, 256, 256) % 148 == 0
