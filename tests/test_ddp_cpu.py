@@ -186,3 +186,22 @@ def test_host_side_planners_over_many_shapes():
             assert 4 <= c <= 64, (side, c)
         prev = c
     assert L.b2s_c1_rows(64, 256, 256) % 148 == 0
+
+
+def test_library_is_sm100a_only_and_uses_the_blackwell_units():
+    """the shipped libb2s.so holds sm_100a cubins only, and its SASS carries the instructions the design rests on:
+    tcgen05 MMA / commit / TMEM loads (UTCHMMA, UTCBAR, LDTM), TMA loads and stores (UTMALDG, UTMASTG), the async
+    global->shared copies of the prefetch ring (LDGSTS) and packed fp32 FMAs (FFMA2). Needs cuobjdump (CUDA toolkit)."""
+    import re
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elfs = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.cubin", elfs))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    for mnemonic in ("UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "LDGSTS", "FFMA2"):
+        assert re.search(r"\b" + mnemonic + r"\b", sass), f"{mnemonic} missing from the SASS of libb2s.so"
+    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync tensor-core instructions in libb2s.so"
