@@ -1466,6 +1466,7 @@ extern "C" int b2s_bn_bwd_reduce(const void* dy, int dy_cstride, const void* dpo
                                  float* partial, int N, int H, int W, int C, void* stream) {
   if (!dy || !r || !mean || !invstd || !partial) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: null pointer");
   if (!ew_channels_ok(C)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: unsupported C");
+  if (dy_cstride % 8 || r_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: strides must be multiples of 8");
   if (dpool && (!scale || !shift || H % 2 || W % 2)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: pool args");
   if (static_cast<long long>(N) * H * W >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_reduce: N*H*W >= 2^31");
   const auto* dyp = static_cast<const __nv_bfloat16*>(dy);
@@ -1511,6 +1512,8 @@ extern "C" int b2s_bn_bwd_apply(const void* dy, int dy_cstride, const void* dpoo
   if (!dy || !r || !mean || !invstd || !coef || !dz || !dbias_partial)
     return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: null pointer");
   if (!ew_channels_ok(C)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: unsupported C");
+  if (dy_cstride % 8 || r_cstride % 8 || dz_cstride % 8)
+    return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: strides must be multiples of 8");
   if (dpool && (!scale || !shift || H % 2 || W % 2)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: pool args");
   if (static_cast<long long>(N) * H * W >= (1ll << 31)) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_apply: N*H*W >= 2^31");
   const auto* dyp = static_cast<const __nv_bfloat16*>(dy);

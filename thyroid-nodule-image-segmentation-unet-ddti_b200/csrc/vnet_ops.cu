@@ -625,6 +625,7 @@ extern "C" int b2s_bn_act_bwd_reduce(const void* da, int da_cstride, const void*
   if (!da || !z || !scale || !shift || !mean || !invstd || !partial)
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: unsupported C");
+  if (da_cstride % 8 || z_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_reduce: strides must be multiples of 8");
   count_launch();
   const uint32_t thresh = drop_threshold(dropout_p);
   launch_bn_act_bwd<false>(relu == 1, thresh != 0, STREAM(stream), static_cast<const __nv_bfloat16*>(da), da_cstride,
@@ -640,6 +641,8 @@ extern "C" int b2s_bn_act_bwd_apply(const void* da, int da_cstride, const void* 
   if (!da || !z || !scale || !shift || !mean || !invstd || !coef || !dz || !dbias_partial)
     return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: unsupported C");
+  if (da_cstride % 8 || z_cstride % 8 || dz_cstride % 8)
+    return set_error(B2S_ERR_ARG, "b2s_bn_act_bwd_apply: strides must be multiples of 8");
   count_launch();
   const uint32_t thresh = drop_threshold(dropout_p);
   launch_bn_act_bwd<true>(relu == 1, thresh != 0, STREAM(stream), static_cast<const __nv_bfloat16*>(da), da_cstride,
@@ -676,6 +679,7 @@ extern "C" int b2s_maxpool2x2_bwd(const void* x, int x_cstride, const void* dpoo
 extern "C" int b2s_channel_sums(const void* x, int x_cstride, float* partial, long long npix, int C, void* stream) {
   if (!x || !partial) return set_error(B2S_ERR_ARG, "b2s_channel_sums: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_channel_sums: unsupported C");
+  if (x_cstride % 8) return set_error(B2S_ERR_ARG, "b2s_channel_sums: stride must be a multiple of 8");
   count_launch();
   constexpr int smem = PrefetchRing<1, kChannelSumsDepth>::kBytes;
   channel_sums_kernel<<<kEwBlocks, kThreads, smem, STREAM(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_cstride,
@@ -705,6 +709,7 @@ extern "C" int b2s_se_pool(const void* x, int x_cstride, const void* y, int y_cs
                            long long HW, int C, void* stream) {
   if (!x || !partial) return set_error(B2S_ERR_ARG, "b2s_se_pool: null pointer");
   if (!ew_channels_supported(C)) return set_error(B2S_ERR_ARG, "b2s_se_pool: unsupported C");
+  if (x_cstride % 8 || (y && y_cstride % 8)) return set_error(B2S_ERR_ARG, "b2s_se_pool: strides must be multiples of 8");
   if (N <= 0 || N > 65535) return set_error(B2S_ERR_ARG, "b2s_se_pool: bad batch");
   const int chunks = b2s_se_chunks(HW);
   dim3 grid(chunks, N);
