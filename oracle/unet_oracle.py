@@ -24,6 +24,9 @@ Call sites restated (reference file:line):
   bce with logits        utils/trainer.py:37,85          (mean over all elements)
   threshold              utils/trainer.py:101,152,217    (sigmoid(logits) > 0.5 in the logits dtype)
 
+Every function is device-agnostic elementary tensor algebra: the GPU tests run the SAME restatement in fp64 on the
+device for the BASELINE-sized cases (4 x 256^2), where the CPU would need minutes.
+
 `q` (quantiser) emulates the CUDA path's storage precision: q = bf16_round reproduces every point where the
 B200 kernels round an activation / gradient / weight operand to bf16; q = identity is the exact-arithmetic oracle.
 """
@@ -99,7 +102,7 @@ def conv_transpose2x2(x, w, b=None):
     """nn.ConvTranspose2d(k=2,s=2) (models/model.py:19): out[n,o,2i+a,2j+b] = sum_c x[n,c,i,j] w[c,o,a,b] + bias."""
     N, C, H, W = x.shape
     O = w.shape[1]
-    out = torch.zeros((N, O, 2 * H, 2 * W), dtype=x.dtype)
+    out = torch.zeros((N, O, 2 * H, 2 * W), dtype=x.dtype, device=x.device)
     for a in range(2):
         for bb in range(2):
             out[:, :, a::2, bb::2] = torch.einsum("nchw,co->nohw", x, w[:, :, a, bb])
@@ -157,7 +160,7 @@ def maxpool2x2(y):
 
 
 def maxpool2x2_bwd(dpool, arg, shape):
-    dy = torch.zeros(shape, dtype=dpool.dtype)
+    dy = torch.zeros(shape, dtype=dpool.dtype, device=dpool.device)
     for qi in range(4):
         dy[:, :, (qi >> 1)::2, (qi & 1)::2] = torch.where(arg == qi, dpool, torch.zeros_like(dpool))
     return dy
@@ -206,7 +209,7 @@ def seg_loss(logits, targets, w_bce=1.0, w_dice=1.0, w_ft=0.0, dice_smooth=1.0, 
     g = g + w_dice * (-(1.0 / B)) * (2.0 * td * den - (2.0 * I + dice_smooth).unsqueeze(1)) / (den * den) * dp
     if w_ft != 0.0:
         dti = (t * D - (TP + ft_smooth) * (t + ft_alpha * (1 - t) - ft_beta * t)) / (D * D)
-        dL_dti = -ft_gamma * (1 - ti) ** (ft_gamma - 1.0) if float(1 - ti) > 0 else torch.zeros(())
+        dL_dti = -ft_gamma * (1 - ti) ** (ft_gamma - 1.0) if float(1 - ti) > 0 else torch.zeros((), dtype=x.dtype, device=x.device)
         g = g + w_ft * dL_dti * dti * dp
     return {"total": total, "bce": bce, "dice": dice, "ft": ft, "dlogits": g.reshape(logits.shape),
             "sums": torch.stack([I, p.sum(dim=1), tsum, bce_el.sum(dim=1)], dim=1)}

@@ -205,3 +205,41 @@ def test_library_is_sm100a_only_and_uses_the_blackwell_units():
     for mnemonic in ("UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "LDGSTS", "FFMA2"):
         assert re.search(r"\b" + mnemonic + r"\b", sass), f"{mnemonic} missing from the SASS of libb2s.so"
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync tensor-core instructions in libb2s.so"
+
+
+def test_parameter_collection_on_data_parallel_replicas():
+    """nn.DataParallel (reference utils/trainer.py:28-30) hands forward() a REPLICA whose `_parameters` are empty: torch's
+    replicate() sets the broadcast copies as plain attributes and lists them in `_former_parameters`. The drop-in UNet
+    must find all 82 tensors there (named_parameters() of a replica yields nothing). The replica tree is
+    built here the way torch.nn.parallel.replicate builds it, on CPU (the real thing needs two GPUs:
+    tests/test_ddp_gpu.py::test_data_parallel_equals_chunked_single_gpu)."""
+    from collections import OrderedDict
+    import b200seg  # noqa: F401
+    from b200seg.models.model import UNet, _named_params
+    torch.manual_seed(0)
+    net = UNet()
+    modules = list(net.modules())
+    index = {m: i for i, m in enumerate(modules)}
+    copies = [m._replicate_for_data_parallel() for m in modules]
+    for r in copies:
+        r._former_parameters = OrderedDict()
+    for m, r in zip(modules, copies):
+        for key, child in m._modules.items():
+            r._modules[key] = None if child is None else copies[index[child]]
+        for key, p in m._parameters.items():
+            c = p * 1.0                       # a non-leaf tensor with a grad_fn, like Broadcast's outputs
+            setattr(r, key, c)
+            r._former_parameters[key] = c
+        for key, b in m._buffers.items():
+            r._buffers[key] = b
+    replica = copies[0]
+    assert len(list(replica.named_parameters())) == 0           # what broke round 1's module under DataParallel
+    master = dict(net.named_parameters())
+    got = _named_params(replica)
+    assert list(got.keys()) == list(master.keys()) and len(got) == 82
+    for k, v in got.items():
+        assert v.shape == master[k].shape and not v.is_leaf and v.requires_grad, k
+    assert list(_named_params(net).keys()) == list(master.keys())
+    assert all(_named_params(net)[k] is master[k] for k in master)
+    assert list(replica._tensor_dict().keys())[:82] == list(master.keys())
+    assert len(replica._tensor_dict()) == 136

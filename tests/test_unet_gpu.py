@@ -97,15 +97,17 @@ def test_train_step_matches_oracle_and_reference(net, unet_golden, ref_params):
             assert int(sd[k]) == int(v)
 
 
-def _cache_from_plan(plan, x_img):
-    """Oracle backward cache rebuilt from the CUDA forward's saved tensors (all exactly representable in fp64)."""
+def _cache_from_plan(plan, x_img, dev="cpu"):
+    """Oracle backward cache rebuilt from the CUDA forward's saved tensors (all exactly representable in fp64).
+    dev="cuda" keeps it on the device for the BASELINE-sized cases (the oracle is device-agnostic tensor algebra)."""
     def nchw(a):
-        return a.to_nchw_float().cpu().double()
+        return a.to_nchw_float().to(dev).double()
+    vec = lambda v: v.to(dev).double()
     cache = {}
     for (name, idx), s in plan.stages.items():
-        xin = x_img.double() if s.x is None else nchw(s.x)
-        cache[f"{name}.{idx}"] = dict(x=xin, r=nchw(s.r), mean=s.mean.cpu().double(), invstd=s.invstd.cpu().double(),
-                                      scale=s.scale.cpu().double(), shift=s.shift.cpu().double())
+        xin = x_img.double().to(dev) if s.x is None else nchw(s.x)
+        cache[f"{name}.{idx}"] = dict(x=xin, r=nchw(s.r), mean=vec(s.mean), invstd=vec(s.invstd),
+                                      scale=vec(s.scale), shift=vec(s.shift))
     for l, enc in enumerate(["encoder1", "encoder2", "encoder3", "encoder4"]):
         y = nchw(plan.stages[(enc, 3)].y)
         _, arg = O.maxpool2x2(y)
@@ -114,7 +116,7 @@ def _cache_from_plan(plan, x_img):
                     ("decoder1.1", "decoder1.0")):
         cache[ct] = dict(x=nchw(plan.stages[(src, 3)].y))
     h = plan.stages[("final.0", 3)]
-    cache["head"] = dict(r=nchw(h.r), scale=h.scale.cpu().double(), shift=h.shift.cpu().double())
+    cache["head"] = dict(r=nchw(h.r), scale=vec(h.scale), shift=vec(h.shift))
     return cache
 
 

@@ -397,11 +397,10 @@ static int launch_conv2_t(int grid, const CUtensorMap& tmA, const CUtensorMap& t
                           const ConvTcParams& p, cudaStream_t stream) {
   using L = Conv2Cfg<BLOCK_N, MT, HALO, STAGES, STAGES_A>;
   auto kfn = conv2_tc_kernel<BLOCK_N, MT, HALO, STAGES, STAGES_A>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes);
+  static std::atomic<unsigned long long> attr_devices{0};
+  {
+    cudaError_t e = allow_dynamic_smem(kfn, L::kDynBytes, attr_devices);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv2_tc_kernel)");
-    attr_set = true;
   }
   kfn<<<grid, kConv2Threads, L::kDynBytes, stream>>>(tmA, tmB, tmOut, p);
   return check_launch("conv2_tc_kernel");

@@ -483,11 +483,10 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        const ConvTcParams& p, cudaStream_t stream) {
   using L = ConvSmem<BLOCK_N, STAGES>;
   auto kfn = conv_tc_kernel<BLOCK_N, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes);
+  static std::atomic<unsigned long long> attr_devices{0};
+  {
+    cudaError_t e = allow_dynamic_smem(kfn, L::kDynBytes, attr_devices);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
-    attr_set = true;
   }
   kfn<<<conv_grid(p.tiles_m, p.tiles_nn), kConvThreads, L::kDynBytes, stream>>>(tmA, tmB, tmOut, p);
   return check_launch("conv_tc_kernel");
@@ -709,11 +708,10 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Wg
                         cudaStream_t stream) {
   using L = WgSmem<BLOCK_N, STAGES, MT>;
   auto kfn = wgrad_tc_kernel<BLOCK_N, STAGES, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes);
+  static std::atomic<unsigned long long> attr_devices{0};
+  {
+    cudaError_t e = allow_dynamic_smem(kfn, L::kDynBytes, attr_devices);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(wgrad_tc_kernel)");
-    attr_set = true;
   }
   kfn<<<grid, kNumThreads, L::kDynBytes, stream>>>(tmA, tmB, p);
   return check_launch("wgrad_tc_kernel");

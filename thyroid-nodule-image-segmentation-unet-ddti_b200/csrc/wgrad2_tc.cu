@@ -197,11 +197,10 @@ static int launch_wg2(int grid, const CUtensorMap& tmX, const CUtensorMap& tmDz,
                       cudaStream_t stream) {
   using L = Wg2Cfg<BLOCK_N, A_SLOTS, STAGES>;
   auto kfn = wgrad_halo_kernel<BLOCK_N, A_SLOTS, STAGES, MAXT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes);
+  static std::atomic<unsigned long long> attr_devices{0};
+  {
+    cudaError_t e = allow_dynamic_smem(kfn, L::kDynBytes, attr_devices);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(wgrad_halo_kernel)");
-    attr_set = true;
   }
   kfn<<<grid, kWg2Threads, L::kDynBytes, stream>>>(tmX, tmDz, p);
   return check_launch("wgrad_halo_kernel");

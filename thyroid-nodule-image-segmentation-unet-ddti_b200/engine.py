@@ -149,7 +149,7 @@ class UNetEngine:
         for st in self._pack_state.values():
             st["versions"] = None
 
-    def _pack_weights(self, P, need_dgrad):
+    def _pack_weights(self, P, need_dgrad, cache=True):
         """fp32 parameters -> bf16 GEMM operands, all tensors in one launch; skipped while the parameters' version
         counters and addresses are unchanged. State is kept per device: nn.DataParallel (utils/trainer.py:30) runs
         replicas of one module — sharing this engine object — concurrently, one thread per GPU."""
@@ -157,23 +157,26 @@ class UNetEngine:
                  and k != "final.1.weight"]
         dev = str(P[names[0]].device)
         st = self._pack_state.setdefault(dev, {"versions": None, "layout": None, "plan": None})
-        versions = tuple((k, P[k]._version, P[k].data_ptr(), need_dgrad) for k in names)
-        if versions == st["versions"]:
+        # (identity, address, version): a freed tensor's address can be handed to a new tensor at version 0, so the
+        # owning tensor object is part of the key (the plan keeps the tensors it packed alive, ids cannot be reused)
+        versions = tuple((k, id(P[k]), P[k]._version, P[k].data_ptr(), need_dgrad) for k in names)
+        if cache and versions == st["versions"]:
             return st["plan"].packed
-        layout = tuple((k, P[k].data_ptr(), need_dgrad) for k in names)
-        if st["layout"] != layout:
+        layout = tuple((k, id(P[k]), P[k].data_ptr(), need_dgrad) for k in names)
+        if not cache or st["layout"] != layout:
             items = []
             for k in names:
                 is_convt = k.split(".")[0] in ("middle", "decoder3", "decoder2", "decoder1") and P[k].shape[2] == 2
                 items.append((k, P[k].detach(), is_convt))
             st["plan"] = ops.PackPlan(items, want_dgrad=need_dgrad)
             st["layout"] = layout
+            st["owners"] = [P[k] for k in names]
         st["plan"].run()
         st["versions"] = versions
         return st["plan"].packed
 
     # ---- forward ----------------------------------------------------------------------------------------------
-    def forward(self, P, x, train, want_mask=False, need_backward=None):
+    def forward(self, P, x, train, want_mask=False, need_backward=None, cache_packed=True):
         """x [N,1,H,W] fp32 CUDA. Returns (logits fp32 [N,O,H,W], plan). P: name -> tensor (params and BN buffers)."""
         if not x.is_cuda:
             raise ops._lib.B2SError("UNetEngine.forward needs a CUDA tensor: the B200 path has no CPU fallback")
@@ -185,7 +188,8 @@ class UNetEngine:
         pl.generation += 1
         x = x.contiguous().float()
         pl.x = x
-        pl.packed = self._pack_weights(P, need_dgrad=need_backward)
+        # nn.DataParallel replicas get fresh broadcast copies of the parameters every forward: never reuse a pack
+        pl.packed = self._pack_weights(P, need_dgrad=need_backward, cache=cache_packed)
         count = lambda l: float(N * pl.dims[l][0] * pl.dims[l][1])
 
         def stage(name, idx, xin, pooled=None):

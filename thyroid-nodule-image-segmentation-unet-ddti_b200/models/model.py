@@ -16,29 +16,51 @@ def _stage_layers(cin, cout):
     return [nn.Conv2d(cin, cout, kernel_size=3, padding=1), nn.ReLU(inplace=True), nn.BatchNorm2d(cout)]
 
 
+def _named_params(module):
+    """name -> parameter tensor of `module`, also on nn.DataParallel replicas (utils/trainer.py:28-30): torch's
+    replicate() leaves a replica's `_parameters` EMPTY and keeps the broadcast copies (non-leaf tensors whose gradient
+    flows back to the master parameters through Broadcast.backward) as plain attributes listed in
+    `_former_parameters`; `named_parameters()` of a replica therefore yields nothing."""
+    out = {}
+    for mname, m in module.named_modules():
+        src = m._parameters
+        if not src and getattr(m, "_is_replica", False):
+            src = getattr(m, "_former_parameters", {})
+        for k, v in src.items():
+            if v is not None:
+                out[f"{mname}.{k}" if mname else k] = v
+    return out
+
+
 class _UNetFunction(torch.autograd.Function):
     """Whole-network autograd node: forward and backward are single passes through the engine."""
 
     @staticmethod
     def forward(ctx, x, module, names, need_bwd, *params):
-        P = module._tensor_dict()
-        logits, plan = module._engine.forward(P, x, train=module.training, need_backward=need_bwd)
-        ctx.module, ctx.plan, ctx.generation, ctx.names = module, plan, plan.generation, names
+        P = dict(zip(names, params))
+        P.update(dict(module.named_buffers()))
+        with torch.cuda.device(x.device):
+            logits, plan = module._engine.forward(P, x, train=module.training, need_backward=need_bwd,
+                                                  cache_packed=not getattr(module, "_is_replica", False))
+        ctx.P, ctx.plan, ctx.generation, ctx.names = P, plan, plan.generation, names
+        ctx.engine = module._engine
         ctx.train_stats = module.training
+        ctx.x_needs_grad = x.requires_grad
         return logits.clone()
 
     @staticmethod
     def backward(ctx, dlogits):
-        module, plan = ctx.module, ctx.plan
+        plan = ctx.plan
         if plan.generation != ctx.generation:
             raise RuntimeError("b200seg UNet: the saved activations of this forward were overwritten by a later forward "
                                "of the same shape; call backward before the next forward")
         if not ctx.train_stats:
             raise RuntimeError("b200seg UNet: backward through eval-mode BatchNorm is not implemented "
                                "(the reference only back-propagates in train mode, utils/trainer.py:55,91)")
-        P = module._tensor_dict()
+        P = ctx.P
         G = {n: torch.empty_like(P[n], dtype=torch.float32) for n in ctx.names}
-        module._engine.backward(P, plan, dlogits, G)
+        with torch.cuda.device(dlogits.device):
+            ctx.engine.backward(P, plan, dlogits, G)
         return (None, None, None, None) + tuple(G[n] for n in ctx.names)
 
 
@@ -67,9 +89,15 @@ class UNet(nn.Module):
                              nn.ConvTranspose2d(in_channels // 2, out_channels, kernel_size=2, stride=2))
 
     def _tensor_dict(self):
-        d = dict(self.named_parameters())
+        d = _named_params(self)
         d.update(dict(self.named_buffers()))
         return d
+
+    def invalidate_packed(self):
+        """Forces the next forward to re-pack the bf16 GEMM operands. The pack is skipped while every weight's
+        (tensor identity, address, version counter) is unchanged; writes that bypass the version counter
+        (`p.data.copy_()`, an external kernel) must be followed by this call."""
+        self._engine.invalidate_packed()
 
     def forward(self, x):
         if x.dim() != 4 or x.shape[1] != self.in_channels:
@@ -78,8 +106,11 @@ class UNet(nn.Module):
             raise RuntimeError("Sizes of tensors must match except in dimension 1: H and W must be multiples of 16")
         if not x.is_cuda:
             raise RuntimeError("b200seg UNet runs on CUDA (sm_100a) only; there is no CPU fallback")
-        names = tuple(n for n, _ in self.named_parameters())
-        params = tuple(p for _, p in self.named_parameters())
+        if x.requires_grad:
+            raise RuntimeError("b200seg UNet does not compute the gradient with respect to the input image (the "
+                               "reference's trainer never asks for it); detach the input or use the reference module")
+        named = _named_params(self)
+        names, params = tuple(named.keys()), tuple(named.values())
         if params[0].device != x.device:
             raise RuntimeError("UNet parameters and input are on different devices; call model.to(device)")
         if torch.is_autocast_enabled():
@@ -92,5 +123,7 @@ class UNet(nn.Module):
     def predict_mask(self, x):
         """Inference entry (utils/trainer.py:216-217): returns (logits, uint8 mask) with mask = sigmoid(logits) > 0.5."""
         P = self._tensor_dict()
-        logits, plan = self._engine.forward(P, x, train=False, want_mask=True, need_backward=False)
+        with torch.cuda.device(x.device):
+            logits, plan = self._engine.forward(P, x, train=False, want_mask=True, need_backward=False,
+                                                cache_packed=not getattr(self, "_is_replica", False))
         return logits, plan.mask

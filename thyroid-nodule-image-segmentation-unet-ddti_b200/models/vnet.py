@@ -145,7 +145,11 @@ class ImprovedVNet(nn.Module):
         ws = [(n, p) for n, p in self.named_parameters()
               if p.dim() == 4 and p.shape[1] >= 64 and p.shape[0] >= 64 and p.shape[0] % 64 == 0 and p.shape[1] % 64 == 0
               and ".fc" not in n]
-        key = tuple((p.data_ptr(), p._version) for _, p in ws)
+        # self.training is part of the key: it decides whether the dgrad operands are packed (an eval forward between
+        # two train forwards must not leave the train step without them)
+        key = (self.training,) + tuple((id(p), p.data_ptr(), p._version) for _, p in ws)
+        if not ws:
+            return        # nn.DataParallel replica (named_parameters() is empty there): the nodes pack on the spot
         if getattr(self, "_pack_key", None) == key:
             return
         layout = tuple((p.data_ptr(), self.training) for _, p in ws)

@@ -9,19 +9,21 @@ from ._lib import B2S_FLAG_RELU, B2S_FLAG_STATS, check
 
 BF16 = torch.bfloat16
 
-# When set to a list, every wrapper below appends (name, kind, work, start_event, end_event): kind "tensor" ->
-# work = algorithmic FLOPs, kind "hbm" -> work = algorithmic bytes. Used by bench.py's roofline pass.
+# When set to a list, every wrapper below appends (name, kind, work, start_event, end_event, nbytes): kind "tensor"
+# -> work = algorithmic FLOPs, kind "hbm" -> work = algorithmic bytes; nbytes = algorithmic HBM bytes of
+# a "tensor" launch whose arithmetic intensity is below the ridge (the high-resolution transposed convs), else None.
+# Used by bench.py's roofline pass.
 PROFILE = None
 
 
-def _timed(name, kind, work, fn):
+def _timed(name, kind, work, fn, nbytes=None):
     if PROFILE is None:
         return fn()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     r = fn()
     e.record()
-    PROFILE.append((name, kind, float(work), s, e))
+    PROFILE.append((name, kind, float(work), s, e, nbytes))
     return r
 
 
@@ -197,16 +199,18 @@ def conv_stats_rows(N, H, W, Cout, tile_n=0):
 
 def convt_fwd(x, w_packed, bias, y, tile_n=0):
     flops = 8.0 * x.N * x.H * x.W * x.C * y.C
+    nbytes = 2.0 * x.N * x.H * x.W * (x.C + 4 * y.C) + 8.0 * x.C * y.C      # read x, write the 2x up-sampled y, weights
     _timed(f"convT_fwd[{x.C}->{y.C}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
         _lib.lib().b2s_convt2x2_fwd(x.ptr, x.cstride, _p(w_packed), _p(bias), y.ptr, y.cstride, x.N, x.H, x.W, x.C,
-                                    y.C, tile_n, _stream()), "b2s_convt2x2_fwd"))
+                                    y.C, tile_n, _stream()), "b2s_convt2x2_fwd"), nbytes)
 
 
 def convt_dgrad(dy, w_packed_d, dx, tile_n=0):
     flops = 8.0 * dx.N * dx.H * dx.W * dx.C * dy.C
+    nbytes = 2.0 * dx.N * dx.H * dx.W * (dx.C + 4 * dy.C) + 8.0 * dx.C * dy.C
     _timed(f"convT_dgrad[{dx.C}<-{dy.C}@{dx.H}x{dx.W}]", "tensor", flops, lambda: check(
         _lib.lib().b2s_convt2x2_dgrad(dy.ptr, dy.cstride, _p(w_packed_d), dx.ptr, dx.cstride, dx.N, dx.H, dx.W,
-                                      dx.C, dy.C, tile_n, _stream()), "b2s_convt2x2_dgrad"))
+                                      dx.C, dy.C, tile_n, _stream()), "b2s_convt2x2_dgrad"), nbytes)
 
 
 def wgrad_workspace(N, H, W, Cin, Cout, taps, tile_n=0, splits=0):
@@ -237,9 +241,10 @@ def convt_wgrad(x, dy, ws, dw, tile_n=0, splits=0):
     assert ws.numel() * 4 >= nbytes, "wgrad workspace too small"
     L = _lib.lib()
     flops = 8.0 * x.N * x.H * x.W * x.C * dy.C
+    nbytes = 2.0 * x.N * x.H * x.W * (x.C + 4 * dy.C) + 16.0 * x.C * dy.C * s
     _timed(f"convT_wgrad[{x.C}->{dy.C}@{x.H}x{x.W}]", "tensor", flops, lambda: check(
         L.b2s_convt2x2_wgrad(x.ptr, x.cstride, dy.ptr, dy.cstride, _p(ws), x.N, x.H, x.W, x.C, dy.C, tile_n, splits,
-                             _stream()), "b2s_convt2x2_wgrad"))
+                             _stream()), "b2s_convt2x2_wgrad"), nbytes)
     _timed(f"wgradT_reduce[{x.C}->{dy.C},s={s}]", "hbm", 4.0 * 4 * x.C * dy.C * (s + 1), lambda: check(
         L.b2s_wgrad_reduce(_p(ws), s, 4, x.C, dy.C, _p(dw), 1, _stream()), "b2s_wgrad_reduce"))
 

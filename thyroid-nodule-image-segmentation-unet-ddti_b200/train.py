@@ -155,19 +155,21 @@ class TrainStep:
         ev.record()
 
     def _graph_body(self):
-        # Single GPU: the whole step is one graph. Data parallel: the graph ends after backward; the gradient
-        # all-reduce (one NCCL call over the flat buffer, ~0.3 ms at 8 GPUs) and AdamW are launched from the host
-        # after the replay, because NCCL calls are kept out of stream capture.
-        self.forward_backward(self._gx, self._gt, reduce=False)
-        if self.world == 1:
+        # The whole optimisation step is ONE graph on every world size. Data parallel: each bucket's ncclAllReduce is
+        # captured on NCCL's own stream (forked from the compute stream by the event recorded after the bucket's last
+        # weight-gradient kernel, joined before AdamW), so inside the replay the collectives overlap the remaining
+        # backward exactly as in the host-launched step; only the last, small bucket and the join are exposed.
+        self.forward_backward(self._gx, self._gt, reduce=self.graph_comm)
+        if self.world == 1 or self.graph_comm:
             ops.adamw_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self._hyper_dev)
         self.engine.invalidate_packed()
 
-    def capture(self, x, t):
-        """Captures forward + loss + backward (+ bucketed all-reduce) + AdamW for inputs shaped like x, t.
-        Runs two eager steps first (lazy initialisation inside the library, NCCL warm-up); they are real optimisation
-        steps. Returns True when the graph is in use, False when capture failed (eager path stays in effect)."""
-        from . import _lib
+    def capture(self, x, t, graph_comm=True):
+        """Captures forward + loss + backward + bucketed all-reduce + AdamW for inputs shaped like x, t.
+        Runs two eager steps first (lazy initialisation inside the library, NCCL communicator set-up); they are real
+        optimisation steps. graph_comm=False keeps NCCL out of the capture (one all-reduce over the flat gradient and
+        AdamW launched after the replay); it is also the automatic second attempt when capturing the collectives fails
+        on any rank. Returns True when the graph is in use, False when capture failed (eager path stays in effect)."""
         self._gx, self._gt = torch.empty_like(x), torch.empty_like(t)
         self._hyper_dev = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._hyper_ring = [(torch.zeros(8, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
@@ -175,29 +177,38 @@ class TrainStep:
         for _ in range(2):
             self.step(x, t)
         torch.cuda.synchronize()
+        self.graph_comm = bool(graph_comm) and self.world > 1
+        ok = self._agree_on_graph(self._try_capture(x, t))
+        if not ok and self.graph_comm:
+            first = getattr(self, "capture_error", "another rank failed")
+            self.graph_comm = False
+            ok = self._agree_on_graph(self._try_capture(x, t))
+            self.capture_error = f"in-graph NCCL capture failed ({first}); collectives launched after the replay"
+        return ok
+
+    def _try_capture(self, x, t):
+        from . import _lib
         g = torch.cuda.CUDAGraph()
         step_before = self.step_count
         try:
             self._gx.copy_(x); self._gt.copy_(t)
             self._write_hyper(None)
             l0 = _lib.launch_count()
-            with torch.cuda.graph(g):
+            # thread_local: NCCL's watchdog / heartbeat threads may query events while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._graph_body()
             self.graph_launches = _lib.launch_count() - l0
             self._graph = g
         except Exception as e:   # capture is an optimisation: report and keep the eager path
             self.capture_error = f"{type(e).__name__}: {e}"
-            self.step_count = step_before
             self._graph = None
             torch.cuda.synchronize()
-            return self._agree_on_graph()
         # the capture itself did not execute the step (and step_count was advanced for it): undo the count
         self.step_count = step_before
-        return self._agree_on_graph()
+        return self._graph is not None
 
-    def _agree_on_graph(self):
-        """Under data parallelism every rank must take the same path (graphed: one all-reduce; eager: bucketed)."""
-        ok = self._graph is not None
+    def _agree_on_graph(self, ok):
+        """Under data parallelism every rank must take the same path (graphed or eager, collectives in or out)."""
         if self.world > 1:
             flag = torch.tensor([1.0 if ok else 0.0], device=self.device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
@@ -214,8 +225,44 @@ class TrainStep:
         self._gt.copy_(t, non_blocking=True)
         self._write_hyper(lr)
         self._graph.replay()
-        if self.world > 1:
+        if self.world > 1 and not self.graph_comm:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
             ops.adamw_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self._hyper_dev)
         key = (x.shape[0], x.shape[2], x.shape[3], str(x.device))
         return self.engine.plans[key].loss_out
+
+
+# ---- verification of the data-parallel semantics ---------------------------------------------------------------------
+def emulate_replicas(state_dict, device, shards, lrs, engine=None, **kw):
+    """The reference's data-parallel semantics (nn.DataParallel, utils/trainer.py:28-30) evaluated on ONE GPU: every
+    replica r runs forward + loss + backward on shards[r] with its OWN BatchNorm batch statistics and running buffers,
+    the parameter gradients are summed over the replicas in rank order, and every replica applies the same AdamW update
+    to the mean gradient, one step per entry of `lrs`. Returns the list of per-replica TrainStep objects (replica 0 holds the buffers that would be
+    checkpointed). Used by bench.py's post-run check and tests/run_ddp_check.py to verify that N NCCL ranks x b images
+    reproduce this chunked single-GPU run."""
+    n = len(shards)
+    engine = engine if engine is not None else UNetEngine(out_channels=state_dict["final.1.bias"].numel())
+    reps = [TrainStep({k: v.clone() for k, v in state_dict.items()}, device, lr=lrs[0] or 0.0, use_dist=False, engine=engine,
+                      **kw) for _ in range(n)]
+    for rep in reps:
+        rep.world = n                      # AdamW consumes g / n, exactly what the ranks do
+    for lr in lrs:
+        for rep, (x, t) in zip(reps, shards):
+            rep.forward_backward(x, t, reduce=False)
+        total = reps[0].flat_g.clone()
+        for rep in reps[1:]:
+            total += rep.flat_g
+        for rep in reps:
+            rep.flat_g.copy_(total)
+            if lr is not None:             # None: forward + backward only (gradient probe), no optimiser step
+                rep.optimizer_step(lr)
+    return reps
+
+
+def ranks_agree(flat, group=None):
+    """True when every rank holds bit-identical `flat` (compared through their int32 views: NaN-safe, sign-of-zero safe)."""
+    world = dist.get_world_size(group)
+    mine = flat.view(torch.int32)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    return all(bool(torch.equal(gathered[0], g)) for g in gathered[1:])

@@ -89,7 +89,7 @@ if rank == 0 and os.environ.get("VNET_PROFILE"):
     _ops.PROFILE = []
     step(); torch.cuda.synchronize()
     agg = {}
-    for n, k, w, s_, e_ in _ops.PROFILE:
+    for n, k, w, s_, e_, _nb in _ops.PROFILE:
         a = agg.setdefault(n, [k, 0, 0.0, 0.0]); a[1] += 1; a[2] += s_.elapsed_time(e_); a[3] += w
     _ops.PROFILE = None
     tot = sum(a[2] for a in agg.values())
