@@ -188,6 +188,22 @@ FAMILY_NOTE = {
 }
 
 
+def shutdown_process_group(timeout_s=20.0):
+    """destroy_process_group() with a deadline: the result line is already printed when this runs, a slow NCCL
+    teardown must not turn a finished run into a hang."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout_s)
+    if t.is_alive():
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def dp_check(world, rank, dev, sd, S, no_graph=False, vb=8):
     """Correctness of the N>1 path on this hardware against the reference's data-parallel semantics (per-replica
     BatchNorm statistics, summed gradients: utils/trainer.py:28-30): fresh TrainSteps, the SAME code path as the timed
@@ -212,6 +228,7 @@ def dp_check(world, rank, dev, sd, S, no_graph=False, vb=8):
     agree = ranks_agree(vts.flat_p)
     gathered = [torch.empty_like(vts.flat_p) for _ in range(world)] if rank == 0 else None
     dist.gather(vts.flat_p, gathered, dst=0)
+    vts.release_graph()
     check = {"ranks_hold_bit_identical_parameters": bool(agree), "batch_per_rank": vb,
              "path": "CUDA graph with in-graph NCCL buckets" if v_graphed and vts.graph_comm else
                      ("CUDA graph + flat all-reduce" if v_graphed else "host-launched bucketed")}
@@ -380,7 +397,8 @@ def run_b200(args):
     # (2b) data parallel: how much of the step is communication that backward does not hide, and do the ranks agree
     if world > 1:
         # the same captured step WITHOUT any collective (a world-1 TrainStep on the same engine and shapes)
-        nocomm = TrainStep(sd, dev, lr=1e-5, use_dist=False, engine=ts.engine)
+        # (own engine: a captured graph bakes in the addresses of its engine's packed-weight buffers)
+        nocomm = TrainStep(sd, dev, lr=1e-5, use_dist=False)
         nc_graphed = (not args.no_graph) and nocomm.capture(x_dev, t_dev)
         nc_step = nocomm.step_graphed if nc_graphed else nocomm.step
         for _ in range(2):
@@ -394,7 +412,8 @@ def run_b200(args):
                                       f"{k_nc} steps each; buckets: {len(ts.buckets)}; what stays exposed is the last "
                                       "bucket's all-reduce (issued after encoder1's weight gradient) plus rank skew")
         extra["comm_in_graph"] = bool(graphed and getattr(ts, "graph_comm", False))
-        del nocomm
+        nocomm.release_graph()
+        del nocomm, nc_step
         check = dp_check(world, rank, dev, sd, S, no_graph=args.no_graph)
         extra["dp_check"] = check
         torch.cuda.empty_cache()
@@ -413,6 +432,7 @@ def run_b200(args):
             extra["configs2_global_batch_512"] = {"batch_per_gpu": gb, "n_gpus": world, "ms_per_step": ms_g / k_g,
                                                   "images_per_s": 512 * k_g / (ms_g * 1e-3), "steps": k_g,
                                                   "cuda_graph": bool(g_graphed)}
+            gts.release_graph()
             del gts, gx, gt
             torch.cuda.empty_cache()
         elif gb == B:
@@ -508,7 +528,9 @@ def run_b200(args):
             json.dump({"batch": B, "size": S, "ms_per_step": ms_step, "kernels": agg}, f, indent=1)
 
     # (4) the other BASELINE configurations and the baselines, outside every timed region above
-    del ts, bufs
+    ts.release_graph()          # also required before the NCCL communicator can be torn down
+    ts.engine.plans.clear()
+    del ts, bufs, run_step
     torch.cuda.empty_cache()
     gpu_baseline = None
     if not args.no_extras:
@@ -537,7 +559,6 @@ def run_b200(args):
 
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -550,7 +571,9 @@ def run_b200(args):
                 "gpu_baseline": gpu_baseline, "extra": extra}
         if capture_error:
             line["cuda_graph_error"] = capture_error
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        shutdown_process_group()
 
 
 def main():

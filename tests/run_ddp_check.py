@@ -18,6 +18,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if os.environ.get("B2S_HANG_DUMP"):          # debugging aid: dump every thread's stack if the run is still alive after N s
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ["B2S_HANG_DUMP"]), exit=True)
 
 
 def main():
@@ -74,8 +77,10 @@ def main():
                                 "bit_identical_rank0": bool(torch.equal(eager.flat_p, graph.flat_p))}
     dist.barrier()
     if rank == 0:
-        print("DDP_JSON " + json.dumps(report))
-    dist.destroy_process_group()
+        print("DDP_JSON " + json.dumps(report), flush=True)
+    graph.release_graph()          # a live graph with captured collectives blocks the communicator teardown
+    del graph, eager
+    bench.shutdown_process_group()
 
 
 if __name__ == "__main__":

@@ -20,6 +20,9 @@ import types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if os.environ.get("B2S_HANG_DUMP"):          # debugging aid: dump every thread's stack if the run is still alive after N s
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ["B2S_HANG_DUMP"]), exit=True)
 
 
 def install_plot_stubs():

@@ -82,3 +82,13 @@ def test_data_parallel_equals_chunked_single_gpu():
         assert d <= 1e-6 * float(g_dp[k].abs().max()) + 1e-12, (k, d)
     for k, v in keep.items():
         assert torch.equal(v, sd_dp[k]), k
+    # eval mode (Trainer.validate / test under DataParallel): samples are independent, so the replicas' logits are the
+    # single-GPU logits of the same frames
+    net.load_state_dict(sd_dp)
+    net.eval()
+    with torch.no_grad():
+        e_dp = dp(x)
+        e_one = torch.cat([net(x[:4].contiguous()), net(x[4:].contiguous())])
+        e_full = net(x)
+    assert torch.equal(e_dp, e_one), float((e_dp - e_one).abs().max())
+    assert float((e_dp - e_full).abs().max()) < 1e-5

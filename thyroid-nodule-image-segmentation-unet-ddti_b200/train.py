@@ -186,6 +186,12 @@ class TrainStep:
             self.capture_error = f"in-graph NCCL capture failed ({first}); collectives launched after the replay"
         return ok
 
+    def release_graph(self):
+        """Drops the captured graph. Call before torch.distributed.destroy_process_group(): NCCL cannot tear down a
+        communicator while a live CUDA graph still holds its captured collectives (the destroy call blocks)."""
+        self._graph = None
+        torch.cuda.synchronize(self.device)
+
     def _try_capture(self, x, t):
         from . import _lib
         g = torch.cuda.CUDAGraph()
