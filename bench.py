@@ -283,12 +283,18 @@ def run_b200(args):
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
             os.environ.pop("NCCL_DEBUG")           # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        if args.nccl_max_ctas > 0:       # bound the SMs the overlapped all-reduces may take from the compute kernels
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = args.nccl_max_ctas
+            opts.config.min_ctas = min(args.nccl_max_ctas, 4)
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     B, S = args.batch, args.size
     torch.manual_seed(42)
     sd = UNet().state_dict()
-    ts = TrainStep(sd, dev, lr=1e-5)
+    ts = TrainStep(sd, dev, lr=1e-5, bucket_mb=args.bucket_mb)
     x_cpu, t_cpu = synth_batch(B, S, S, seed=1234 + rank)
     x_pin, t_pin = x_cpu.pin_memory(), t_cpu.pin_memory()
     x_dev, t_dev = x_pin.to(dev, non_blocking=True), t_pin.to(dev, non_blocking=True)
@@ -533,6 +539,7 @@ def run_b200(args):
     del ts, bufs, run_step
     torch.cuda.empty_cache()
     gpu_baseline = None
+    extra["bucket_mb"], extra["nccl_max_ctas"] = args.bucket_mb, args.nccl_max_ctas
     if not args.no_extras:
         try:
             extra["configs4_vnet_training"] = bench_legs.vnet_leg(dev, world, rank, local, batch=args.vnet_batch)
@@ -586,6 +593,8 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[2]/[3]/[4] legs and the stock-torch baseline")
+    ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient bucket size of the all-reduce")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="ncclConfig max_ctas for the gradient all-reduces (0: NCCL default)")
     ap.add_argument("--vnet-batch", type=int, default=16, help="per-GPU batch of the V-Net leg (configs[4])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph per step")
     ap.add_argument("--profile-out", default="", help="write the per-kernel roofline table (JSON) here")

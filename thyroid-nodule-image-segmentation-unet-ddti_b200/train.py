@@ -44,7 +44,7 @@ class TrainStep:
     """Owns flat fp32 parameter / gradient / Adam-moment buckets laid out in gradient-ready order."""
 
     def __init__(self, state_dict, device, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 bucket_mb=16.0, w_bce=1.0, w_dice=1.0, w_ft=0.0, process_group=None, use_dist=None, engine=None):
+                 bucket_mb=32.0, w_bce=1.0, w_dice=1.0, w_ft=0.0, process_group=None, use_dist=None, engine=None):
         self.device = torch.device(device)
         self.engine = engine if engine is not None else UNetEngine(out_channels=state_dict["final.1.bias"].numel())
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
@@ -88,24 +88,42 @@ class TrainStep:
                 self.buckets.append((start, end))
                 start = end
         self.order = order
-        self._works = []
+        self._works, self._reduce, self._opt, self._side = [], True, None, None
 
     # ---- parameter access -------------------------------------------------------------------------------------
     def state_dict(self):
         return {k: v.detach().clone() for k, v in self.P.items()}
 
     def _on_grad_ready(self, name):
-        if self.world == 1:
-            return
+        """Bucket hook of UNetEngine.backward: when the last gradient of a bucket has been enqueued, its all-reduce is
+        issued (NCCL's stream, ordered after the compute stream) and — if this step carries a fused optimiser — AdamW
+        for the bucket's parameter range is enqueued on a side stream behind the all-reduce. Both overlap the rest of
+        backward. Safe because a parameter's last reader in a step is its own layer's backward, which precedes this
+        hook (the tensor-core kernels read the packed bf16 copies, refreshed at the start of the next forward)."""
         b = self.bucket_of[name]
-        if self.bucket_last[b] == name:
-            s, e = self.buckets[b]
-            self._works.append(dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        if self.bucket_last[b] != name:
+            return
+        s, e = self.buckets[b]
+        work = None
+        if self.world > 1 and self._reduce:
+            work = dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self._works.append(work)
+        if self._opt is not None:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            if work is None:
+                self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                if work is not None:
+                    work.wait()                    # the side stream waits for the collective; the host does not block
+                self._opt(s, e)
 
     # ---- one optimisation step ------------------------------------------------------------------------------------
-    def forward_backward(self, x, t, reduce=True):
+    def forward_backward(self, x, t, reduce=True, opt=None):
         """x [B,1,H,W] fp32, t [B,1,H,W] fp32 on the device. Returns the 8-float loss vector (device tensor).
-        reduce=False leaves the gradients un-reduced (the caller all-reduces flat_g itself)."""
+        reduce=False leaves the gradients un-reduced (the caller all-reduces flat_g itself).
+        opt: None, or a callable (start, end) applying the optimiser to that range of the flat buffers; it is launched
+        per bucket, overlapped with the remaining backward (see _on_grad_ready)."""
         eng = self.engine
         _, pl = eng.forward(self.P, x, train=True)
         out = eng.loss(pl, t, w_bce=self.w_bce, w_dice=self.w_dice, w_ft=self.w_ft)
@@ -118,10 +136,14 @@ class TrainStep:
             dist.all_reduce(ft_tot, op=dist.ReduceOp.SUM, group=self.pg)
             w_ft = self.w_ft * self.world
         dl = eng.loss_backward(pl, t, ft_tot=ft_tot, w_bce=self.w_bce, w_dice=self.w_dice, w_ft=w_ft)
-        self._works = []
-        eng.backward(self.P, pl, dl, self.G, on_grad_ready=self._on_grad_ready if reduce else None)
+        self._works, self._reduce, self._opt = [], reduce, opt
+        hook = self._on_grad_ready if (opt is not None or (reduce and self.world > 1)) else None
+        eng.backward(self.P, pl, dl, self.G, on_grad_ready=hook)
         for w in self._works:
             w.wait()
+        if opt is not None and self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+        self._opt = None
         return out
 
     def optimizer_step(self, lr=None):
@@ -131,8 +153,16 @@ class TrainStep:
         self.engine.invalidate_packed()      # the kernel updated flat_p behind torch's version counters
 
     def step(self, x, t, lr=None):
-        out = self.forward_backward(x, t)
-        self.optimizer_step(lr)
+        """Host-launched step: forward, loss, backward with the bucketed all-reduce and per-bucket AdamW overlapped."""
+        self.step_count += 1
+        lr_ = lr if lr is not None else self.lr
+        b1, b2, step, scale = self.betas[0], self.betas[1], self.step_count, 1.0 / self.world
+
+        def opt(s, e):
+            ops.adamw_step(self.flat_p[s:e], self.flat_g[s:e], self.flat_m[s:e], self.flat_v[s:e], lr_, b1, b2, self.eps,
+                           self.wd, step, scale)
+        out = self.forward_backward(x, t, opt=opt)
+        self.engine.invalidate_packed()      # the kernel updated flat_p behind torch's version counters
         return out
 
     # ---- the same step as ONE CUDA graph -----------------------------------------------------------------------
@@ -159,9 +189,13 @@ class TrainStep:
         # captured on NCCL's own stream (forked from the compute stream by the event recorded after the bucket's last
         # weight-gradient kernel, joined before AdamW), so inside the replay the collectives overlap the remaining
         # backward exactly as in the host-launched step; only the last, small bucket and the join are exposed.
-        self.forward_backward(self._gx, self._gt, reduce=self.graph_comm)
+        # AdamW runs per bucket on a side stream behind the bucket's all-reduce (world 1: behind its last gradient).
         if self.world == 1 or self.graph_comm:
-            ops.adamw_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self._hyper_dev)
+            def opt(s, e):
+                ops.adamw_step_dev(self.flat_p[s:e], self.flat_g[s:e], self.flat_m[s:e], self.flat_v[s:e], self._hyper_dev)
+            self.forward_backward(self._gx, self._gt, reduce=self.graph_comm, opt=opt)
+        else:
+            self.forward_backward(self._gx, self._gt, reduce=False)
         self.engine.invalidate_packed()
 
     def capture(self, x, t, graph_comm=True):

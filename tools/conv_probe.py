@@ -48,6 +48,8 @@ def main():
     ap.add_argument("--tile-n", type=int, default=0)
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--json", default="")
+    ap.add_argument("--concat", action="store_true", help="convT: write into the first half of a concat buffer")
+    ap.add_argument("--convt-mode", default="fwd", choices=["fwd", "dgrad", "wgrad"])
     args = ap.parse_args()
     B = args.batch
     results = []
@@ -81,9 +83,22 @@ def main():
             w = torch.randn((cin, cout, 2, 2), device=DEV) * 0.05
             wf, _ = ops.pack_convt_weight(w)
             bias = torch.randn(cout, device=DEV)
-            ys = [ops.Act.empty(B, 2 * h, 2 * h, cout, DEV) for _ in range(nbuf)]
+            if args.concat:   # the engine's layout: the up-conv writes the first half of a [.., 2*Cout] concat buffer
+                ys = [ops.Act.empty(B, 2 * h, 2 * h, 2 * cout, DEV).slice(0, cout) for _ in range(nbuf)]
+            else:
+                ys = [ops.Act.empty(B, 2 * h, 2 * h, cout, DEV) for _ in range(nbuf)]
             flops = 8.0 * B * h * h * cin * cout
-            fn = lambda i: ops.convt_fwd(xs[i % nbuf], wf, bias, ys[i % nbuf], tile_n=args.tile_n)
+            gb = (2.0 * B * h * h * (cin + 4 * cout)) / 1e9
+            if args.convt_mode == "dgrad":
+                _, wdp = ops.pack_convt_weight(w)
+                fn = lambda i: ops.convt_dgrad(ys[i % nbuf], wdp, xs[i % nbuf], tile_n=args.tile_n)
+            elif args.convt_mode == "wgrad":
+                nbytes, _ = ops.wgrad_workspace(B, h, h, cin, cout, 4, args.tile_n, args.splits)
+                ws = torch.empty(nbytes // 4, dtype=torch.float32, device=DEV)
+                dw = torch.empty((cin, cout, 2, 2), dtype=torch.float32, device=DEV)
+                fn = lambda i: ops.convt_wgrad(xs[i % nbuf], ys[i % nbuf], ws, dw, tile_n=args.tile_n, splits=args.splits)
+            else:
+                fn = lambda i: ops.convt_fwd(xs[i % nbuf], wf, bias, ys[i % nbuf], tile_n=args.tile_n)
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
@@ -95,7 +110,8 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
         tf = flops / (ms * 1e-3) / 1e12
-        print(f"{name:34s} {ms * 1e3:9.1f} us  {tf:8.1f} TFLOP/s", flush=True)
+        extra = f"  {gb / (ms * 1e-3):8.1f} GB/s" if kind == "convT" else ""
+        print(f"{name:34s} {ms * 1e3:9.1f} us  {tf:8.1f} TFLOP/s{extra}", flush=True)
         results.append({"name": name, "us": ms * 1e3, "tflops": tf})
         del xs
         torch.cuda.empty_cache()
