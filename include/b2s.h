@@ -242,6 +242,37 @@ int b2s_se_fc_bwd(const float* partial, int chunks, const float* gate, const flo
                   const float* w1, const float* w2, float* ds, float* dh, float* dmean, float* dw1, float* db1,
                   float* dw2, float* db2, int N, int C, int Cr, void* stream);
 
+/* AttentionGate (models/mod.py:211-234): psi = sigmoid(BatchNorm2d(1)(conv1x1(relu(g1 + x1)))), out = x * psi.
+ * The F_int -> 1 conv is b2s_head_fwd over channel slices of at most 256 channels (up to four fp32 maps, summed on
+ * the fly by the kernels below). One-channel BatchNorm + sigmoid over n = N*H*W values:
+ *   b2s_psi_stats       partial [b2s_psi_rows(n)][2] = {sum v, sum v^2}; finalise with b2s_bn_finalize(C = 1)
+ *   b2s_psi_fwd         psi = sigmoid(v * scale[0] + shift[0])
+ *   b2s_psi_bwd_reduce  partial [b2s_psi_rows(n)][2] = {sum g, sum g*xhat}, g = dpsi*psi*(1-psi); finalise with
+ *                       b2s_bn_bwd_finalize(C = 1) -> dgamma, dbeta, coef[3]
+ *   b2s_psi_bwd_apply   dv = coef0 * (g - coef1 - xhat*coef2)   (the gradient of every input map)
+ * b2s_pixel_scale_fwd: out[p,c] = x[p,c]*psi[p]; b2s_pixel_scale_bwd: dx = dy*psi, dpsi[p] = sum_c dy[p,c]*x[p,c]. */
+int b2s_psi_rows(long long n);
+int b2s_psi_stats(const float* const* maps, int n_maps, long long n, float* partial, void* stream);
+int b2s_psi_fwd(const float* const* maps, int n_maps, const float* scale, const float* shift, float* psi, long long n,
+                void* stream);
+int b2s_psi_bwd_reduce(const float* const* maps, int n_maps, const float* psi, const float* dpsi, const float* mean,
+                       const float* invstd, long long n, float* partial, void* stream);
+int b2s_psi_bwd_apply(const float* const* maps, int n_maps, const float* psi, const float* dpsi, const float* mean,
+                      const float* invstd, const float* coef, float* dv, long long n, void* stream);
+int b2s_pixel_scale_fwd(const void* x, int x_cstride, const float* psi, void* out, int out_cstride, long long npix, int C,
+                        void* stream);
+int b2s_pixel_scale_bwd(const void* x, int x_cstride, const float* psi, const void* dy, int dy_cstride, void* dx,
+                        int dx_cstride, float* dpsi, long long npix, int C, void* stream);
+/* F.interpolate(x, size=(Ho,Wo), mode='bilinear', align_corners=False) on NHWC bf16 (models/mod.py:61-62,126-127,
+ * 289-290: taken when H or W is not a multiple of 2^depth) and its input gradient (deterministic gather). */
+int b2s_bilinear_fwd(const void* x, int x_cstride, void* y, int y_cstride, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                     void* stream);
+int b2s_bilinear_bwd(const void* dy, int dy_cstride, void* dx, int dx_cstride, int N, int Hi, int Wi, int Ho, int Wo,
+                     int C, void* stream);
+/* Multi-channel input images (UNet(in_channels > 1), models/model.py:6,10): x [N,C,H*W] fp32 -> y [N,H*W,Cpad] bf16 with
+ * channels >= C zero; the first conv then takes the tensor-core path with its weight zero-padded to Cpad inputs. */
+int b2s_image_to_nhwc(const float* x, void* y, int N, int C, long long HW, int Cpad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

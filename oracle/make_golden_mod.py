@@ -19,10 +19,17 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     out = {"param_count_default": {"ResUNet": sum(p.numel() for p in R.ResUNet().parameters()),
                                    "UNet": sum(p.numel() for p in R.UNet().parameters())}}
+    out["param_count_default"]["AttentionUNet"] = sum(p.numel() for p in R.AttentionUNet().parameters())
     x, t = synth_batch(2, 32, 32, seed=1234)
-    for name, cls in (("ResUNet", R.ResUNet), ("UNet", R.UNet)):
+    xo, to = synth_batch(2, 36, 44, seed=1235)          # 36 -> 18 -> 9 -> 4: the up-sampled 8 != 9 takes the bilinear branch
+    g3 = torch.Generator().manual_seed(9)
+    x3 = torch.cat([x, torch.rand((2, 2, 32, 32), generator=g3)], dim=1)      # a 3-channel image
+    cases = (("ResUNet", R.ResUNet, {}, x, t), ("UNet", R.UNet, {}, x, t), ("AttentionUNet", R.AttentionUNet, {}, x, t),
+             ("UNet_odd", R.UNet, {}, xo, to), ("AttentionUNet_odd", R.AttentionUNet, {}, xo, to),
+             ("ResUNet_rgb", R.ResUNet, {"in_channels": 3}, x3, t), ("UNet_rgb", R.UNet, {"in_channels": 3}, x3, t))
+    for name, cls, kw, x, t in cases:
         torch.manual_seed(42)
-        net = cls(depth=3)
+        net = cls(depth=3, **kw)
         net.train()
         sd0 = net.state_dict()
         case = dict(depth=3, x=x, t=t, state_dict_keys=list(sd0.keys()),

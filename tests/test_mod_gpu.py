@@ -70,14 +70,88 @@ def test_residual_block_forward_backward():
         assert rel < 0.05, f"{k}: rel L2 {rel}"
 
 
-@pytest.mark.parametrize("name", ["ResUNet", "UNet"])
+def test_bilinear_resize_forward_backward():
+    """b2s_bilinear_fwd/bwd (models/mod.py:61-62) against F.interpolate on the same bf16-representable values"""
+    import b200seg  # noqa: F401
+    from b200seg import vnet_functional as VF
+    g = torch.Generator().manual_seed(5)
+    for (hi, wi, ho, wo) in ((8, 10, 9, 11), (4, 5, 9, 11), (16, 16, 17, 19), (9, 11, 8, 10)):
+        x = torch.randn((2, 64, hi, wi), generator=g).to(torch.bfloat16).float()
+        dy = torch.randn((2, 64, ho, wo), generator=g).to(torch.bfloat16).float()
+        xg = nhwc(x).requires_grad_(True)
+        y = VF.Bilinear.apply(xg, ho, wo)
+        y.backward(nhwc(dy))
+        torch.cuda.synchronize()
+        xr = x.clone().requires_grad_(True)
+        yr = torch.nn.functional.interpolate(xr, size=(ho, wo), mode="bilinear", align_corners=False)
+        yr.backward(dy)
+        assert float((nchw(y.detach()) - yr.detach()).abs().max()) <= 2 ** -8 * float(yr.abs().max()) + 1e-6
+        assert float((nchw(xg.grad) - xr.grad).abs().max()) <= 2 ** -8 * float(xr.grad.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("ch", [64, 128, 1024])
+def test_attention_gate_forward_backward(ch):
+    """AttentionGate (models/mod.py:211-234) incl. the zero-padded F_int = 32 case and the 512-channel psi conv"""
+    import b200seg  # noqa: F401
+    from b200seg.models.mod import AttentionGate
+    torch.manual_seed(3)
+    gate = AttentionGate(ch, ch, ch // 2).train()
+    with torch.no_grad():
+        for m in gate.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    sd = {k: v.detach().clone() for k, v in gate.state_dict().items()}
+    gen = torch.Generator().manual_seed(4)
+    g_in = torch.randn((2, ch, 8, 12), generator=gen).to(torch.bfloat16).float()
+    x = torch.randn((2, ch, 8, 12), generator=gen).to(torch.bfloat16).float()
+    dy = torch.randn((2, ch, 8, 12), generator=gen).to(torch.bfloat16).float()
+    gate = gate.to(DEV)
+    gg, xg = nhwc(g_in).requires_grad_(True), nhwc(x).requires_grad_(True)
+    y = gate.forward_nhwc(gg, xg)
+    y.backward(nhwc(dy))
+    torch.cuda.synchronize()
+    P = {f"a.{k}": (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    gr, xr = g_in.double().requires_grad_(True), x.double().requires_grad_(True)
+    stats = {}
+    yr = M.attention_gate(P, "a", gr, xr, True, O.bf16_round, stats)
+    yr.backward(dy.double())
+    err = (nchw(y.detach()).double() - yr.detach()).abs()
+    assert float(err.max()) < 2 ** -7 * float(yr.abs().max()) + 1e-2, float(err.max())
+    for name, got, ref in (("dx", xg.grad, xr.grad), ("dg", gg.grad, gr.grad)):
+        rel = float((nchw(got).double() - ref).norm() / ref.norm())
+        assert rel < 0.05, f"{name} rel L2 {rel}"
+    for k, p in gate.named_parameters():
+        ref = P[f"a.{k}"].grad
+        if k.endswith("0.bias") and "psi" not in k or k == "psi.0.bias":
+            continue           # a conv bias in front of train-mode BatchNorm: the exact gradient is zero
+        rel = float((p.grad.double().cpu() - ref).norm() / (ref.norm() + 1e-30))
+        assert rel < 0.06, f"{k}: rel L2 {rel}"
+    # running statistics of the three BatchNorms (incl. the copy-back from the zero-padded buffers)
+    from oracle.vnet_oracle import running_stats_update
+    upd = running_stats_update({k: v.detach() for k, v in P.items()}, stats)
+    new = gate.state_dict()
+    for k, v in upd.items():
+        assert float((new[k[2:]].cpu().double() - v).abs().max()) < 1e-2 * max(1.0, float(v.abs().max())), k
+
+
+CASES = {"ResUNet": ("ResUNet", {}, M.resunet_forward), "UNet": ("UNet", {}, M.unet_forward),
+         "AttentionUNet": ("AttentionUNet", {}, M.attention_unet_forward),
+         "UNet_odd": ("UNet", {}, M.unet_forward), "AttentionUNet_odd": ("AttentionUNet", {}, M.attention_unet_forward),
+         "ResUNet_rgb": ("ResUNet", {"in_channels": 3}, M.resunet_forward),
+         "UNet_rgb": ("UNet", {"in_channels": 3}, M.unet_forward)}
+
+
+@pytest.mark.parametrize("name", list(CASES))
 def test_whole_net_train_step_and_eval_mask(name):
     import b200seg  # noqa: F401
     from b200seg.models import mod
     from b200seg.models.loss import BCEDiceLoss
     g = torch.load(GOLDEN, weights_only=False)[name]
+    cls, kw, fwd = CASES[name]
     torch.manual_seed(42)
-    net = getattr(mod, name)(depth=3)
+    net = getattr(mod, cls)(depth=3, **kw)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.to(DEV).train()
     logits = net(g["x"].to(DEV))
@@ -86,7 +160,6 @@ def test_whole_net_train_step_and_eval_mask(name):
     torch.cuda.synchronize()
     P = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
          for k, v in sd.items()}
-    fwd = M.resunet_forward if name == "ResUNet" else M.unet_forward
     lq = fwd(P, g["x"].double(), 3, train=True, q=O.bf16_round)
     Lq = O.seg_loss(lq.detach(), g["t"].double())
     assert float((logits.detach().cpu().double() - lq.detach()).abs().mean()) < 1e-2
@@ -96,6 +169,8 @@ def test_whole_net_train_step_and_eval_mask(name):
     stats = {}
     for k, p in net.named_parameters():
         ref = P[k].grad
+        if ref is None or float(ref.norm()) < 1e-12:
+            continue           # conv biases in front of train-mode BatchNorm (AttentionGate): exact gradient zero
         gg = p.grad.double().cpu()
         stats[k] = (float((gg - ref).norm() / (ref.norm() + 1e-30)), float((gg * ref).sum() / (gg.norm() * ref.norm() + 1e-30)))
     rels = sorted(v[0] for v in stats.values()); coss = sorted(v[1] for v in stats.values())

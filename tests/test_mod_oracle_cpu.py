@@ -17,14 +17,23 @@ def mg():
     return torch.load(GOLDEN, weights_only=False)
 
 
+# golden case -> (drop-in class, constructor kwargs, oracle forward)
+CASES = {"ResUNet": ("ResUNet", {}, M.resunet_forward), "UNet": ("UNet", {}, M.unet_forward),
+         "AttentionUNet": ("AttentionUNet", {}, M.attention_unet_forward),
+         "UNet_odd": ("UNet", {}, M.unet_forward), "AttentionUNet_odd": ("AttentionUNet", {}, M.attention_unet_forward),
+         "ResUNet_rgb": ("ResUNet", {"in_channels": 3}, M.resunet_forward),
+         "UNet_rgb": ("UNet", {"in_channels": 3}, M.unet_forward)}
+
+
 def build(name):
     import b200seg  # noqa: F401
     from b200seg.models import mod
+    cls, kw, _ = CASES[name]
     torch.manual_seed(42)
-    return getattr(mod, name)(depth=3)
+    return getattr(mod, cls)(depth=3, **kw)
 
 
-@pytest.mark.parametrize("name", ["ResUNet", "UNet"])
+@pytest.mark.parametrize("name", list(CASES))
 def test_layout_init_and_forward_match_reference(mg, name):
     g = mg[name]
     net = build(name)
@@ -33,7 +42,7 @@ def test_layout_init_and_forward_match_reference(mg, name):
     for k, d in g["init_digest"].items():
         assert abs(float(sd[k].double().sum()) - d["sum"]) <= 1e-9 * max(1.0, d["abs_sum"]), k
     P = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
-    fwd = M.resunet_forward if name == "ResUNet" else M.unet_forward
+    fwd = CASES[name][2]
     stats = {}
     logits = fwd(P, g["x"].double(), 3, train=True, stats_out=stats)
     assert float((logits - g["logits"].double()).abs().max()) < 2e-4
@@ -50,6 +59,21 @@ def test_default_parameter_counts(mg):
     from b200seg.models import mod
     assert sum(p.numel() for p in mod.ResUNet().parameters()) == mg["param_count_default"]["ResUNet"]
     assert sum(p.numel() for p in mod.UNet().parameters()) == mg["param_count_default"]["UNet"]
+    assert sum(p.numel() for p in mod.AttentionUNet().parameters()) == mg["param_count_default"]["AttentionUNet"]
+
+
+def test_bilinear_resize_matches_torch():
+    """the oracle's restatement of F.interpolate(mode='bilinear', align_corners=False), values and gradient"""
+    g = torch.Generator().manual_seed(2)
+    for (hi, wi, ho, wo) in ((8, 10, 9, 11), (4, 5, 9, 11), (7, 7, 5, 3), (6, 6, 6, 6)):
+        x = torch.randn((2, 3, hi, wi), generator=g, dtype=torch.float64, requires_grad=True)
+        dy = torch.randn((2, 3, ho, wo), generator=g, dtype=torch.float64)
+        y = M.bilinear_resize(x, ho, wo)
+        y.backward(dy)
+        xr = x.detach().clone().requires_grad_(True)
+        yr = torch.nn.functional.interpolate(xr, size=(ho, wo), mode="bilinear", align_corners=False)
+        yr.backward(dy)
+        assert float((y - yr).abs().max()) < 1e-12 and float((x.grad - xr.grad).abs().max()) < 1e-12
 
 
 def test_first_max_pool_gradient():

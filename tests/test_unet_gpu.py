@@ -383,3 +383,42 @@ def test_graft_entry_smoke():
     """the driver's round-end smoke (one small forward + loss + backward on cuda:0 checked against the oracle)"""
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_multichannel_input_unet():
+    """UNet(in_channels=3) (reference models/model.py:6,10): the image is stored as NHWC bf16 (zero-padded to 64
+    channels) and encoder1.0 runs on the tensor cores with a zero-padded bf16 weight — the oracle is given the same
+    rounded image and first weight."""
+    import b200seg  # noqa: F401
+    from b200seg.models.model import UNet
+    from b200seg.models.loss import BCEDiceLoss
+    torch.manual_seed(42)
+    net = UNet(in_channels=3, out_channels=1)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    assert sd["encoder1.0.weight"].shape == (64, 3, 3, 3)
+    net = net.to(DEV).train()
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand((2, 3, 32, 48), generator=g)
+    _, t = O.synth_batch(2, 32, 48, seed=5)
+    logits = net(x.to(DEV))
+    loss = BCEDiceLoss()(logits, t.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    P = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    P["encoder1.0.weight"] = O.bf16_round(P["encoder1.0.weight"])
+    cache = {}
+    lq = O.unet_forward(P, O.bf16_round(x.double()), train=True, q=O.bf16_round, cache=cache)
+    Lq = O.seg_loss(lq, t.double())
+    Gq = O.unet_backward(P, cache, Lq["dlogits"], q=O.bf16_round)
+    assert float((logits.detach().cpu().double() - lq).abs().mean()) < 6e-3
+    assert abs(float(loss) - float(Lq["total"])) < 1e-3
+    named = dict(net.named_parameters())
+    for k in ("final.1.weight", "final.0.3.weight"):
+        assert rel_l2(named[k].grad, Gq[k]) < 0.1, k
+    g0 = named["encoder1.0.weight"].grad
+    assert g0.shape == (64, 3, 3, 3) and bool(torch.isfinite(g0).all())
+    assert cosine(g0, Gq["encoder1.0.weight"]) > 0.7
+    net.eval()
+    with torch.no_grad():
+        le, mask = net.predict_mask(x.to(DEV))
+    assert torch.equal(mask.bool(), torch.sigmoid(le) > 0.5)

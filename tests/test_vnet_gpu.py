@@ -349,3 +349,29 @@ def test_vnet_eval_logits_and_mask(vnet_case):
     assert bool((mask.cpu().bool()[band] == A["eval_mask"][band]).all()), f"mask differs outside the band ({inside} px inside)"
     # the mask is the thresholded logits of THIS run, bit-exactly
     assert torch.equal(mask.cpu().bool(), O.threshold_mask(le))
+
+
+def test_vnet_multichannel_input():
+    """ImprovedVNet(in_channels=3): zero-padded NHWC bf16 image, zero-padded first conv / projection weights"""
+    import b200seg  # noqa: F401
+    from b200seg.models.vnet import ImprovedVNet
+    from b200seg.models.loss import BCEDiceLoss
+    torch.manual_seed(42)
+    net = ImprovedVNet(in_channels=3, dropout_rate=0.0)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV).train()
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand((2, 3, 32, 32), generator=g)
+    _, t = O.synth_batch(2, 32, 32, seed=5)
+    logits = net(x.to(DEV))
+    BCEDiceLoss()(logits, t.to(DEV)).backward()
+    torch.cuda.synchronize()
+    P = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    for b in range(3):          # the tensors that read the image are stored in bf16 on this path
+        for k in (f"enc_blocks.{b}.0.convs.0.weight", f"enc_blocks.{b}.0.res_proj.weight"):
+            P[k] = O.bf16_round(P[k])
+    lq = V.vnet_forward(P, O.bf16_round(x.double()), train=True, q=O.bf16_round)
+    assert float((logits.detach().cpu().double() - lq).abs().mean()) < 1e-2
+    for k, p in net.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape and bool(torch.isfinite(p.grad).all()), k
+    assert float(dict(net.named_parameters())["enc_blocks.0.0.convs.0.weight"].grad.abs().sum()) > 0

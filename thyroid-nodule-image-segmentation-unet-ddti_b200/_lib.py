@@ -72,6 +72,16 @@ SIGNATURES = {
     "b2s_se_fc_fwd": (I, [P, I, LL, P, P, P, P, P, P, P, I, I, I, P]),
     "b2s_se_scale": (I, [P, I, P, P, F, P, I, I, LL, I, P]),
     "b2s_se_fc_bwd": (I, [P, I, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "b2s_psi_rows": (I, [LL]),
+    "b2s_psi_stats": (I, [P, I, LL, P, P]),
+    "b2s_psi_fwd": (I, [P, I, P, P, P, LL, P]),
+    "b2s_psi_bwd_reduce": (I, [P, I, P, P, P, P, LL, P, P]),
+    "b2s_psi_bwd_apply": (I, [P, I, P, P, P, P, P, P, LL, P]),
+    "b2s_pixel_scale_fwd": (I, [P, I, P, P, I, LL, I, P]),
+    "b2s_pixel_scale_bwd": (I, [P, I, P, P, I, P, I, P, LL, I, P]),
+    "b2s_bilinear_fwd": (I, [P, I, P, I, I, I, I, I, I, I, P]),
+    "b2s_bilinear_bwd": (I, [P, I, P, I, I, I, I, I, I, I, P]),
+    "b2s_image_to_nhwc": (I, [P, P, I, I, LL, I, P]),
 }
 
 

@@ -65,8 +65,15 @@ static inline int make_tmap(CUtensorMap* m, const void* base, int rank, const ui
   if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(B2S_ERR_ARG, "tensor base not 16-B aligned");
   for (int i = 0; i + 1 < rank; ++i)
     if (gstr[i] & 15) return set_error(B2S_ERR_ARG, "tensor stride not a multiple of 16 B");
+  // L2 promotion: a 128-byte box row (64 channels) is promoted to a 256-byte DRAM fetch only when the neighbouring
+  // 128 bytes belong to the same tensor view (the view covers whole pixel records, so another k-chunk / tap of the same
+  // kernel reads them next). For a channel SLICE of a wider buffer (the up-conv half of a concat gradient: 128 B of every
+  // 256-B record) the promoted half is never used: ncu showed 2.0x the algorithmic DRAM reads in the transposed-conv
+  // dgrad / wgrad (1.05 GB for 537 MB).
+  const bool whole_records = rank < 2 || dims[0] * 2 == strides_b[0];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  whole_records ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[256];

@@ -1453,7 +1453,8 @@ extern "C" int b2s_bn_apply(const void* r, int r_cstride, const float* scale, co
 
 extern "C" int b2s_maxpool2x2(const void* x, int x_cstride, void* pooled, int N, int H, int W, int C, void* stream) {
   if (!x || !pooled) return set_error(B2S_ERR_ARG, "b2s_maxpool2x2: null pointer");
-  if (C % 8 || x_cstride % 8 || H % 2 || W % 2) return set_error(B2S_ERR_ARG, "b2s_maxpool2x2: need C % 8 == 0, even H and W");
+  // odd H / W: floor semantics of F.max_pool2d (the last row / column is not pooled)
+  if (C % 8 || x_cstride % 8 || H < 2 || W < 2) return set_error(B2S_ERR_ARG, "b2s_maxpool2x2: need C % 8 == 0, H, W >= 2");
   const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   count_launch();
   maxpool2x2_kernel<<<grid_for(items, kThreads * 2), kThreads, 0, STREAM(stream)>>>(

@@ -666,8 +666,9 @@ extern "C" int b2s_relu_bwd(const void* dy, int dy_cstride, const void* y, int y
 extern "C" int b2s_maxpool2x2_bwd(const void* x, int x_cstride, const void* dpool, int dpool_cstride, void* dx,
                                   int dx_cstride, int N, int H, int W, int C, void* stream) {
   if (!x || !dpool || !dx) return set_error(B2S_ERR_ARG, "b2s_maxpool2x2_bwd: null pointer");
-  if (C % 8 || x_cstride % 8 || dpool_cstride % 8 || dx_cstride % 8 || H % 2 || W % 2)
-    return set_error(B2S_ERR_ARG, "b2s_maxpool2x2_bwd: need C % 8 == 0, even H and W");
+  // odd H / W: the last row / column receives no gradient; the caller zero-fills dx in that case
+  if (C % 8 || x_cstride % 8 || dpool_cstride % 8 || dx_cstride % 8 || H < 2 || W < 2)
+    return set_error(B2S_ERR_ARG, "b2s_maxpool2x2_bwd: need C % 8 == 0, H, W >= 2");
   const long long items = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   count_launch();
   maxpool2x2_bwd_kernel<<<ew_grid_for(items, kThreads * 2), kThreads, 0, STREAM(stream)>>>(

@@ -52,8 +52,12 @@ class UNetPlan:
         if H % 16 or W % 16:
             raise RuntimeError(f"Sizes of tensors must match: H={H}, W={W} must be multiples of 16 "
                                "(reference models/model.py:64 torch.cat)")
-        if in_channels != 1:
-            raise NotImplementedError("the B200 path implements the reference default in_channels=1")
+        if not 1 <= in_channels <= 64:
+            raise NotImplementedError("the B200 path implements 1 <= in_channels <= 64")
+        # in_channels > 1: the image is converted once to NHWC bf16 zero-padded to 64 channels and encoder1.0 takes the
+        # tensor-core conv with its weight zero-padded to 64 inputs (in_channels = 1 keeps the fp32 Cin = 1 kernels)
+        self.Cin = in_channels
+        self.x_act = Act.empty(N, H, W, 64, device) if in_channels > 1 else None
         self.N, self.H, self.W, self.device = N, H, W, device
         self.O = out_channels
         f32 = dict(dtype=torch.float32, device=device)
@@ -65,6 +69,8 @@ class UNetPlan:
         self.stages = {}
         for (name, idx, cin, cout, l) in conv_stages():
             s = _Stage()
+            if cin is None and in_channels > 1:
+                cin = 64
             s.name, s.idx, s.cin, s.cout, s.level = name, idx, cin, cout, l
             s.r = A(l, cout)
             s.y = None
@@ -112,6 +118,8 @@ class UNetPlan:
         self.dpool = [A(l + 1, dims[l][2]) for l in range(4)]
         ws_bytes = 0
         for (name, idx, cin, cout, l) in conv_stages():
+            if cin is None and self.Cin > 1:
+                cin = 64
             if cin is None:
                 continue
             nb, _ = ops.wgrad_workspace(N, dims[l][0], dims[l][1], cin, cout, 9)
@@ -133,11 +141,11 @@ class UNetEngine:
         self._pack_state = {}
 
     # ---- plumbing -----------------------------------------------------------------------------------------
-    def plan(self, N, H, W, device, train):
-        key = (N, H, W, str(device))
+    def plan(self, N, H, W, device, train, in_channels=1):
+        key = (N, H, W, str(device)) if in_channels == 1 else (N, H, W, str(device), in_channels)
         p = self.plans.get(key)
         if p is None:
-            p = UNetPlan(N, H, W, device, out_channels=self.O, train_buffers=train)
+            p = UNetPlan(N, H, W, device, in_channels=in_channels, out_channels=self.O, train_buffers=train)
             self.plans[key] = p
         if train:
             p._alloc_train()
@@ -180,16 +188,22 @@ class UNetEngine:
         """x [N,1,H,W] fp32 CUDA. Returns (logits fp32 [N,O,H,W], plan). P: name -> tensor (params and BN buffers)."""
         if not x.is_cuda:
             raise ops._lib.B2SError("UNetEngine.forward needs a CUDA tensor: the B200 path has no CPU fallback")
-        if x.dim() != 4 or x.shape[1] != 1:
-            raise RuntimeError(f"expected input [N,1,H,W], got {tuple(x.shape)}")
+        cin = P["encoder1.0.weight"].shape[1]
+        if x.dim() != 4 or x.shape[1] != cin:
+            raise RuntimeError(f"expected input [N,{cin},H,W], got {tuple(x.shape)}")
         need_backward = train if need_backward is None else need_backward
         N, _, H, W = x.shape
-        pl = self.plan(N, H, W, x.device, need_backward)
+        pl = self.plan(N, H, W, x.device, need_backward, in_channels=cin)
         pl.generation += 1
         x = x.contiguous().float()
         pl.x = x
         # nn.DataParallel replicas get fresh broadcast copies of the parameters every forward: never reuse a pack
         pl.packed = self._pack_weights(P, need_dgrad=need_backward, cache=cache_packed)
+        if cin > 1:
+            ops.image_to_nhwc(x, 64, out=pl.x_act)
+            wpad = torch.nn.functional.pad(P["encoder1.0.weight"].detach(), (0, 0, 0, 0, 0, 64 - cin))
+            pl.packed = dict(pl.packed)
+            pl.packed["encoder1.0.weight"] = (ops.pack_conv_weight(wpad, want_dgrad=False)[0], None)
         count = lambda l: float(N * pl.dims[l][0] * pl.dims[l][1])
 
         def stage(name, idx, xin, pooled=None):
@@ -234,7 +248,7 @@ class UNetEngine:
             s0 = stage(name, 0, xin)
             return stage(name, 3, s0.y, pooled)
 
-        cur = None
+        cur = pl.x_act           # None for in_channels = 1: encoder1.0 then runs the fp32 Cin = 1 kernels on x
         for l, name in enumerate(ENC):
             block(name, cur, pl.pooled[l])
             cur = pl.pooled[l]
@@ -283,6 +297,12 @@ class UNetEngine:
             wname = f"{name}.{idx}.weight"
             if s.x is None:
                 ops.conv3x3_c1_wgrad(pl.x, dz, pl.c1_partial, pl.scratch, G[wname])
+                ready(wname)
+                return
+            if dx_out is None:      # encoder1.0 of a multi-channel image: padded weight gradient, no input gradient
+                tmp = torch.empty((s.cout, 64, 3, 3), dtype=torch.float32, device=dz.buf.device)
+                ops.conv3x3_wgrad(s.x, dz, pl.wgrad_ws, tmp)
+                G[wname].copy_(tmp[:, :pl.Cin])
                 ready(wname)
                 return
             ops.conv3x3_wgrad(s.x, dz, pl.wgrad_ws, G[wname])

@@ -14,6 +14,7 @@ import itertools
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import vnet_functional as VF
 from ..ops import BF16
@@ -81,16 +82,21 @@ class ConvBlock(nn.Module):
         return (self._seed_base + 7919 * i) & 0xFFFFFFFF
 
     def forward_nhwc(self, x):
-        """x: NHWC bf16, or the fp32 image [N,1,H,W] when in_channels == 1"""
+        """x: NHWC bf16, or the fp32 image [N,1,H,W] when in_channels == 1. For 1 < in_channels < 64 the caller passes
+        the image zero-padded to 64 NHWC channels (VF.ImageToAct) and the weights reading it are zero-padded here (the
+        gradient of the real input channels flows back through autograd's slice)."""
+        cin = self.convs[0].weight.shape[1]
+        pad = (lambda w: F.pad(w, (0, 0, 0, 0, 0, 64 - cin))) if 1 < cin < 64 else (lambda w: w)
         if self.res_proj is not None:
-            residual = VF.Conv1x1.apply(x, self.res_proj.weight, self.res_proj.bias)
+            residual = VF.Conv1x1.apply(x, pad(self.res_proj.weight), self.res_proj.bias)
         else:
             residual = x
         p = float(self.drop.p)
         n = len(self.convs)
         for i, (conv, bn) in enumerate(zip(self.convs, self.bns)):
             res = residual if i == n - 1 else None       # the residual add is fused into the last stage's apply pass
-            x = VF.ConvBnAct.apply(x, res, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+            w = pad(conv.weight) if i == 0 else conv.weight
+            x = VF.ConvBnAct.apply(x, res, w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                    bn.num_batches_tracked, self.training, p, self._layer_seed(i) if (self.training and p > 0) else 0, 1)
         return x
 
@@ -134,9 +140,9 @@ class ImprovedVNet(nn.Module):
         ])
         self.dec_se_final = SEBlock(filters[0], reduction=se_reduction)
         self.final_conv = nn.Conv2d(filters[0], num_classes, kernel_size=1)
-        if in_channels != 1 or base_num_filters % 64:
-            raise NotImplementedError("the B200 path implements in_channels=1 and base_num_filters a multiple of 64 "
-                                      "(the reference defaults)")
+        if not 1 <= in_channels <= 64 or base_num_filters % 64:
+            raise NotImplementedError("the B200 path implements 1 <= in_channels <= 64 and base_num_filters a multiple "
+                                      "of 64")
 
     def _pack_all_weights(self):
         """bf16 GEMM operands of every tensor-core conv / transposed-conv weight, refreshed in a few launches whenever
@@ -177,6 +183,8 @@ class ImprovedVNet(nn.Module):
         if x.shape[2] % 16 or x.shape[3] % 16:
             raise RuntimeError("Sizes of tensors must match except in dimension 1: H and W must be multiples of 16")
         x = x.float().contiguous()
+        if self.in_channels > 1:
+            x = VF.ImageToAct.apply(x)
         nb = self.num_branches
         feats = [[None] * 5 for _ in range(nb)]
         for b in range(nb):

@@ -553,3 +553,103 @@ def se_backward(dy, x, mean, hidden, gate, w1, w2, dx):
         L.b2s_se_scale(dy.ptr, dy.cstride, _p(gate), _p(dmean), 1.0 / HW, dx.ptr, dx.cstride, N, HW, C, _stream()),
         "b2s_se_scale"))
     return dw1, db1, dw2, db2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# models/mod.py AttentionGate, bilinear re-size branch, multi-channel input images
+# ---------------------------------------------------------------------------------------------------------
+def _map_ptrs(maps):
+    arr = (ctypes.c_void_p * 4)()
+    for i, m in enumerate(maps):
+        assert m.dtype == torch.float32 and m.is_contiguous() and m.numel() == maps[0].numel()
+        arr[i] = m.data_ptr()
+    return arr
+
+
+def psi_forward(maps, gamma, beta, rm, rv, nbt, training):
+    """psi = sigmoid(BatchNorm2d(1)(sum(maps))) (models/mod.py:223-227,233). maps: 1..4 fp32 tensors [N,1,H,W].
+    Returns (psi, mean, invstd); mean / invstd are None in eval mode."""
+    L = _lib.lib()
+    _need_cuda(*maps)
+    n = maps[0].numel()
+    dev = maps[0].device
+    f32 = dict(dtype=torch.float32, device=dev)
+    arr = _map_ptrs(maps)
+    scale, shift = torch.empty(1, **f32), torch.empty(1, **f32)
+    mean = invstd = None
+    if training:
+        rows = L.b2s_psi_rows(n)
+        partial = torch.empty(rows * 2, **f32)
+        scratch = torch.empty(128 * 2, **f32)
+        mean, invstd = torch.empty(1, **f32), torch.empty(1, **f32)
+        _timed("psi_stats", "hbm", 4.0 * n * len(maps), lambda: check(
+            L.b2s_psi_stats(arr, len(maps), n, _p(partial), _stream()), "b2s_psi_stats"))
+        bn_finalize(partial, rows, 1, float(n), gamma, beta, rm, rv, nbt, 0.1, 1e-5, scale, shift, mean, invstd, scratch)
+    else:
+        bn_eval_affine(gamma, beta, rm, rv, 1e-5, scale, shift)
+    psi = torch.empty_like(maps[0])
+    _timed("psi_fwd", "hbm", 4.0 * n * (len(maps) + 1), lambda: check(
+        L.b2s_psi_fwd(arr, len(maps), _p(scale), _p(shift), _p(psi), n, _stream()), "b2s_psi_fwd"))
+    return psi, mean, invstd
+
+
+def psi_backward(maps, psi, dpsi, mean, invstd, gamma):
+    """returns (dv [same shape as a map], dgamma [1], dbeta [1])"""
+    L = _lib.lib()
+    n = psi.numel()
+    f32 = dict(dtype=torch.float32, device=psi.device)
+    arr = _map_ptrs(maps)
+    rows = L.b2s_psi_rows(n)
+    partial, scratch = torch.empty(rows * 2, **f32), torch.empty(128 * 2, **f32)
+    coef, dgamma, dbeta = torch.empty(3, **f32), torch.empty(1, **f32), torch.empty(1, **f32)
+    dpsi = dpsi.contiguous().float()
+    _timed("psi_bwd_reduce", "hbm", 4.0 * n * (len(maps) + 2), lambda: check(
+        L.b2s_psi_bwd_reduce(arr, len(maps), _p(psi), _p(dpsi), _p(mean), _p(invstd), n, _p(partial), _stream()),
+        "b2s_psi_bwd_reduce"))
+    check(L.b2s_bn_bwd_finalize(_p(partial), rows, 1, float(n), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta), _p(coef),
+                                _p(scratch), _stream()), "b2s_bn_bwd_finalize")
+    dv = torch.empty_like(psi)
+    _timed("psi_bwd_apply", "hbm", 4.0 * n * (len(maps) + 3), lambda: check(
+        L.b2s_psi_bwd_apply(arr, len(maps), _p(psi), _p(dpsi), _p(mean), _p(invstd), _p(coef), _p(dv), n, _stream()),
+        "b2s_psi_bwd_apply"))
+    return dv, dgamma, dbeta
+
+
+def pixel_scale_fwd(x, psi, out):
+    npix = x.N * x.H * x.W
+    assert psi.dtype == torch.float32 and psi.is_contiguous() and psi.numel() == npix
+    _timed("pixel_scale", "hbm", npix * (4.0 * x.C + 4.0), lambda: check(
+        _lib.lib().b2s_pixel_scale_fwd(x.ptr, x.cstride, _p(psi), out.ptr, out.cstride, npix, x.C, _stream()),
+        "b2s_pixel_scale_fwd"))
+
+
+def pixel_scale_bwd(x, psi, dy, dx, dpsi):
+    npix = x.N * x.H * x.W
+    _timed("pixel_scale_bwd", "hbm", npix * (6.0 * x.C + 8.0), lambda: check(
+        _lib.lib().b2s_pixel_scale_bwd(x.ptr, x.cstride, _p(psi), dy.ptr, dy.cstride, dx.ptr, dx.cstride, _p(dpsi), npix,
+                                       x.C, _stream()), "b2s_pixel_scale_bwd"))
+
+
+def bilinear_fwd(x, y):
+    _timed("bilinear", "hbm", 2.0 * x.C * x.N * (x.H * x.W + y.H * y.W), lambda: check(
+        _lib.lib().b2s_bilinear_fwd(x.ptr, x.cstride, y.ptr, y.cstride, x.N, x.H, x.W, y.H, y.W, x.C, _stream()),
+        "b2s_bilinear_fwd"))
+
+
+def bilinear_bwd(dy, dx):
+    _timed("bilinear_bwd", "hbm", 2.0 * dx.C * dx.N * (dx.H * dx.W + dy.H * dy.W), lambda: check(
+        _lib.lib().b2s_bilinear_bwd(dy.ptr, dy.cstride, dx.ptr, dx.cstride, dx.N, dx.H, dx.W, dy.H, dy.W, dx.C, _stream()),
+        "b2s_bilinear_bwd"))
+
+
+def image_to_nhwc(x, cpad=64, out=None):
+    """x [N,C,H,W] fp32 -> Act [N,H,W,cpad] bf16 (channels >= C zero)"""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 4
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    y = out if out is not None else Act.empty(N, H, W, cpad, x.device)
+    assert y.c0 == 0 and y.C == y.cstride == cpad
+    _timed("image_to_nhwc", "hbm", N * H * W * (4.0 * C + 2.0 * cpad), lambda: check(
+        _lib.lib().b2s_image_to_nhwc(_p(x), y.ptr, N, C, H * W, cpad, _stream()), "b2s_image_to_nhwc"))
+    return y

@@ -84,9 +84,14 @@ def _bn_affine(training, stats, rows, count, gamma, beta, rm, rv, nbt, C, device
     return scale, shift, mean, invstd
 
 
-class ConvBnAct(torch.autograd.Function):
-    """out = dropout(relu(BN(conv3x3(x) + b))) (+ res)      models/vnet.py:51-59 (one loop trip, + the residual add)
+_PAIR = 1 << 10          # conv entry points' tile_n flag: force the tile-pair kernel (its partial-statistics row count
+                         # is the one b2s_conv_stats_rows reports for the same flag, also for 1x1 convs)
 
+
+class ConvBnAct(torch.autograd.Function):
+    """out = dropout(relu(BN(conv(x) + b))) (+ res)      models/vnet.py:51-59 (one loop trip, + the residual add)
+
+    The conv is 3x3 (pad 1) or 1x1, read off w (AttentionGate's W_g / W_x are 1x1 conv + BN, models/mod.py:214-221).
     x: NHWC bf16 activation, or the fp32 image [N,1,H,W] for the first conv of a branch (Cin = 1 kernel)."""
 
     @staticmethod
@@ -110,10 +115,12 @@ class ConvBnAct(torch.autograd.Function):
             stats = torch.empty(rows * 2 * Cout, dtype=torch.float32, device=dev) if training else None
             ops.conv3x3_c1_fwd(x, w.detach(), bias, za, relu=False, stats=stats)
         else:
+            k = w.shape[2]
+            tile_n = 0 if k == 3 else _PAIR
             wf, _ = packed_conv(w, False)
-            rows = ops.conv_stats_rows(N, H, W, Cout)
+            rows = ops.conv_stats_rows(N, H, W, Cout, tile_n)
             stats = torch.empty(rows * 2 * Cout, dtype=torch.float32, device=dev) if training else None
-            ops.conv_fwd(xa, wf, bias, za, ksize=3, relu=False, stats=stats)
+            ops.conv_fwd(xa, wf, bias, za, ksize=k, relu=False, stats=stats, tile_n=tile_n)
         scale, shift, mean, invstd = _bn_affine(training, stats, rows, float(N * H * W), gamma.detach(), beta.detach(),
                                                 rm, rv, nbt, Cout, dev)
         out = new_act(N, H, W, Cout, dev)
@@ -148,7 +155,8 @@ class ConvBnAct(torch.autograd.Function):
         dgamma, dbeta, dbias = torch.empty(Cout, **f32), torch.empty(Cout, **f32), torch.empty(Cout, **f32)
         ops.bn_act_bwd(da, za, scale, shift, mean, invstd, gamma.detach(), float(N * H * W), Act(dz), dgamma, dbeta,
                        dbias, relu=1 if relu_mode == 1 else 0, dropout_p=p_drop, seed=seed, step_counter=ctx.nbt)
-        dw = torch.empty((Cout, Cin, 3, 3), **f32)
+        k = w.shape[2]
+        dw = torch.empty((Cout, Cin, k, k), **f32)
         dx = None
         if first:
             rows = ops.c1_rows(N, H, W)
@@ -157,13 +165,16 @@ class ConvBnAct(torch.autograd.Function):
             ops.conv3x3_c1_wgrad(x, Act(dz), partial, scratch, dw)
         else:
             xa = as_act(x)
-            nbytes, _ = ops.wgrad_workspace(N, H, W, Cin, Cout, 9)
-            ws = torch.empty(nbytes // 4, **f32)
-            ops.conv3x3_wgrad(xa, Act(dz), ws, dw)
+            if k == 3:
+                nbytes, _ = ops.wgrad_workspace(N, H, W, Cin, Cout, 9)
+                ws = torch.empty(nbytes // 4, **f32)
+                ops.conv3x3_wgrad(xa, Act(dz), ws, dw)
+            else:
+                ops.conv1x1_wgrad(xa, Act(dz), dw)
             if ctx.needs_input_grad[0]:
                 _, wd = packed_conv(w, True)
                 dx = new_act(N, H, W, Cin, dev)
-                ops.conv_fwd(Act(dz), wd, None, Act(dx), ksize=3)
+                ops.conv_fwd(Act(dz), wd, None, Act(dx), ksize=k)
         dres = dout if has_res else None
         return dx, dres, dw, (dbias if has_bias else None), dgamma, dbeta, None, None, None, None, None, None, None
 
@@ -339,6 +350,8 @@ class MaxPool2x2(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         xa = as_act(x)
         dx = new_act(xa.N, xa.H, xa.W, xa.C, x.device)
+        if xa.H % 2 or xa.W % 2:       # floor pooling: the last row / column is outside every window (zero gradient)
+            dx.zero_()
         ops.maxpool2x2_bwd(xa, as_act(dout), Act(dx))
         return dx
 
@@ -391,8 +404,10 @@ class Head(torch.autograd.Function):
         xa = as_act(x)
         O = w.shape[0]
         logits = torch.empty((xa.N, O, xa.H, xa.W), dtype=torch.float32, device=w.device)
-        ops.head_fwd(xa, None, None, w.detach().reshape(O, -1).contiguous(), b.detach(), logits, None)
+        ops.head_fwd(xa, None, None, w.detach().reshape(O, -1).contiguous(), b.detach() if b is not None else None,
+                     logits, None)
         ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
         return logits
 
     @staticmethod
@@ -408,4 +423,82 @@ class Head(torch.autograd.Function):
         dwdb = torch.empty(O * C + O, **f32)
         ops.head_bwd(dlogits.contiguous().float(), xa, None, None, w.detach().reshape(O, C).contiguous(), Act(dx),
                      partial, scratch, dwdb)
-        return dx, dwdb[:O * C].view(O, C, 1, 1).clone(), dwdb[O * C:].clone()
+        return dx, dwdb[:O * C].view(O, C, 1, 1).clone(), (dwdb[O * C:].clone() if ctx.has_bias else None)
+
+
+class PsiGate(torch.autograd.Function):
+    """psi = sigmoid(BatchNorm2d(1)(sum(maps)))      AttentionGate.psi after its 1x1 conv (models/mod.py:223-227,233)
+
+    maps: the fp32 [N,1,H,W] outputs of the F_int -> 1 conv, one per channel slice of at most 256 channels (Head over a
+    slice); the kernels sum them on the fly."""
+
+    @staticmethod
+    def forward(ctx, gamma, beta, rm, rv, nbt, training, *maps):
+        maps = [m.contiguous() for m in maps]
+        psi, mean, invstd = ops.psi_forward(maps, gamma.detach(), beta.detach(), rm, rv, nbt, training)
+        ctx.training = training
+        if training:
+            ctx.save_for_backward(gamma, psi, mean, invstd, *maps)
+        return psi
+
+    @staticmethod
+    def backward(ctx, dpsi):
+        if not ctx.training:
+            raise RuntimeError("b200seg AttentionGate: backward through eval-mode BatchNorm is not implemented")
+        gamma, psi, mean, invstd, *maps = ctx.saved_tensors
+        dv, dgamma, dbeta = ops.psi_backward(maps, psi, dpsi, mean, invstd, gamma.detach())
+        return (dgamma, dbeta, None, None, None, None) + tuple(dv for _ in maps)
+
+
+class PixelScale(torch.autograd.Function):
+    """x * psi with psi [N,1,H,W] broadcast over the channels of the NHWC bf16 x (models/mod.py:234)"""
+
+    @staticmethod
+    def forward(ctx, x, psi):
+        xa = as_act(x)
+        out = new_act(xa.N, xa.H, xa.W, xa.C, x.device)
+        psi = psi.contiguous()
+        ops.pixel_scale_fwd(xa, psi, Act(out))
+        ctx.save_for_backward(x, psi)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, psi = ctx.saved_tensors
+        xa, dy = as_act(x), as_act(dout)
+        dx = new_act(xa.N, xa.H, xa.W, xa.C, x.device)
+        dpsi = torch.empty_like(psi)
+        ops.pixel_scale_bwd(xa, psi, dy, Act(dx), dpsi)
+        return dx, dpsi
+
+
+class Bilinear(torch.autograd.Function):
+    """F.interpolate(x, size=(Ho, Wo), mode='bilinear', align_corners=False) on NHWC bf16 (models/mod.py:61-62)"""
+
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        xa = as_act(x)
+        out = new_act(xa.N, Ho, Wo, xa.C, x.device)
+        ops.bilinear_fwd(xa, Act(out))
+        ctx.in_shape = (xa.N, xa.H, xa.W, xa.C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, H, W, C = ctx.in_shape
+        dx = new_act(N, H, W, C, dout.device)
+        ops.bilinear_bwd(as_act(dout), Act(dx))
+        return dx, None, None
+
+
+class ImageToAct(torch.autograd.Function):
+    """fp32 image [N,C,H,W] with 1 < C <= 64 -> NHWC bf16 [N,H,W,64], channels >= C zero (no input gradient: the
+    drop-in nets do not differentiate with respect to the image)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.image_to_nhwc(x.float(), 64).buf
+
+    @staticmethod
+    def backward(ctx, dout):
+        return None
