@@ -169,8 +169,11 @@ def test_whole_net_train_step_and_eval_mask(name):
     stats = {}
     for k, p in net.named_parameters():
         ref = P[k].grad
-        if ref is None or float(ref.norm()) < 1e-12:
-            continue           # conv biases in front of train-mode BatchNorm (AttentionGate): exact gradient zero
+        if ref is None or ("attn_gates" in k and k.endswith(".0.bias")):
+            continue           # conv biases in front of train-mode BatchNorm (AttentionGate): the exact gradient is zero
+        if ref.numel() == 1:
+            continue           # the one-channel BatchNorm of a gate: a cancelling sum of signed terms, no direction to compare
+                               # (checked to 6 % in test_attention_gate_forward_backward)
         gg = p.grad.double().cpu()
         stats[k] = (float((gg - ref).norm() / (ref.norm() + 1e-30)), float((gg * ref).sum() / (gg.norm() * ref.norm() + 1e-30)))
     rels = sorted(v[0] for v in stats.values()); coss = sorted(v[1] for v in stats.values())

@@ -151,6 +151,13 @@ class UNetEngine:
             p._alloc_train()
         return p
 
+    def packed_plan(self, P, need_dgrad=True):
+        """Packs now if needed and returns the PackPlan whose buffers the next forwards of P will read."""
+        self._pack_weights(P, need_dgrad=need_dgrad)
+        names = [k for k in P if k.endswith(".weight") and P[k].dim() == 4 and k != "encoder1.0.weight"
+                 and k != "final.1.weight"]
+        return self._pack_state[(str(P[names[0]].device), bool(need_dgrad))]["plan"]
+
     def invalidate_packed(self):
         """Call after parameters were updated outside torch (e.g. by b2s_adamw_step, which does not bump tensor
         version counters): forces the next forward to re-pack the bf16 operands."""
@@ -163,7 +170,9 @@ class UNetEngine:
         replicas of one module — sharing this engine object — concurrently, one thread per GPU."""
         names = [k for k in P if k.endswith(".weight") and P[k].dim() == 4 and k != "encoder1.0.weight"
                  and k != "final.1.weight"]
-        dev = str(P[names[0]].device)
+        # one state per (device, with / without the dgrad operands): an eval forward between two training steps must
+        # not replace the buffers a captured training graph or TrainStep's per-bucket re-pack points at
+        dev = (str(P[names[0]].device), bool(need_dgrad))
         st = self._pack_state.setdefault(dev, {"versions": None, "layout": None, "plan": None})
         # (identity, address, version): a freed tensor's address can be handed to a new tensor at version 0, so the
         # owning tensor object is part of the key (the plan keeps the tensors it packed alive, ids cannot be reused)
@@ -306,9 +315,10 @@ class UNetEngine:
                 ready(wname)
                 return
             ops.conv3x3_wgrad(s.x, dz, pl.wgrad_ws, G[wname])
-            ready(wname)
             _, wd = pl.packed[wname]
             ops.conv_fwd(dz, wd, None, dx_out, ksize=3, relu=False, stats=pl.stats_partial if dx_stats else None)
+            # after the input-gradient launch: a bucket hook may re-pack this layer's bf16 operands on a side stream
+            ready(wname)
 
         def block_bwd(name, dy1, dx_out, dpool=None, dx_stats=False):
             l = pl.stages[(name, 0)].level
@@ -337,9 +347,9 @@ class UNetEngine:
             up_in = pl.stages[(DEC[l + 1] if l < 3 else "middle.1", 3)].y      # input of the transposed conv
             dY = pl.dcat[l].slice(0, C)
             ops.convt_wgrad(up_in, dY, pl.wgrad_ws, G[f"{ct}.weight"])
-            ready(f"{ct}.weight")
             _, wd = pl.packed[f"{ct}.weight"]
             ops.convt_dgrad(dY, wd, pl.ga[l + 1])
+            ready(f"{ct}.weight")
             dy = pl.ga[l + 1]
         block_bwd("middle.1", dy, pl.dpool[3])
         for l in (3, 2, 1, 0):

@@ -124,8 +124,9 @@ class PackPlan:
     """Pre-allocated bf16 operands of a set of conv / transposed-conv weights and the argument arrays of the single
     b2s_pack_weights_all launch that refreshes all of them."""
 
-    def __init__(self, weights, want_dgrad):
-        """weights: list of (name, fp32 tensor); 4-D [Cout,Cin,k,k] or transposed-conv [Cin,Cout,2,2] (flag in name map)"""
+    def __init__(self, weights, want_dgrad, outputs=None):
+        """weights: list of (name, fp32 tensor, is_convt); 4-D [Cout,Cin,k,k] or transposed-conv [Cin,Cout,2,2].
+        outputs: optional name -> (w_fwd, w_dgrad) of ANOTHER plan to write into (a sub-plan refreshing part of it)."""
         self.items = []
         n = len(weights)
         self._w = (ctypes.c_void_p * n)()
@@ -137,15 +138,17 @@ class PackPlan:
         for i, (name, w, is_convt) in enumerate(weights):
             _need_cuda(w)
             assert w.dtype == torch.float32 and w.is_contiguous()
+            given = outputs[name] if outputs is not None else None
             if is_convt:
                 Cin, Cout = w.shape[0], w.shape[1]
-                wf = torch.empty((4 * Cout, Cin), dtype=BF16, device=w.device)
-                wd = torch.empty((4 * Cin, Cout), dtype=BF16, device=w.device)
+                wf = given[0] if given else torch.empty((4 * Cout, Cin), dtype=BF16, device=w.device)
+                wd = given[1] if given else torch.empty((4 * Cin, Cout), dtype=BF16, device=w.device)
                 d0, d1, taps, kind = Cin, Cout, 4, 1
             else:
                 Cout, Cin, k, _ = w.shape
-                wf = torch.empty((k * k, Cout, Cin), dtype=BF16, device=w.device)
-                wd = torch.empty((k * k, Cin, Cout), dtype=BF16, device=w.device) if want_dgrad else None
+                wf = given[0] if given else torch.empty((k * k, Cout, Cin), dtype=BF16, device=w.device)
+                wd = (given[1] if given else torch.empty((k * k, Cin, Cout), dtype=BF16, device=w.device)) \
+                    if want_dgrad else None
                 d0, d1, taps, kind = Cout, Cin, k * k, 0
             self.packed[name] = (wf, wd)
             self._w[i], self._wf[i] = w.data_ptr(), wf.data_ptr()

@@ -89,6 +89,7 @@ class TrainStep:
                 start = end
         self.order = order
         self._works, self._reduce, self._opt, self._side = [], True, None, None
+        self._pack_src, self._bucket_packs = None, {}
 
     # ---- parameter access -------------------------------------------------------------------------------------
     def state_dict(self):
@@ -117,6 +118,23 @@ class TrainStep:
                 if work is not None:
                     work.wait()                    # the side stream waits for the collective; the host does not block
                 self._opt(s, e)
+                # ... and the bf16 GEMM operands of the bucket's conv weights are re-packed from the updated fp32
+                # masters right away (also overlapped), so the next forward starts without a packing pass
+                pk = self._bucket_pack(b)
+                if pk is not None:
+                    pk.run()
+
+    def _bucket_pack(self, b):
+        """Sub-plan of the engine's weight pack covering bucket b (same output buffers), built on first use."""
+        plan = self.engine.packed_plan(self.P, need_dgrad=True)
+        if self._pack_src is not plan:              # the engine re-allocated its operands: rebuild the sub-plans
+            self._pack_src, self._bucket_packs = plan, {}
+        if b not in self._bucket_packs:
+            names = [k for k in self.order if self.bucket_of[k] == b and k in plan.packed]
+            items = [(k, self.P[k].detach(), k.split(".")[0] in ("middle", "decoder3", "decoder2", "decoder1")
+                      and self.P[k].shape[2] == 2) for k in names]
+            self._bucket_packs[b] = ops.PackPlan(items, want_dgrad=True, outputs=plan.packed) if items else None
+        return self._bucket_packs[b]
 
     # ---- one optimisation step ------------------------------------------------------------------------------------
     def forward_backward(self, x, t, reduce=True, opt=None):
@@ -161,8 +179,7 @@ class TrainStep:
         def opt(s, e):
             ops.adamw_step(self.flat_p[s:e], self.flat_g[s:e], self.flat_m[s:e], self.flat_v[s:e], lr_, b1, b2, self.eps,
                            self.wd, step, scale)
-        out = self.forward_backward(x, t, opt=opt)
-        self.engine.invalidate_packed()      # the kernel updated flat_p behind torch's version counters
+        out = self.forward_backward(x, t, opt=opt)   # the bucket hooks also refreshed the packed bf16 operands
         return out
 
     # ---- the same step as ONE CUDA graph -----------------------------------------------------------------------
@@ -196,7 +213,6 @@ class TrainStep:
             self.forward_backward(self._gx, self._gt, reduce=self.graph_comm, opt=opt)
         else:
             self.forward_backward(self._gx, self._gt, reduce=False)
-        self.engine.invalidate_packed()
 
     def capture(self, x, t, graph_comm=True):
         """Captures forward + loss + backward + bucketed all-reduce + AdamW for inputs shaped like x, t.
@@ -266,6 +282,7 @@ class TrainStep:
         self._write_hyper(lr)
         self._graph.replay()
         if self.world > 1 and not self.graph_comm:
+            self.engine.invalidate_packed()
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
             ops.adamw_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self._hyper_dev)
         key = (x.shape[0], x.shape[2], x.shape[3], str(x.device))
