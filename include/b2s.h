@@ -26,6 +26,7 @@ extern "C" {
 
 #define B2S_FLAG_RELU 1   /* apply max(x,0) in the conv epilogue            (models/model.py:37,40) */
 #define B2S_FLAG_STATS 2  /* emit per-channel sum / sum-of-squares partials (BatchNorm2d, model.py:38,41) */
+#define B2S_FLAG_BNRED 4  /* with STATS on an input-gradient launch: second partial = sum(dy * r) (BatchNorm backward) */
 
 const char* b2s_last_error(void);
 long long b2s_launch_count(void); /* kernels launched by this library in this process (bench.py gpu_launches) */
@@ -241,6 +242,22 @@ int b2s_se_scale(const void* x, int x_cstride, const float* gate, const float* a
 int b2s_se_fc_bwd(const float* partial, int chunks, const float* gate, const float* hidden, const float* mean,
                   const float* w1, const float* w2, float* ds, float* dh, float* dmean, float* dw1, float* db1,
                   float* dw2, float* db2, int N, int C, int Cr, void* stream);
+
+/* BatchNorm-backward reduction fused into the launch that PRODUCES dy (autograd of models/model.py:38,41 behind a conv /
+ * transposed conv): input-gradient launches whose output dy is the gradient of a train-mode BatchNorm output also emit
+ * partial [rows][2][C] = {sum dy, sum dy * r} per channel (r = that BatchNorm's saved input, same pixels / channels as
+ * dy; rows = b2s_conv_stats_rows / b2s_convt2x2_dgrad_rows), so the separate b2s_bn_bwd_reduce pass over dy and r is not
+ * needed; b2s_bn_bwd_finalize_raw turns them into dgamma, dbeta and the coefficients b2s_bn_bwd_apply expects. Both
+ * *_bnred entry points return 1 (nothing launched) when the shape takes the one-tile fallback kernel. */
+int b2s_conv_dgrad_bnred(const void* dz, int dz_cstride, const void* w_dgrad_packed, void* dy, int dy_cstride,
+                         const void* r, int r_cstride, float* partial, int N, int H, int W, int Cin, int Cout, int ksize,
+                         int tile_n, void* stream);
+int b2s_convt2x2_dgrad_bnred(const void* dy, int dy_cstride, const void* w_packed, void* dx, int dx_cstride, const void* r,
+                             int r_cstride, float* partial, int N, int Hi, int Wi, int Cin, int Cout, int tile_n,
+                             void* stream);
+int b2s_convt2x2_dgrad_rows(int N, int Hi, int Wi, int Cin, int tile_n);
+int b2s_bn_bwd_finalize_raw(const float* partial, int rows, int C, double count, const float* gamma, const float* mean,
+                            const float* invstd, float* dgamma, float* dbeta, float* coef, float* scratch, void* stream);
 
 /* AttentionGate (models/mod.py:211-234): psi = sigmoid(BatchNorm2d(1)(conv1x1(relu(g1 + x1)))), out = x * psi.
  * The F_int -> 1 conv is b2s_head_fwd over channel slices of at most 256 channels (up to four fp32 maps, summed on

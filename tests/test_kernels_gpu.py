@@ -285,6 +285,57 @@ def test_conv_transpose_fwd_dgrad_wgrad(ops, N, Hi, Wi, Cin, Cout):
     report("convT wgrad", dw, rdw, rel=1e-4, abs_frac=1e-4)
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 32, 32, 128, 64), (2, 8, 8, 128, 256),
+                                            (2, 4, 128, 64, 64), (1, 6, 256, 64, 128), (3, 24, 40, 64, 128)])
+def test_conv3x3_dgrad_with_fused_bn_reduction(ops, N, H, W, Cin, Cout):
+    """b2s_conv_dgrad_bnred: same dx as the plain input-gradient launch (bit for bit) plus the BatchNorm-backward
+    partials {sum dx, sum dx * r} over the stored bf16 values; tile-pair and row-halo (W % 128 == 0) kernels, a ragged
+    shape with out-of-range tile rows, r as a channel slice of a wider buffer."""
+    w = bf(rnd((Cout, Cin, 3, 3), 32, 0.05))
+    dz = bf(rnd((N, Cout, H, W), 33))
+    r = bf(rnd((N, Cin, H, W), 34).clamp_min(0))
+    _, wd = ops.pack_conv_weight(w.to(DEV))
+    dza = act_from_nchw(ops, dz)
+    ra = act_from_nchw(ops, r, ctot=Cin + 64, c0=64)
+    dx0, dx1 = ops.Act.empty(N, H, W, Cin, DEV), ops.Act.empty(N, H, W, Cin, DEV)
+    ops.conv_fwd(dza, wd, None, dx0, ksize=3)
+    partial = torch.full((2 * 160 * 2 * Cin,), float("nan"), dtype=torch.float32, device=DEV)
+    rows = ops.conv_dgrad_bnred(dza, wd, dx1, ra, partial, ksize=3)
+    torch.cuda.synchronize()
+    if rows == 0:
+        pytest.skip("shape takes the one-tile kernel (no fused reduction)")
+    assert torch.equal(dx0.buf, dx1.buf)
+    sums = partial[: rows * 2 * Cin].view(rows, 2, Cin).double().sum(0).cpu()
+    dx = dx1.to_nchw_float().double().cpu()
+    ref_s, ref_q = dx.sum(dim=(0, 2, 3)), (dx * r.double()).sum(dim=(0, 2, 3))
+    scale = float((dx.abs() * r.double()).sum(dim=(0, 2, 3)).max()) + 1e-30
+    assert float((sums[0] - ref_s).abs().max()) <= 1e-5 * float(dx.abs().sum(dim=(0, 2, 3)).max())
+    assert float((sums[1] - ref_q).abs().max()) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("N,Hi,Wi,Cin,Cout", [(2, 8, 8, 128, 64), (1, 16, 16, 256, 128), (3, 6, 10, 128, 64)])
+def test_convt_dgrad_with_fused_bn_reduction(ops, N, Hi, Wi, Cin, Cout):
+    w = bf(rnd((Cin, Cout, 2, 2), 52, 0.05))
+    dy = bf(rnd((N, Cout, 2 * Hi, 2 * Wi), 54))
+    r = bf(rnd((N, Cin, Hi, Wi), 55).clamp_min(0))
+    _, wd = ops.pack_convt_weight(w.to(DEV))
+    dya = act_from_nchw(ops, dy, ctot=2 * Cout, c0=0)
+    ra = act_from_nchw(ops, r)
+    dx0, dx1 = ops.Act.empty(N, Hi, Wi, Cin, DEV), ops.Act.empty(N, Hi, Wi, Cin, DEV)
+    ops.convt_dgrad(dya, wd, dx0)
+    partial = torch.full((2 * 160 * 2 * Cin,), float("nan"), dtype=torch.float32, device=DEV)
+    rows = ops.convt_dgrad_bnred(dya, wd, dx1, ra, partial)
+    torch.cuda.synchronize()
+    if rows == 0:
+        pytest.skip("shape takes the one-tile kernel (no fused reduction)")
+    assert torch.equal(dx0.buf, dx1.buf)
+    sums = partial[: rows * 2 * Cin].view(rows, 2, Cin).double().sum(0).cpu()
+    dx = dx1.to_nchw_float().double().cpu()
+    assert float((sums[0] - dx.sum(dim=(0, 2, 3))).abs().max()) <= 1e-5 * float(dx.abs().sum(dim=(0, 2, 3)).max())
+    ref_q = (dx * r.double()).sum(dim=(0, 2, 3))
+    assert float((sums[1] - ref_q).abs().max()) <= 1e-5 * (float((dx.abs() * r.double()).sum(dim=(0, 2, 3)).max()) + 1e-30)
+
+
 def test_conv3x3_large_vs_torch(ops):
     """B x 64 x 128 x 128 against torch fp32 conv on the GPU (size the CPU oracle would not finish in seconds)."""
     N, H, W, Cin, Cout = 4, 128, 128, 64, 128

@@ -72,6 +72,10 @@ SIGNATURES = {
     "b2s_se_fc_fwd": (I, [P, I, LL, P, P, P, P, P, P, P, I, I, I, P]),
     "b2s_se_scale": (I, [P, I, P, P, F, P, I, I, LL, I, P]),
     "b2s_se_fc_bwd": (I, [P, I, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "b2s_conv_dgrad_bnred": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, I, I, P]),
+    "b2s_convt2x2_dgrad_bnred": (I, [P, I, P, P, I, P, I, P, I, I, I, I, I, I, P]),
+    "b2s_convt2x2_dgrad_rows": (I, [I, I, I, I, I]),
+    "b2s_bn_bwd_finalize_raw": (I, [P, I, I, c_double, P, P, P, P, P, P, P, P]),
     "b2s_psi_rows": (I, [LL]),
     "b2s_psi_stats": (I, [P, I, LL, P, P]),
     "b2s_psi_fwd": (I, [P, I, P, P, P, LL, P]),

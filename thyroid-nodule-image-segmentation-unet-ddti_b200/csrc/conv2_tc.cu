@@ -47,7 +47,7 @@ struct Conv2Cfg {
 // Row-shifted operands: the tensor core applies the SWIZZLE_128B XOR to the absolute shared-memory address bits, the
 // same function TMA used when it wrote the 1024-B aligned row slots, so a descriptor may start at any 128-byte pixel
 // row of a slot with base_offset = 0 (measured on B200: base_offset = (addr >> 7) & 7 gives wrong results).
-template <int BLOCK_N, int MT, bool HALO, int STAGES, int STAGES_A>
+template <int BLOCK_N, int MT, bool HALO, int STAGES, int STAGES_A, bool RED>
 __global__ void __launch_bounds__(kConv2Threads, 1)
 conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const ConvTcParams p) {
@@ -258,6 +258,11 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int row = q * 32 + lane;   // tile row == TMEM lane
     const bool do_relu = p.flags & B2S_FLAG_RELU;
     const bool do_stats = (p.flags & B2S_FLAG_STATS) && p.stats != nullptr;
+    // BatchNorm-backward reduction fused into an input-gradient launch: sum(dy) and sum(dy * r) per channel, where r
+    // is the saved input of the BatchNorm that dy (this launch's output) is the gradient of
+    // (RED is a template parameter: the forward / plain dgrad instantiations keep their register allocation)
+    const bool do_red = RED && do_stats;
+    const int sh_w = __ffs(p.bw) - 1, sh_h = __ffs(p.bh) - 1;   // pick_box: bw, bh, bn are powers of two
     uint8_t* stage_buf = smem + L::kStagingOffset + g * kATileBytes;
     const int bar_id = 1 + g;
     const int wl = row % p.bw;
@@ -324,6 +329,19 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (!valid) { a = 0.f; b = 0.f; }
           packed[j] = pack_bf16x2(a, b);
         }
+        // r words of this warp's 32 rows for the lane's column pair (one coalesced 128-byte row per load), issued now
+        // so that their L2 latency overlaps the staging write below
+        uint32_t rw[RED ? 32 : 1];
+        if (RED && do_red) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const int rr = q * 32 + r;
+            const int rw_l = rr & (p.bw - 1), rh_l = (rr >> sh_w) & (p.bh - 1), rn_l = rr >> (sh_w + sh_h);
+            const bool rv = HALO || ((w0 + rw_l < p.W) && (h0 + rh_l < p.H) && (n0 + rn_l < p.N));
+            const long long pix = (static_cast<long long>(n0 + rn_l) * p.H + (h0 + rh_l)) * p.W + (w0 + rw_l);
+            rw[r] = rv ? __ldg(reinterpret_cast<const unsigned int*>(p.red_r + pix * p.red_cs + col_base) + lane) : 0u;
+          }
+        }
         // the previous TMA store of this group must have finished READING the staging tile
         if (row == 0) tma_store_wait_read<0>();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -337,14 +355,26 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
           const int chunk = lane >> 2, within = (lane & 3) * 4;
+          if (RED) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const int rr = q * 32 + r;
+              const uint32_t u =
+                  *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
+              const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+              s0 += x0; s1 += x1;
+              q0 = fmaf(x0, bf16_lo(rw[RED ? r : 0]), q0); q1 = fmaf(x1, bf16_hi(rw[RED ? r : 0]), q1);
+            }
+          } else {
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            const int rr = q * 32 + r;
-            const uint32_t u =
-                *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
-            const float x0 = bf16_lo(u), x1 = bf16_hi(u);
-            s0 += x0; s1 += x1;
-            q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+            for (int r = 0; r < 32; ++r) {
+              const int rr = q * 32 + r;
+              const uint32_t u =
+                  *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
+              const float x0 = bf16_lo(u), x1 = bf16_hi(u);
+              s0 += x0; s1 += x1;
+              q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+            }
           }
           st_acc[s][0] += s0; st_acc[s][1] += s1; st_acc[s][2] += q0; st_acc[s][3] += q1;
         }
@@ -392,11 +422,11 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BLOCK_N, int MT, bool HALO, int STAGES, int STAGES_A>
-static int launch_conv2_t(int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+template <int BLOCK_N, int MT, bool HALO, int STAGES, int STAGES_A, bool RED>
+static int launch_conv2_r(int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                           const ConvTcParams& p, cudaStream_t stream) {
   using L = Conv2Cfg<BLOCK_N, MT, HALO, STAGES, STAGES_A>;
-  auto kfn = conv2_tc_kernel<BLOCK_N, MT, HALO, STAGES, STAGES_A>;
+  auto kfn = conv2_tc_kernel<BLOCK_N, MT, HALO, STAGES, STAGES_A, RED>;
   static std::atomic<unsigned long long> attr_devices{0};
   {
     cudaError_t e = allow_dynamic_smem(kfn, L::kDynBytes, attr_devices);
@@ -404,6 +434,15 @@ static int launch_conv2_t(int grid, const CUtensorMap& tmA, const CUtensorMap& t
   }
   kfn<<<grid, kConv2Threads, L::kDynBytes, stream>>>(tmA, tmB, tmOut, p);
   return check_launch("conv2_tc_kernel");
+}
+
+// B2S_FLAG_BNRED selects the instantiation with the fused BatchNorm-backward reduction
+template <int BLOCK_N, int MT, bool HALO, int STAGES, int STAGES_A>
+static int launch_conv2_t(int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                          const ConvTcParams& p, cudaStream_t stream) {
+  if ((p.flags & B2S_FLAG_BNRED) && p.red_r != nullptr)
+    return launch_conv2_r<BLOCK_N, MT, HALO, STAGES, STAGES_A, true>(grid, tmA, tmB, tmOut, p, stream);
+  return launch_conv2_r<BLOCK_N, MT, HALO, STAGES, STAGES_A, false>(grid, tmA, tmB, tmOut, p, stream);
 }
 
 int launch_conv2(const ConvPlan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,

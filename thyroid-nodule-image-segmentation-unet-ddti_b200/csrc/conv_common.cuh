@@ -32,6 +32,10 @@ struct ConvTcParams {
   const float* post_shift;         // post_shift per output channel (both nullptr in training)
   int items_m;                     // work items of the tile-pair / halo kernels (see conv_plan)
   float* stats;                    // [2 * gridDim.x / tiles_nn][2][n_total] partial column sums, or nullptr
+  // B2S_FLAG_BNRED (input-gradient launches whose output dy feeds a train-mode BatchNorm backward): the second partial
+  // row holds sum(dy * r) instead of sum(dy^2); r = that BatchNorm's saved input, same pixel space and channels as dy
+  const __nv_bfloat16* red_r;
+  int red_cs;                      // pixel stride of r in elements
 };
 
 // ------------------------------------------------------------------------------------------------

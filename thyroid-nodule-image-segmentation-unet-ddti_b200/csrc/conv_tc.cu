@@ -522,7 +522,8 @@ using namespace b2s;
 // Generic tap-GEMM conv. ksize 3 (pad 1) or 1. See include/b2s.h.
 static int conv_fwd_impl(const void* x, int x_cstride, const void* w_packed, const float* bias, const float* post_scale,
                          const float* post_shift, void* y, int y_cstride, float* stats_partial, int N, int H, int W,
-                         int Cin, int Cout, int ksize, int flags, int tile_n, void* stream_) {
+                         int Cin, int Cout, int ksize, int flags, int tile_n, void* stream_,
+                         const void* red_r = nullptr, int red_cs = 0) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if ((post_scale == nullptr) != (post_shift == nullptr))
     return set_error(B2S_ERR_ARG, "b2s_conv_fwd: post_scale and post_shift must both be given");
@@ -541,6 +542,11 @@ static int conv_fwd_impl(const void* x, int x_cstride, const void* w_packed, con
   p.n_total = Cout; p.cout_sub = Cout;
   p.flags = flags; p.bias = bias; p.stats = stats_partial;
   p.post_scale = post_scale; p.post_shift = post_shift;
+  if (flags & B2S_FLAG_BNRED) {
+    if (!red_r || !stats_partial || red_cs % 8) return set_error(B2S_ERR_ARG, "b2s_conv_dgrad_bnred: r / partial missing");
+    if (pl.kind == CONV_LEGACY) return 1;    // the one-tile kernel has no fused reduction: caller takes the two-pass path
+    p.red_r = static_cast<const __nv_bfloat16*>(red_r); p.red_cs = red_cs;
+  }
 
   CUtensorMap tmA, tmB, tmOut;
   int rc;
@@ -569,6 +575,17 @@ extern "C" int b2s_conv_fwd_affine(const void* x, int x_cstride, const void* w_p
   if (!post_scale || !post_shift) return set_error(B2S_ERR_ARG, "b2s_conv_fwd_affine: null pointer");
   return conv_fwd_impl(x, x_cstride, w_packed, bias, post_scale, post_shift, y, y_cstride, nullptr, N, H, W, Cin, Cout,
                        ksize, flags & ~B2S_FLAG_STATS, tile_n, stream);
+}
+
+// Input gradient of a conv (a conv over dz with the rotated weights) whose output dy is the gradient of a train-mode
+// BatchNorm output: the epilogue also emits partial [b2s_conv_stats_rows][2][Cout] = {sum dy, sum dy * r} per channel
+// (r = that BatchNorm's saved input), which replaces the separate reduce pass of the BatchNorm backward
+// (b2s_bn_bwd_finalize_raw consumes it). Returns 1 (nothing launched) when the shape takes the one-tile kernel.
+extern "C" int b2s_conv_dgrad_bnred(const void* dz, int dz_cstride, const void* w_dgrad_packed, void* dy, int dy_cstride,
+                                    const void* r, int r_cstride, float* partial, int N, int H, int W, int Cin, int Cout,
+                                    int ksize, int tile_n, void* stream) {
+  return conv_fwd_impl(dz, dz_cstride, w_dgrad_packed, nullptr, nullptr, nullptr, dy, dy_cstride, partial, N, H, W, Cin,
+                       Cout, ksize, B2S_FLAG_STATS | B2S_FLAG_BNRED, tile_n, stream, r, r_cstride);
 }
 
 // nn.Conv2d(Cin,Cout,3,stride=2,padding=1) forward (models/vnet.py:97): x [N,H,W,Cin] -> y [N,H/2,W/2,Cout].
@@ -677,8 +694,13 @@ extern "C" int b2s_convt2x2_fwd(const void* x, int x_cstride, const void* w_pack
 }
 
 // ConvTranspose2d(k=2,s=2) input gradient: dy [N,2Hi,2Wi,Cout] -> dx [N,Hi,Wi,Cin]; w_packed [(a*2+b)*Cin+ci][Cout].
-extern "C" int b2s_convt2x2_dgrad(const void* dy, int dy_cstride, const void* w_packed, void* dx, int dx_cstride,
-                                  int N, int Hi, int Wi, int Cin, int Cout, int tile_n, void* stream_) {
+static int convt_dgrad_plan(int N, int Hi, int Wi, int Cin, int tile_n, ConvPlan* pl) {
+  return conv_plan(1, Hi * N, Wi, Cin, Cin, A_CONVT_DGRAD, OUT_4D, tile_n, pl);
+}
+
+static int convt_dgrad_impl(const void* dy, int dy_cstride, const void* w_packed, void* dx, int dx_cstride, const void* red_r,
+                            int red_cs, float* partial, int N, int Hi, int Wi, int Cin, int Cout, int tile_n,
+                            void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!dy || !w_packed || !dx) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: null pointer");
   if (Cin % 64 || Cout % 64) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: channels must be multiples of 64");
@@ -687,18 +709,43 @@ extern "C" int b2s_convt2x2_dgrad(const void* dy, int dy_cstride, const void* w_
   p.a_mode = A_CONVT_DGRAD; p.out_mode = OUT_4D;
   const int Hm = Hi * N;   // image rows merged into one dimension (see b2s_convt2x2_fwd)
   ConvPlan pl;
-  if (conv_plan(1, Hm, Wi, Cin, Cin, p.a_mode, p.out_mode, tile_n, &pl))
+  if (convt_dgrad_plan(N, Hi, Wi, Cin, tile_n, &pl))
     return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad: tile_n must be 64/128/256 and divide Cin");
   p.W = Wi; p.H = Hm; p.N = 1;
   p.num_taps = 4; p.k_chunks = Cout / 64;
   p.n_total = Cin; p.cout_sub = Cin;
   p.flags = 0; p.bias = nullptr; p.stats = nullptr;
+  if (red_r) {   // dx is the gradient of a train-mode BatchNorm output: fused {sum dx, sum dx * r} partials
+    if (!partial || red_cs % 8) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad_bnred: partial missing / bad stride");
+    if (pl.kind == CONV_LEGACY) return 1;
+    p.flags = B2S_FLAG_STATS | B2S_FLAG_BNRED; p.stats = partial;
+    p.red_r = static_cast<const __nv_bfloat16*>(red_r); p.red_cs = red_cs;
+  }
   CUtensorMap tmA, tmB, tmOut;
   int rc;
   if ((rc = make_up_map5(&tmA, dy, Cout, Wi, Hm, 1, dy_cstride, pl.bw, pl.bh * pl.bn))) return rc;
   if ((rc = make_weight_map(&tmB, w_packed, Cout, 4 * Cin, pl.block_n))) return rc;
   if ((rc = make_act_map4(&tmOut, dx, Cin, Wi, Hm, 1, dx_cstride, pl.bw, pl.bh, pl.bn))) return rc;
   return dispatch_conv(pl, tmA, tmB, tmOut, p, stream);
+}
+
+extern "C" int b2s_convt2x2_dgrad(const void* dy, int dy_cstride, const void* w_packed, void* dx, int dx_cstride,
+                                  int N, int Hi, int Wi, int Cin, int Cout, int tile_n, void* stream) {
+  return convt_dgrad_impl(dy, dy_cstride, w_packed, dx, dx_cstride, nullptr, 0, nullptr, N, Hi, Wi, Cin, Cout, tile_n, stream);
+}
+
+// ... with the fused BatchNorm-backward reduction (see b2s_conv_dgrad_bnred); partial [b2s_convt2x2_dgrad_rows][2][Cin].
+extern "C" int b2s_convt2x2_dgrad_bnred(const void* dy, int dy_cstride, const void* w_packed, void* dx, int dx_cstride,
+                                        const void* r, int r_cstride, float* partial, int N, int Hi, int Wi, int Cin,
+                                        int Cout, int tile_n, void* stream) {
+  if (!r) return set_error(B2S_ERR_ARG, "b2s_convt2x2_dgrad_bnred: null pointer");
+  return convt_dgrad_impl(dy, dy_cstride, w_packed, dx, dx_cstride, r, r_cstride, partial, N, Hi, Wi, Cin, Cout, tile_n, stream);
+}
+
+extern "C" int b2s_convt2x2_dgrad_rows(int N, int Hi, int Wi, int Cin, int tile_n) {
+  ConvPlan pl;
+  if (convt_dgrad_plan(N, Hi, Wi, Cin, tile_n, &pl)) return -1;
+  return pl.stats_rows;
 }
 
 // ---- wgrad -----------------------------------------------------------------------------------

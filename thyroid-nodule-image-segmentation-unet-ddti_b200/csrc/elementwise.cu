@@ -675,13 +675,16 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, const __nv_bfloat
     for (int o = threadIdx.x; o < nout; o += kThreads) partial[static_cast<size_t>(rr) * nout + o] = 0.f;
 }
 
+// mean != nullptr: the second sum is the RAW sum(dy * r) of the fused dgrad epilogue (b2s_conv_dgrad_bnred), turned
+// into sum(dy * xhat) = invstd * (sum(dy * r) - mean * sum(dy)) here
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int rows, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
-                                       float* dgamma, float* dbeta, float* coef) {
+                                       float* dgamma, float* dbeta, float* coef, const float* __restrict__ mean = nullptr) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s, q;
   block_sum_pairs(partial, rows, C, c, s, q);
   if (threadIdx.y != 0 || c >= C) return;
+  if (mean) q = static_cast<double>(invstd[c]) * (q - static_cast<double>(mean[c]) * s);
   if (dgamma) dgamma[c] = static_cast<float>(q);
   if (dbeta) dbeta[c] = static_cast<float>(s);
   coef[c] = (gamma ? gamma[c] : 1.f) * invstd[c];
@@ -1504,6 +1507,19 @@ extern "C" int b2s_bn_bwd_finalize(const float* partial, int rows, int C, double
   bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, STREAM(stream)>>>(src, r, C, count, gamma, invstd, dgamma, dbeta,
                                                                       coef);
   return check_launch("bn_bwd_finalize_kernel");
+}
+
+extern "C" int b2s_bn_bwd_finalize_raw(const float* partial, int rows, int C, double count, const float* gamma,
+                                       const float* mean, const float* invstd, float* dgamma, float* dbeta, float* coef,
+                                       float* scratch, void* stream) {
+  if (!partial || !invstd || !mean || !coef) return set_error(B2S_ERR_ARG, "b2s_bn_bwd_finalize_raw: null pointer");
+  const float* src; int r;
+  int rc = reduce_to_small(partial, rows, 2 * C, scratch, &src, &r, STREAM(stream));
+  if (rc) return rc;
+  count_launch();
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, STREAM(stream)>>>(src, r, C, count, gamma, invstd, dgamma, dbeta,
+                                                                      coef, mean);
+  return check_launch("bn_bwd_finalize_kernel<raw>");
 }
 
 extern "C" int b2s_bn_bwd_apply(const void* dy, int dy_cstride, const void* dpool, const void* r, int r_cstride,

@@ -129,6 +129,8 @@ class UNetPlan:
             nb, _ = ops.wgrad_workspace(N, dims[l + 1][0], dims[l + 1][1], cin, cout, 4)
             ws_bytes = max(ws_bytes, nb)
         self.wgrad_ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=device)
+        # {sum dy, sum dy*r} partials of the fused BatchNorm-backward reduction (<= 2 rows per SM, <= 1024 channels)
+        self.red_partial = torch.empty(2 * 160 * 2 * 1024, dtype=torch.float32, device=device)
         self.train_ready = True
 
 
@@ -139,6 +141,10 @@ class UNetEngine:
         self.O = out_channels
         self.plans = {}
         self._pack_state = {}
+        # BatchNorm-backward sums emitted by the dgrad / transposed-conv dgrad launch that produces dy (13 of 18 stages)
+        # instead of a separate pass over dy and r; B2S_FUSE_BN_REDUCE=0 restores the two-pass scheme (A/B measurements)
+        import os
+        self.fuse_bn_reduce = os.environ.get("B2S_FUSE_BN_REDUCE", "1") != "0"
 
     # ---- plumbing -----------------------------------------------------------------------------------------
     def plan(self, N, H, W, device, train, in_channels=1):
@@ -293,37 +299,47 @@ class UNetEngine:
         ready = on_grad_ready or (lambda name: None)
         count = lambda l: float(N * pl.dims[l][0] * pl.dims[l][1])
 
-        def stage_bwd(name, idx, dy, dx_out, dpool=None, dx_stats=False):
-            """BN+ReLU backward -> dz; conv wgrad; conv dgrad into dx_out (None for the image conv)."""
+        def stage_bwd(name, idx, dy, dx_out, dpool=None, dx_stats=False, pre=None, red_for=None):
+            """BN+ReLU backward -> dz; conv wgrad; conv dgrad into dx_out (None for the image conv).
+            pre: (partial, rows) when the launch that produced dy already emitted the BatchNorm-backward sums.
+            red_for: the stage whose BatchNorm consumes dx_out directly: this stage's dgrad then emits those sums
+            (fused epilogue) and the function returns them for that stage's `pre`."""
             s = pl.stages[(name, idx)]
             bn = f"{name}.{idx + 2}"
             l = s.level
             dz = pl.gb[l]
             ops.bn_bwd(dy, dpool, s.r, s.scale, s.shift, s.mean, s.invstd, P[f"{bn}.weight"], count(l), dz,
                        pl.ew_partial, pl.scratch, pl.coef, G[f"{bn}.weight"], G[f"{bn}.bias"],
-                       G[f"{name}.{idx}.bias"])
+                       G[f"{name}.{idx}.bias"], pre=pre)
             ready(f"{bn}.weight"); ready(f"{bn}.bias"); ready(f"{name}.{idx}.bias")
             wname = f"{name}.{idx}.weight"
             if s.x is None:
                 ops.conv3x3_c1_wgrad(pl.x, dz, pl.c1_partial, pl.scratch, G[wname])
                 ready(wname)
-                return
+                return None
             if dx_out is None:      # encoder1.0 of a multi-channel image: padded weight gradient, no input gradient
                 tmp = torch.empty((s.cout, 64, 3, 3), dtype=torch.float32, device=dz.buf.device)
                 ops.conv3x3_wgrad(s.x, dz, pl.wgrad_ws, tmp)
                 G[wname].copy_(tmp[:, :pl.Cin])
                 ready(wname)
-                return
+                return None
             ops.conv3x3_wgrad(s.x, dz, pl.wgrad_ws, G[wname])
             _, wd = pl.packed[wname]
-            ops.conv_fwd(dz, wd, None, dx_out, ksize=3, relu=False, stats=pl.stats_partial if dx_stats else None)
+            out_pre = None
+            if red_for is not None and self.fuse_bn_reduce:
+                rows = ops.conv_dgrad_bnred(dz, wd, dx_out, pl.stages[red_for].r, pl.red_partial, ksize=3)
+                out_pre = (pl.red_partial, rows) if rows else None
+            if out_pre is None:
+                ops.conv_fwd(dz, wd, None, dx_out, ksize=3, relu=False, stats=pl.stats_partial if dx_stats else None)
             # after the input-gradient launch: a bucket hook may re-pack this layer's bf16 operands on a side stream
             ready(wname)
+            return out_pre
 
-        def block_bwd(name, dy1, dx_out, dpool=None, dx_stats=False):
+        def block_bwd(name, dy1, dx_out, dpool=None, dx_stats=False, pre=None):
+            """pre: fused BatchNorm-backward sums for the block's SECOND stage (dy1 came out of a transposed-conv dgrad)"""
             l = pl.stages[(name, 0)].level
-            stage_bwd(name, 3, dy1, pl.ga[l], dpool=dpool)
-            stage_bwd(name, 0, pl.ga[l], dx_out, dx_stats=dx_stats)
+            pre0 = stage_bwd(name, 3, dy1, pl.ga[l], dpool=dpool, pre=pre, red_for=(name, 0))
+            stage_bwd(name, 0, pl.ga[l], dx_out, dx_stats=dx_stats, pre=pre0)
 
         # head (final.1) -> dy of final.0's second BN
         s = pl.stages[("final.0", 3)]
@@ -334,10 +350,11 @@ class UNetEngine:
         ready("final.1.weight"); ready("final.1.bias")
 
         dy = pl.ga[0]
+        pre = None
         for l in (0, 1, 2, 3):
             name = "final.0" if l == 0 else DEC[l]
             C = pl.dims[l][2]
-            block_bwd(name, dy, pl.dcat[l], dx_stats=True)
+            block_bwd(name, dy, pl.dcat[l], dx_stats=True, pre=pre)
             # transposed conv writing cat[l][:, :C]: bias grad = column sums of dcat[l][..., :C] (dgrad epilogue)
             ct = CONVT_INTO[l]
             rows = ops.conv_stats_rows(N, pl.dims[l][0], pl.dims[l][1], 2 * C)
@@ -348,10 +365,16 @@ class UNetEngine:
             dY = pl.dcat[l].slice(0, C)
             ops.convt_wgrad(up_in, dY, pl.wgrad_ws, G[f"{ct}.weight"])
             _, wd = pl.packed[f"{ct}.weight"]
-            ops.convt_dgrad(dY, wd, pl.ga[l + 1])
+            # ga[l+1] is the gradient of the BatchNorm output of the next block's second stage: fused reduction
+            nxt = (DEC[l + 1] if l < 3 else "middle.1", 3)
+            rows = ops.convt_dgrad_bnred(dY, wd, pl.ga[l + 1], pl.stages[nxt].r, pl.red_partial) \
+                if self.fuse_bn_reduce else 0
+            pre = (pl.red_partial, rows) if rows else None
+            if pre is None:
+                ops.convt_dgrad(dY, wd, pl.ga[l + 1])
             ready(f"{ct}.weight")
             dy = pl.ga[l + 1]
-        block_bwd("middle.1", dy, pl.dpool[3])
+        block_bwd("middle.1", dy, pl.dpool[3], pre=pre)
         for l in (3, 2, 1, 0):
             C = pl.dims[l][2]
             skip_grad = pl.dcat[l].slice(C, C)

@@ -216,6 +216,40 @@ def convt_dgrad(dy, w_packed_d, dx, tile_n=0):
                                       dx.C, dy.C, tile_n, _stream()), "b2s_convt2x2_dgrad"), nbytes)
 
 
+def conv_dgrad_bnred(dz, w_packed_d, dy, r, partial, ksize=3, tile_n=0):
+    """dy = input gradient of a conv (conv of dz with the rotated weights) AND partial [rows][2][C] = {sum dy, sum dy*r}
+    for the BatchNorm backward that consumes dy (r: its saved input). Returns the partial's row count, or 0 when the
+    shape takes the one-tile kernel (nothing launched: use conv_fwd + the two-pass bn_bwd)."""
+    flops = 2.0 * dz.N * dz.H * dz.W * dz.C * dy.C * ksize * ksize
+    rc = _timed(f"conv{ksize}x{ksize}[{dz.C}->{dy.C}@{dz.H}x{dz.W}]", "tensor", flops, lambda: _lib.lib().b2s_conv_dgrad_bnred(
+        dz.ptr, dz.cstride, _p(w_packed_d), dy.ptr, dy.cstride, r.ptr, r.cstride, _p(partial), dz.N, dz.H, dz.W, dz.C,
+        dy.C, ksize, tile_n, _stream()))
+    if rc == 1:
+        if PROFILE is not None:
+            PROFILE.pop()
+        return 0
+    check(rc, "b2s_conv_dgrad_bnred")
+    return conv_stats_rows(dz.N, dz.H, dz.W, dy.C, tile_n)
+
+
+def convt_dgrad_bnred(dy, w_packed_d, dx, r, partial, tile_n=0):
+    """transposed-conv input gradient with the same fused reduction over its output dx; returns rows or 0"""
+    flops = 8.0 * dx.N * dx.H * dx.W * dx.C * dy.C
+    nbytes = 2.0 * dx.N * dx.H * dx.W * (dx.C + 4 * dy.C) + 8.0 * dx.C * dy.C
+    rc = _timed(f"convT_dgrad[{dx.C}<-{dy.C}@{dx.H}x{dx.W}]", "tensor", flops, lambda: _lib.lib().b2s_convt2x2_dgrad_bnred(
+        dy.ptr, dy.cstride, _p(w_packed_d), dx.ptr, dx.cstride, r.ptr, r.cstride, _p(partial), dx.N, dx.H, dx.W, dx.C,
+        dy.C, tile_n, _stream()), nbytes)
+    if rc == 1:
+        if PROFILE is not None:
+            PROFILE.pop()
+        return 0
+    check(rc, "b2s_convt2x2_dgrad_bnred")
+    rows = _lib.lib().b2s_convt2x2_dgrad_rows(dx.N, dx.H, dx.W, dx.C, tile_n)
+    if rows <= 0:
+        raise _lib.B2SError("b2s_convt2x2_dgrad_rows: unsupported shape")
+    return rows
+
+
 def wgrad_workspace(N, H, W, Cin, Cout, taps, tile_n=0, splits=0):
     s = ctypes.c_int(0)
     nbytes = _lib.lib().b2s_conv_wgrad_workspace(N, H, W, Cin, Cout, 3 if taps == 9 else taps, tile_n, splits,
@@ -317,19 +351,27 @@ def bn_apply(r, scale, shift, y, pooled=None):
         "b2s_bn_apply"))
 
 
-def bn_bwd(dy, dpool, r, scale, shift, mean, invstd, gamma, count, dz, partial, scratch, coef, dgamma, dbeta, dbias):
-    """Full BatchNorm(+ReLU, + optional max-pool routing) backward: writes dz, dgamma, dbeta, dbias."""
+def bn_bwd(dy, dpool, r, scale, shift, mean, invstd, gamma, count, dz, partial, scratch, coef, dgamma, dbeta, dbias,
+           pre=None):
+    """Full BatchNorm(+ReLU, + optional max-pool routing) backward: writes dz, dgamma, dbeta, dbias.
+    pre = (partial, rows): {sum dy, sum dy*r} partials already emitted by the launch that produced dy
+    (conv_dgrad_bnred / convt_dgrad_bnred); the reduce pass over dy and r is then skipped."""
     L = _lib.lib()
     rows = L.b2s_ew_rows()
     C = r.C
     dp = dpool.ptr if dpool is not None else None
     nel = r.N * r.H * r.W * C * 2.0
     extra = 0.25 if dpool is not None else 0.0
-    _timed("bn_bwd_reduce", "hbm", nel * (2.0 + extra), lambda: check(
-        L.b2s_bn_bwd_reduce(dy.ptr, dy.cstride, dp, r.ptr, r.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
-                            _p(partial), r.N, r.H, r.W, C, _stream()), "b2s_bn_bwd_reduce"))
-    check(L.b2s_bn_bwd_finalize(_p(partial), rows, C, float(count), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta),
-                                _p(coef), _p(scratch), _stream()), "b2s_bn_bwd_finalize")
+    if pre is not None:
+        assert dpool is None
+        check(L.b2s_bn_bwd_finalize_raw(_p(pre[0]), pre[1], C, float(count), _p(gamma), _p(mean), _p(invstd), _p(dgamma),
+                                        _p(dbeta), _p(coef), _p(scratch), _stream()), "b2s_bn_bwd_finalize_raw")
+    else:
+        _timed("bn_bwd_reduce", "hbm", nel * (2.0 + extra), lambda: check(
+            L.b2s_bn_bwd_reduce(dy.ptr, dy.cstride, dp, r.ptr, r.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
+                                _p(partial), r.N, r.H, r.W, C, _stream()), "b2s_bn_bwd_reduce"))
+        check(L.b2s_bn_bwd_finalize(_p(partial), rows, C, float(count), _p(gamma), _p(invstd), _p(dgamma), _p(dbeta),
+                                    _p(coef), _p(scratch), _stream()), "b2s_bn_bwd_finalize")
     _timed("bn_bwd_apply", "hbm", nel * (3.0 + extra), lambda: check(
         L.b2s_bn_bwd_apply(dy.ptr, dy.cstride, dp, r.ptr, r.cstride, _p(scale), _p(shift), _p(mean), _p(invstd),
                            _p(coef), dz.ptr, dz.cstride, _p(partial), r.N, r.H, r.W, C, _stream()),
