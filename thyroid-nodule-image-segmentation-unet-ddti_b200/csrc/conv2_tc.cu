@@ -290,6 +290,19 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.bn;
         valid = (w0 + wl < p.W) && (h0 + hl < p.H) && (n0 + nl < p.N);
       }
+      if (RED && do_red) {
+        // pull this tile's r rows (one pixel row of BLOCK_N channels per lane) into L2 while the MMAs of the item are
+        // still running: the 32-bit loads of the column sums below then pay L2 instead of HBM latency
+        const int rr = q * 32 + lane;
+        const int rw_l = rr & (p.bw - 1), rh_l = (rr >> sh_w) & (p.bh - 1), rn_l = rr >> (sh_w + sh_h);
+        if (HALO || ((w0 + rw_l < p.W) && (h0 + rh_l < p.H) && (n0 + rn_l < p.N))) {
+          const long long pix = (static_cast<long long>(n0 + rn_l) * p.H + (h0 + rh_l)) * p.W + (w0 + rw_l);
+          const __nv_bfloat16* line = p.red_r + pix * p.red_cs + ncol0;
+#pragma unroll
+          for (int s = 0; s < BLOCK_N / 64; ++s)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(line + s * 64));
+        }
+      }
       mbar_wait(&tmem_full_bar[set], par);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (set * MT + (MT == 2 ? g : 0)) * BLOCK_N;

@@ -141,10 +141,13 @@ class UNetEngine:
         self.O = out_channels
         self.plans = {}
         self._pack_state = {}
-        # BatchNorm-backward sums emitted by the dgrad / transposed-conv dgrad launch that produces dy (13 of 18 stages)
-        # instead of a separate pass over dy and r; B2S_FUSE_BN_REDUCE=0 restores the two-pass scheme (A/B measurements)
+        # Optional (B2S_FUSE_BN_REDUCE=1, default off): BatchNorm-backward sums emitted by the dgrad / transposed-conv dgrad
+        # launch that produces dy (13 of 18 stages) instead of a separate pass over dy and r. Measured on a B200 at batch
+        # 64 @256^2: the reduce passes shrink by 0.92 ms per step, but the tensor-core epilogues that take them over grow
+        # by 2.4 ms (32 extra 128-byte row loads per warp and sub-tile on the critical path of kernels with one
+        # accumulator set or one or two items per CTA): 25.2 vs 23.7 ms per step. Kept for the A/B and its kernel tests.
         import os
-        self.fuse_bn_reduce = os.environ.get("B2S_FUSE_BN_REDUCE", "1") != "0"
+        self.fuse_bn_reduce = os.environ.get("B2S_FUSE_BN_REDUCE", "0") == "1"
 
     # ---- plumbing -----------------------------------------------------------------------------------------
     def plan(self, N, H, W, device, train, in_channels=1):
