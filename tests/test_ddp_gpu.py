@@ -92,3 +92,34 @@ def test_data_parallel_equals_chunked_single_gpu():
         e_full = net(x)
     assert torch.equal(e_dp, e_one), float((e_dp - e_one).abs().max())
     assert float((e_dp - e_full).abs().max()) < 1e-5
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_modules_on_a_second_gpu_without_set_device():
+    """libb2s launches on the current device; the entry points make the input's device current themselves
+    (a model on cuda:1 called while cuda:0 is current must not launch on cuda:0)."""
+    import torch
+    import b200seg  # noqa: F401
+    from b200seg.models.model import UNet
+    from b200seg.models.mod import ResUNet
+    from b200seg.models.loss import BCEDiceLoss
+    from b200seg.models.metrics import SegMetrics
+    from b200seg.synth import synth_batch
+    assert torch.cuda.current_device() == 0
+    x, t = synth_batch(2, 32, 32, seed=3)
+    for make in (UNet, lambda: ResUNet(depth=3)):
+        outs = []
+        for dev in ("cuda:0", "cuda:1"):
+            torch.manual_seed(42)
+            net = make().to(dev).train()
+            lg = net(x.to(dev))
+            loss = BCEDiceLoss()(lg, t.to(dev))
+            loss.backward()
+            m = SegMetrics(dev)
+            m.update(lg.detach(), t.to(dev))
+            torch.cuda.synchronize(dev)
+            g = next(p.grad for p in net.parameters() if p.grad is not None)
+            outs.append((lg.detach().cpu(), float(loss), g.cpu(), m.compute()["iou"]))
+        assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+        assert torch.equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
+    assert torch.cuda.current_device() == 0

@@ -12,6 +12,7 @@ from .. import ops
 
 class _SegLossFunction(torch.autograd.Function):
     @staticmethod
+    @ops.on_device_of_input
     def forward(ctx, logits, targets, cfg):
         if not logits.is_cuda:
             raise RuntimeError("b200seg losses run on CUDA (sm_100a) only; there is no CPU fallback")
@@ -30,6 +31,7 @@ class _SegLossFunction(torch.autograd.Function):
         return out[0].clone()
 
     @staticmethod
+    @ops.on_device_of_input
     def backward(ctx, grad_out):
         lg, tg, sums, out = ctx.saved_tensors
         dl = torch.empty_like(lg)

@@ -16,6 +16,7 @@ class SegMetrics:
     def reset(self):
         self.counters.zero_()
 
+    @ops.on_device_of_input
     def update(self, logits, targets):
         if not logits.is_cuda:
             raise RuntimeError("b200seg metrics run on CUDA (sm_100a) only; there is no CPU fallback")

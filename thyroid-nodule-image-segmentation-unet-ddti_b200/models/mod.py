@@ -125,6 +125,7 @@ class UNet(nn.Module, _PackMixin):
         x = _conv_bn(x, None, blk[0], blk[1], self.training, 1, weight=w0)
         return _conv_bn(x, None, blk[3], blk[4], self.training, 1)
 
+    @VF.ops.on_device_of_input
     def forward(self, x):
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             raise RuntimeError(f"expected input [N,{self.in_channels},H,W], got {tuple(x.shape)}")
@@ -195,6 +196,7 @@ class ResUNet(nn.Module, _PackMixin):
         self.final_conv = nn.Conv2d(base_filters, out_channels, 1)
         _check_channels(in_channels, base_filters)
 
+    @VF.ops.on_device_of_input
     def forward(self, x):
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             raise RuntimeError(f"expected input [N,{self.in_channels},H,W], got {tuple(x.shape)}")
@@ -308,6 +310,7 @@ class AttentionUNet(nn.Module, _PackMixin):
         x = _conv_bn(x, None, blk[0], blk[1], self.training, 1, weight=w0)
         return _conv_bn(x, None, blk[3], blk[4], self.training, 1)
 
+    @VF.ops.on_device_of_input
     def forward(self, x):
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             raise RuntimeError(f"expected input [N,{self.in_channels},H,W], got {tuple(x.shape)}")

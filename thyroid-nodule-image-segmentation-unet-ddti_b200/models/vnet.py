@@ -204,10 +204,12 @@ class ImprovedVNet(nn.Module):
             d = self.dec_blocks[blk].forward_nhwc(d)
         return self.dec_se_final.forward_nhwc(d)
 
+    @VF.ops.on_device_of_input
     def forward(self, x):
         return VF.Head.apply(self._trunk(x), self.final_conv.weight, self.final_conv.bias)
 
     @torch.no_grad()
+    @VF.ops.on_device_of_input
     def predict_mask(self, x):
         """Inference entry (utils/trainer.py:216-217): (logits, uint8 mask) with mask = sigmoid(logits) > 0.5 fused
         into the head kernel."""

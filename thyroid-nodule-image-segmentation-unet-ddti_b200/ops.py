@@ -1,6 +1,7 @@
 """Tensor-level wrappers over the C ABI (include/b2s.h). PyTorch supplies device memory and streams only; every
 computation below is a libb2s kernel. Activations are NHWC bf16 `Act` views (a channel slice of a buffer)."""
 import ctypes
+import functools
 
 import torch
 
@@ -29,6 +30,19 @@ def _timed(name, kind, work, fn, nbytes=None):
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def on_device_of_input(fn):
+    """Decorator for entry points (module forward, autograd Function forward / backward): runs the body with the CUDA
+    device of the first tensor argument current. libb2s launches on the CURRENT device's current stream and never
+    calls cudaSetDevice, so a model on cuda:1 called while cuda:0 is current would otherwise launch on the wrong GPU."""
+    @functools.wraps(fn)
+    def wrapper(self, x, *args, **kwargs):
+        if isinstance(x, torch.Tensor) and x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):
+                return fn(self, x, *args, **kwargs)
+        return fn(self, x, *args, **kwargs)
+    return wrapper
 
 
 def _p(t):
