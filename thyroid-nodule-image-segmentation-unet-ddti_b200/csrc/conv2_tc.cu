@@ -37,12 +37,44 @@ struct Conv2Cfg {
   static constexpr int kBarOffset = kStagingOffset + 2 * kATileBytes;
   static constexpr int kNumBars = 2 * STAGES + 2 * STAGES_A + 2 * kSets;
   static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;
-  static constexpr int kTotal = kTmemPtrOffset + 16;
+  static constexpr int kBiasOffset = kTmemPtrOffset + 16;            // BLOCK_N floats: the CTA's bias columns
+  static constexpr int kTotal = kBiasOffset + BLOCK_N * 4;
   static constexpr int kDynBytes = kTotal + 1024;  // slack for manual 1024-B alignment
   static_assert(kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns");
   static_assert(kDynBytes <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA may use");
   static_assert(MT == 1 || MT == 2, "one or two M tiles per work item");
 };
+
+// Epilogue conversion of one 64-column sub-tile row: accumulators (+bias) (ReLU) (eval-mode BatchNorm affine) -> 32
+// packed bf16 pairs. The three options are compile-time: with them as run-time tests inside the unrolled loop the
+// sub-tile cost 737 issued instructions per warp (ncu source page: 100 LDC, 96 predicated LDG, 142 IMAD, 64 FSEL ...),
+// and one warp owns 32 rows, so a GEMM with a short K loop (the transposed-conv forward: 2 k-iterations per item) was
+// bound by its epilogue warps' issue rate (3 600 clk per item with or without the stores, HBM- or L2-resident alike).
+// Same arithmetic in the same order as before: bit-identical results.
+template <bool BIAS, bool RELU, bool POST>
+__device__ __forceinline__ void epi_convert(const uint32_t (&v0)[32], const uint32_t (&v1)[32], uint32_t (&packed)[32],
+                                            const float* bias_s, const float* __restrict__ post_scale,
+                                            const float* __restrict__ post_shift) {
+#pragma unroll
+  for (int j2 = 0; j2 < 16; ++j2) {
+    float a0 = __uint_as_float(j2 < 8 ? v0[4 * j2] : v1[4 * j2 - 32]);
+    float b0 = __uint_as_float(j2 < 8 ? v0[4 * j2 + 1] : v1[4 * j2 - 31]);
+    float a1 = __uint_as_float(j2 < 8 ? v0[4 * j2 + 2] : v1[4 * j2 - 30]);
+    float b1 = __uint_as_float(j2 < 8 ? v0[4 * j2 + 3] : v1[4 * j2 - 29]);
+    if (BIAS) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias_s + 4 * j2);   // shared memory, broadcast
+      a0 += bb.x; b0 += bb.y; a1 += bb.z; b1 += bb.w;
+    }
+    if (RELU) { a0 = fmaxf(a0, 0.f); b0 = fmaxf(b0, 0.f); a1 = fmaxf(a1, 0.f); b1 = fmaxf(b1, 0.f); }
+    if (POST) {
+      const float4 ps = __ldg(reinterpret_cast<const float4*>(post_scale) + j2);
+      const float4 pt = __ldg(reinterpret_cast<const float4*>(post_shift) + j2);
+      a0 = fmaf(a0, ps.x, pt.x); b0 = fmaf(b0, ps.y, pt.y); a1 = fmaf(a1, ps.z, pt.z); b1 = fmaf(b1, ps.w, pt.w);
+    }
+    packed[2 * j2] = pack_bf16x2(a0, b0);
+    packed[2 * j2 + 1] = pack_bf16x2(a1, b1);
+  }
+}
 
 // Row-shifted operands: the tensor core applies the SWIZZLE_128B XOR to the absolute shared-memory address bits, the
 // same function TMA used when it wrote the 1024-B aligned row slots, so a descriptor may start at any 128-byte pixel
@@ -271,6 +303,14 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float st_acc[BLOCK_N / 64][4];
 #pragma unroll
     for (int s = 0; s < BLOCK_N / 64; ++s) st_acc[s][0] = st_acc[s][1] = st_acc[s][2] = st_acc[s][3] = 0.f;
+    // this CTA's bias columns, once, in shared memory (a column's bias index is its position inside the (a,b)
+    // sub-block for the transposed-conv forward); both epilogue groups fill and then meet on named barrier 3
+    float* bias_smem = reinterpret_cast<float*>(smem + L::kBiasOffset);
+    const int emode = (p.bias != nullptr ? 1 : 0) | (do_relu ? 2 : 0) | (p.post_scale != nullptr ? 4 : 0);
+    if (p.bias != nullptr) {
+      for (int c = threadIdx.x - 96; c < BLOCK_N; c += 256) bias_smem[c] = __ldg(p.bias + (ncol0 + c) % p.cout_sub);
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+    }
 
     for (int i = (MT == 2 ? 0 : g); i < my_items; i += (MT == 2 ? 1 : 2)) {
       const int item = mgroup + i * num_mgroups;
@@ -323,24 +363,24 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int col_base = ncol0 + s * 64;
         const int bias_base = col_base % p.cout_sub;
         uint32_t packed[32];
+        {
+          const float* bs = bias_smem + s * 64;
+          const float* ps = p.post_scale + bias_base;
+          const float* pt = p.post_shift + bias_base;
+          switch (emode) {
+            case 0: epi_convert<false, false, false>(v0, v1, packed, bs, ps, pt); break;
+            case 1: epi_convert<true, false, false>(v0, v1, packed, bs, ps, pt); break;
+            case 2: epi_convert<false, true, false>(v0, v1, packed, bs, ps, pt); break;
+            case 3: epi_convert<true, true, false>(v0, v1, packed, bs, ps, pt); break;
+            case 4: epi_convert<false, false, true>(v0, v1, packed, bs, ps, pt); break;
+            case 5: epi_convert<true, false, true>(v0, v1, packed, bs, ps, pt); break;
+            case 6: epi_convert<false, true, true>(v0, v1, packed, bs, ps, pt); break;
+            default: epi_convert<true, true, true>(v0, v1, packed, bs, ps, pt); break;
+          }
+          if (!HALO && !valid) {      // rows of a ragged tile that lie outside the image store zeros
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(j < 16 ? v0[2 * j] : v1[2 * j - 32]);
-          float b = __uint_as_float(j < 16 ? v0[2 * j + 1] : v1[2 * j - 31]);
-          if (p.bias != nullptr) {
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + bias_base) + j);
-            a += bb.x;
-            b += bb.y;
+            for (int j = 0; j < 32; ++j) packed[j] = 0u;
           }
-          if (do_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          if (p.post_scale != nullptr) {
-            const float2 ps = __ldg(reinterpret_cast<const float2*>(p.post_scale + bias_base) + j);
-            const float2 pt = __ldg(reinterpret_cast<const float2*>(p.post_shift + bias_base) + j);
-            a = fmaf(a, ps.x, pt.x);
-            b = fmaf(b, ps.y, pt.y);
-          }
-          if (!valid) { a = 0.f; b = 0.f; }
-          packed[j] = pack_bf16x2(a, b);
         }
         // r words of this warp's 32 rows for the lane's column pair (one coalesced 128-byte row per load), issued now
         // so that their L2 latency overlaps the staging write below
@@ -393,7 +433,7 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        if (row == 0) {
+        if (row == 0 && !(p.flags & (1 << 30))) {
           if (p.out_mode == OUT_4D) {
             tma_store_4d(&tmOut, stage_buf, col_base, w0, h0, n0);
           } else if (p.out_mode == OUT_SUB_5D) {   // one fixed sub-lattice of the 2x larger output

@@ -48,6 +48,8 @@ def main():
     ap.add_argument("--tile-n", type=int, default=0)
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--json", default="")
+    ap.add_argument("--no-bias", action="store_true")
+    ap.add_argument("--nbuf", type=int, default=0, help="number of rotating buffer sets (1: L2-resident operands)")
     ap.add_argument("--concat", action="store_true", help="convT: write into the first half of a concat buffer")
     ap.add_argument("--convt-mode", default="fwd", choices=["fwd", "dgrad", "wgrad"])
     args = ap.parse_args()
@@ -59,7 +61,7 @@ def main():
             continue
         torch.manual_seed(0)
         in_bytes = B * h * h * cin * 2
-        nbuf = max(2, min(8, int(200e6 // max(in_bytes, 1)) + 1))
+        nbuf = args.nbuf if args.nbuf > 0 else max(2, min(8, int(200e6 // max(in_bytes, 1)) + 1))
         xs = [ops.Act(torch.randn((B, h, h, cin), device=DEV).to(torch.bfloat16)) for _ in range(nbuf)]
         if kind == "fwd":
             w = torch.randn((cout, cin, 3, 3), device=DEV) * 0.05
@@ -98,7 +100,7 @@ def main():
                 dw = torch.empty((cin, cout, 2, 2), dtype=torch.float32, device=DEV)
                 fn = lambda i: ops.convt_wgrad(xs[i % nbuf], ys[i % nbuf], ws, dw, tile_n=args.tile_n, splits=args.splits)
             else:
-                fn = lambda i: ops.convt_fwd(xs[i % nbuf], wf, bias, ys[i % nbuf], tile_n=args.tile_n)
+                fn = lambda i: ops.convt_fwd(xs[i % nbuf], wf, None if args.no_bias else bias, ys[i % nbuf], tile_n=args.tile_n)
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
