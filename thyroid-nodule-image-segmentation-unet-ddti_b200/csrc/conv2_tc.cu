@@ -63,7 +63,8 @@ __device__ __forceinline__ void epi_convert(const uint32_t (&v0)[32], const uint
     float b1 = __uint_as_float(j2 < 8 ? v0[4 * j2 + 3] : v1[4 * j2 - 29]);
     if (BIAS) {
       const float4 bb = *reinterpret_cast<const float4*>(bias_s + 4 * j2);   // shared memory, broadcast
-      a0 += bb.x; b0 += bb.y; a1 += bb.z; b1 += bb.w;
+      f2_unpack(f2_add(f2_pack(a0, b0), f2_pack(bb.x, bb.y)), a0, b0);
+      f2_unpack(f2_add(f2_pack(a1, b1), f2_pack(bb.z, bb.w)), a1, b1);
     }
     if (RELU) { a0 = fmaxf(a0, 0.f); b0 = fmaxf(b0, 0.f); a1 = fmaxf(a1, 0.f); b1 = fmaxf(b1, 0.f); }
     if (POST) {
@@ -406,29 +407,21 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (do_stats) {
           // column sums over this warp's own 32 rows, taken from the bf16-rounded values actually stored
           __syncwarp();
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          // packed fp32 pairs (FADD2 / FFMA2: one issue slot for both columns, bit-identical per lane)
+          f32x2 s01 = f2_pack(0.f, 0.f), q01 = f2_pack(0.f, 0.f);
           const int chunk = lane >> 2, within = (lane & 3) * 4;
-          if (RED) {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const int rr = q * 32 + r;
-              const uint32_t u =
-                  *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
-              const float x0 = bf16_lo(u), x1 = bf16_hi(u);
-              s0 += x0; s1 += x1;
-              q0 = fmaf(x0, bf16_lo(rw[RED ? r : 0]), q0); q1 = fmaf(x1, bf16_hi(rw[RED ? r : 0]), q1);
-            }
-          } else {
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const int rr = q * 32 + r;
-              const uint32_t u =
-                  *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
-              const float x0 = bf16_lo(u), x1 = bf16_hi(u);
-              s0 += x0; s1 += x1;
-              q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
-            }
+          for (int r = 0; r < 32; ++r) {
+            const int rr = q * 32 + r;
+            const uint32_t u =
+                *reinterpret_cast<const uint32_t*>(stage_buf + rr * 128 + ((chunk ^ (rr & 7)) << 4) + within);
+            const f32x2 x01 = f2_pack(bf16_lo(u), bf16_hi(u));
+            s01 = f2_add(s01, x01);
+            q01 = f2_fma(x01, RED ? f2_pack(bf16_lo(rw[RED ? r : 0]), bf16_hi(rw[RED ? r : 0])) : x01, q01);
           }
+          float s0, s1, q0, q1;
+          f2_unpack(s01, s0, s1);
+          f2_unpack(q01, q0, q1);
           st_acc[s][0] += s0; st_acc[s][1] += s1; st_acc[s][2] += q0; st_acc[s][3] += q1;
         }
         fence_proxy_async_smem();
