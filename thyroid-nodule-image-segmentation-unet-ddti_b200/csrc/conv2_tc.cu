@@ -426,7 +426,7 @@ conv2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        if (row == 0 && !(p.flags & (1 << 30))) {
+        if (row == 0) {
           if (p.out_mode == OUT_4D) {
             tma_store_4d(&tmOut, stage_buf, col_base, w0, h0, n0);
           } else if (p.out_mode == OUT_SUB_5D) {   // one fixed sub-lattice of the 2x larger output

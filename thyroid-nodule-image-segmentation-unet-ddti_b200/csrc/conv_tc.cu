@@ -10,7 +10,6 @@
 // conv_tc_kernel is persistent (one CTA per SM, 320 threads): warp0 = TMA producer (+TMEM alloc), warp1 = MMA
 // issuer, warps 2-5 / 6-9 = two epilogue groups draining the two TMEM accumulators alternately.
 // wgrad_tc_kernel runs one long split-K tile per CTA (192 threads, one epilogue group).
-#include <stdlib.h>
 #include "conv_common.cuh"
 
 namespace b2s {
@@ -685,7 +684,7 @@ extern "C" int b2s_convt2x2_fwd(const void* x, int x_cstride, const void* w_pack
   p.W = Wi; p.H = Hm; p.N = 1;
   p.num_taps = 1; p.k_chunks = Cin / 64;
   p.n_total = 4 * Cout; p.cout_sub = Cout;
-  p.flags = getenv("B2S_DEBUG_SKIP_STORE") ? (1 << 30) : 0; p.bias = bias; p.stats = nullptr;
+  p.flags = 0; p.bias = bias; p.stats = nullptr;
   CUtensorMap tmA, tmB, tmOut;
   int rc;
   if ((rc = make_act_map4(&tmA, x, Cin, Wi, Hm, 1, x_cstride, pl.bw, pl.bh, pl.bn))) return rc;
