@@ -173,9 +173,9 @@ def family_of(name, kind, nbytes):
 
 
 FAMILY_NOTE = {
-    "conv3x3 fwd+dgrad @256^2 (N<=128 tiles)": "tensor pipe 44 % active under ncu (N=64 MMAs shared-memory-read bound)",
+    "conv3x3 fwd+dgrad @256^2 (N<=128 tiles)": "tensor pipe 46 % active under ncu (N=64 MMAs: shared-memory bandwidth, 668 KB per item)",
     "conv3x3 fwd+dgrad @128^2": "tensor pipe; halo kernel",
-    "conv3x3 fwd+dgrad deep (<=64^2)": "tensor pipe 83 % active under ncu (tile-pair kernel, L2 -> smem)",
+    "conv3x3 fwd+dgrad deep (<=64^2)": "tensor pipe 85 % active under ncu (tile-pair kernel, L2 -> smem)",
     "wgrad3x3 @256^2/128^2 (halo kernel)": "tensor pipe 50-59 % active under ncu",
     "wgrad3x3 deep (<=64^2)": "tensor pipe 91 % active under ncu",
     "convT high-res (HBM-bound, GB/s)": "dram throughput (arithmetic intensity 85-171 FLOP/B < ridge)",
@@ -487,16 +487,17 @@ def run_b200(args):
                              "limited_by": FAMILY_NOTE.get(name, "")})
     traffic, traffic_note = None, "no ncu capture found under profiles/"
     try:   # DRAM bytes of one launch from the committed `ncu --set full` capture (profiles/)
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_conv_full.json")) as f:
-            for d in json.load(f):
-                if d["kernel"].startswith("void conv2_tc_kernel<256, 2, 0, 3, 0>"):
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_conv_full.json")) as f:
+            for d in json.load(f)["kernels"]:
+                if d["kernel"].startswith("void conv2_tc_kernel<256, 2, 0, 3, 0"):
                     def to_bytes(v):
                         x, u = v.split()
                         return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
                     traffic = to_bytes(d["dram_read"]) + to_bytes(d["dram_write"])
                     traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one conv2_tc_kernel<256,2,0,3,0> launch "
-                                    "(512->512 @32x32, batch 64; algorithmic 2 x 67.1 MB activations + 4.7 MB weights), "
-                                    "profiles/r1_ncu_conv_full.json")
+                                    "(512->512 @32x32, batch 64; algorithmic 2 x 67.1 MB activations + 4.7 MB weights; the "
+                                    "input is partly L2-resident), profiles/r2_ncu_conv_full.json; the 64->64 @256x256 launch "
+                                    "moves 537 + 491 MB = its algorithmic bytes")
                     break
     except (OSError, KeyError, ValueError):
         pass
