@@ -150,6 +150,29 @@ def test_backward_given_forward_state(net, ref_params, B, S):
     assert not bad, bad
 
 
+def test_backward_with_fused_bn_reduction_matches_two_pass(net, ref_params):
+    """The optional fused BatchNorm-backward reduction (engine.fuse_bn_reduce, off by default: DESIGN.md §9) gives the
+    same gradients as the two-pass scheme up to the summation order of the per-channel sums."""
+    net.load_state_dict(ref_params, strict=True)
+    net.train()
+    x, t = O.synth_batch(2, 64, 128, seed=79)
+    x, t = x.to(DEV), t.to(DEV)
+    grads = []
+    try:
+        for fuse in (False, True):
+            net._engine.fuse_bn_reduce = fuse
+            net.load_state_dict(ref_params, strict=True)
+            net.zero_grad(set_to_none=True)
+            from b200seg.models.loss import BCEDiceLoss
+            BCEDiceLoss()(net(x), t).backward()
+            grads.append({k: p.grad.detach().clone() for k, p in net.named_parameters()})
+    finally:
+        net._engine.fuse_bn_reduce = False
+    torch.cuda.synchronize()
+    for k in grads[0]:
+        assert rel_l2(grads[1][k], grads[0][k]) < 2e-3, (k, rel_l2(grads[1][k], grads[0][k]))
+
+
 def test_eval_logits_and_mask(net, unet_golden, ref_params):
     """Inference path (utils/trainer.py:216-217): eval-mode BN with the reference's post-step running stats."""
     A = unet_golden["A"]
