@@ -375,3 +375,48 @@ def test_vnet_multichannel_input():
     for k, p in net.named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape and bool(torch.isfinite(p.grad).all()), k
     assert float(dict(net.named_parameters())["enc_blocks.0.0.convs.0.weight"].grad.abs().sum()) > 0
+
+
+def test_vnet_train_step_vs_oracle_at_128_on_device():
+    """Whole V-Net train step at 2 x 128 x 128 (8 x 8 pixels at the deepest level instead of 2 x 2, so the BatchNorm
+    statistics there average over 128 values instead of 8) against the oracle evaluated in fp64 ON THE GPU — the same
+    device-agnostic restatement, with autograd over its elementary ops for the gradients. Dropout off."""
+    import json
+    import b200seg  # noqa: F401
+    from b200seg.models.vnet import ImprovedVNet
+    from b200seg.models.loss import BCEDiceLoss
+    torch.manual_seed(42)
+    net = ImprovedVNet(dropout_rate=0.0)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV).train()
+    x, t = O.synth_batch(2, 128, 128, seed=4242)
+    logits = net(x.to(DEV))
+    loss = BCEDiceLoss()(logits, t.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    P = {k: (v.double().to(DEV).requires_grad_(True) if v.is_floating_point() and "running" not in k
+             else v.clone().to(DEV)) for k, v in sd.items()}
+    lq = V.vnet_forward(P, x.double().to(DEV), train=True, q=O.bf16_round)
+    Lq = O.seg_loss(lq.detach(), t.double().to(DEV))
+    d = (logits.detach().double() - lq.detach()).abs()
+    lq.backward(Lq["dlogits"])
+    stats = {}
+    for k, p in net.named_parameters():
+        ref = P[k].grad
+        if ref is None or (".convs." in k and k.endswith(".bias")):
+            continue      # conv bias in front of train-mode BatchNorm: the exact gradient is zero
+        g = p.grad.double()
+        stats[k] = (float((g - ref).norm() / ref.norm().clamp_min(1e-30)),
+                    float((g * ref).sum() / (g.norm() * ref.norm()).clamp_min(1e-30)))
+    rels, coss = sorted(v[0] for v in stats.values()), sorted(v[1] for v in stats.values())
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/vnet_parity_128.json", "w") as f:
+        json.dump({"logits_mean_abs_vs_bf16_oracle": float(d.mean()), "loss": float(loss), "loss_oracle_bf16": float(Lq["total"]),
+                   "rel_l2_median": rels[len(rels) // 2], "rel_l2_max": rels[-1], "cos_median": coss[len(coss) // 2],
+                   "cos_min": coss[0], "grads_rel_l2_cos": stats}, f, indent=1)
+    assert float(d.mean()) < 1e-2, float(d.mean())
+    assert abs(float(loss) - float(Lq["total"])) < 2e-3
+    assert len(stats) > 250
+    assert rels[len(rels) // 2] < 0.45 and coss[len(coss) // 2] > 0.9, (rels[len(rels) // 2], coss[len(coss) // 2])
+    for k in ("final_conv.weight", "dec_blocks.3.convs.1.weight", "up9.weight"):
+        assert stats[k][0] < 0.08, (k, stats[k])
