@@ -59,6 +59,11 @@ def _match_size(x, skip):
 
 
 class _PackMixin:
+    def invalidate_packed(self):
+        """Forces the next forward to re-pack the bf16 GEMM operands (needed only after a weight update that bypasses
+        torch's version counters, e.g. `p.data.copy_()` or an external kernel)."""
+        self._pack_key = None
+
     def _pack_all_weights(self):
         """bf16 operands of every tensor-core conv weight, refreshed in a few launches when a parameter changed"""
         from .. import ops

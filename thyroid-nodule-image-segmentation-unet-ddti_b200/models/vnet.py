@@ -144,6 +144,11 @@ class ImprovedVNet(nn.Module):
             raise NotImplementedError("the B200 path implements 1 <= in_channels <= 64 and base_num_filters a multiple "
                                       "of 64")
 
+    def invalidate_packed(self):
+        """Forces the next forward to re-pack the bf16 GEMM operands (needed only after a weight update that bypasses
+        torch's version counters, e.g. `p.data.copy_()` or an external kernel)."""
+        self._pack_key = None
+
     def _pack_all_weights(self):
         """bf16 GEMM operands of every tensor-core conv / transposed-conv weight, refreshed in a few launches whenever
         a parameter changed (optimizer step, load_state_dict, .to()); registered for the autograd nodes."""
