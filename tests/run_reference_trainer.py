@@ -28,7 +28,7 @@ if os.environ.get("B2S_HANG_DUMP"):          # debugging aid: dump every thread'
 def install_plot_stubs():
     """matplotlib / skimage / pytz / seaborn are not installed; Trainer.test()'s plotting tail (trainer.py:268-299)
     needs callable stand-ins, the rest only needs the imports to succeed."""
-    from oracle import ref_env
+    from tools import ref_env
     ref_env.stub_missing_modules()
     plt = sys.modules["matplotlib.pyplot"]
     if not hasattr(plt, "subplots"):
@@ -75,7 +75,7 @@ def main():
     from b200seg.models.metrics import SegMetrics
     from b200seg.synth import synth_batch
     from b200seg import _lib
-    from oracle import ref_env
+    from tools import ref_env
 
     install_plot_stubs()
     ref = ref_env.ref_root()

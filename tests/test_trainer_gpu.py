@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _have_reference():
     sys.path.insert(0, ROOT)
-    from oracle import ref_env
+    from tools import ref_env
     return ref_env.ref_root() is not None
 
 

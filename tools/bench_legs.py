@@ -7,8 +7,8 @@
   cpu_reference_leg the reference's own modules on the host cores, BASELINE configs[0] exactly (fp32, B=4 @256^2,
                     forward + BCE + Dice + backward, no optimiser step)
 
-Everything that touches the reference goes through oracle/ref_env.py (test infrastructure); the product package is
-never routed through it.
+Everything that touches the reference goes through tools/ref_env.py (a loader; measurement infrastructure); the product
+package is never routed through it, and oracle/ is imported only by the CPU fallback of cpu_reference_times.
 """
 import os
 import sys
@@ -135,7 +135,7 @@ def vnet_leg(dev, world, rank, local, batch=16, size=512, steps=5, warmup=3):
 
 def _reference_unet():
     """(UNet class, DiceLoss class, kind): the reference's own modules when staged, else None."""
-    from oracle import ref_env
+    from tools import ref_env
     if ref_env.ref_root() is None:
         return None
     return ref_env.load_ref_module("models/model.py").UNet, ref_env.load_ref_module("models/loss.py").DiceLoss

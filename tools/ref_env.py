@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE (not product code): locating and importing the UNMODIFIED reference.
+"""MEASUREMENT / TEST INFRASTRUCTURE (not product code): locating and importing the UNMODIFIED reference.
 
 The reference tree is found at ``baseline/_ref/`` (git-ignored copy staged by tools/stage_reference.py; it travels to
-the GPU box) or at ``/root/reference`` (build container only). Used by tests/, ``__graft_entry__`` and by
-``bench.py``'s reference / baseline legs — never by the product package.
+the GPU box) or at ``/root/reference`` (build container only). Used by tests/ and by ``bench.py``'s reference /
+baseline legs (tools/bench_legs.py) — never by the product package. It is a loader only: nothing of ``oracle/`` is
+involved when the reference's own modules are timed.
 """
 import importlib
 import importlib.util
